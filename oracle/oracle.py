@@ -1,0 +1,425 @@
+"""TEST INFRASTRUCTURE — ctypes front end of the CPU oracle (oracle/mbavo_oracle.c) and, where it was built,
+of oracle/_ref (the reference's own header arithmetic), plus the numpy restatement of the host-side
+Levenberg–Marquardt loop of the reference tracker.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs import this module.
+
+Restated host logic (reference file:line):
+    solve_normal_equation             src/ba_tracker/solve_normal_equation.h:10-35   (JacobiSVD / LDLT -> numpy)
+    computeTrustRegionStep            src/ba_tracker/blur_aware_direct_tracker.cpp:799-831
+    Plus_t / Plus_R                   src/core/common/Spline.h:307-330  (Sophus SO3::exp == quaternion exp map)
+    optimizePyramidLevel / LM loop    src/ba_tracker/blur_aware_direct_tracker.cpp:590-637, 885-924
+    detectOutliersAndUploadToGpu      src/ba_tracker/blur_aware_direct_tracker.cpp:639-699
+    LevenbergMarquardtStrategy        src/ba_tracker/levenberg_marquardt_strategy.cpp:9-44
+    TrustRegionStepEvaluator          src/ba_tracker/trust_region_step_evaluator.cpp:45-126
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_u8p = C.POINTER(C.c_ubyte)
+_fp = C.POINTER(C.c_float)
+
+
+def _ptr(a, typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def build(verbose: bool = False) -> None:
+    """Compile oracle/libmbavo_oracle.so, and oracle/_ref/* when the reference tree is present."""
+    r = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+
+
+class _Lib:
+    """Common call surface of libmbavo_oracle.so (prefix mbavo_oracle_) and _ref/libmbavo_ref.so (mbavo_ref_)."""
+
+    def __init__(self, path: str, prefix: str):
+        self.path = path
+        self.prefix = prefix
+        self.lib = C.CDLL(path)
+        self.kind = "reference" if prefix == "mbavo_ref_" else "port"
+
+    def fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def num_threads(self) -> int:
+        return int(self.fn("num_threads")())
+
+    def set_num_threads(self, n: int) -> None:
+        self.fn("set_num_threads")(C.c_int(n))
+
+    # -- stage 1
+    def virtual_poses(self, N, cap, exp, k, t0, dt, knots_t, knots_R, jac=True):
+        cap = np.ascontiguousarray(cap, dtype=np.float64)
+        exp = np.ascontiguousarray(exp, dtype=np.float64)
+        kt = np.ascontiguousarray(knots_t, dtype=np.float64)
+        kR = np.ascontiguousarray(knots_R, dtype=np.float64)
+        F = cap.shape[0]
+        poses = np.zeros((F, N, 7))
+        Jt = np.zeros((F, N, 3, 3 * k)) if jac else None
+        JR = np.zeros((F, N, 4, 3 * k)) if jac else None
+        seg = np.zeros((F, N), dtype=np.int32)
+        f = self.fn("virtual_poses")
+        f.restype = C.c_int
+        if self.prefix == "mbavo_ref_":
+            rc = f(C.c_int(N), C.c_int(F), _ptr(cap, _dp), _ptr(exp, _dp), C.c_int(k), C.c_double(t0), C.c_double(dt),
+                   _ptr(kt, _dp), _ptr(kR, _dp), _ptr(poses, _dp), _ptr(Jt, _dp), _ptr(JR, _dp), _ptr(seg, _ip))
+        else:
+            rc = f(C.c_int(N), C.c_int(F), _ptr(cap, _dp), _ptr(exp, _dp), C.c_int(k), C.c_double(t0), C.c_double(dt),
+                   _ptr(kt, _dp), _ptr(kR, _dp), C.c_int(kt.shape[0]), _ptr(poses, _dp), _ptr(seg, _ip),
+                   _ptr(Jt, _dp), _ptr(JR, _dp))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}virtual_poses rc={rc}")
+        return poses, seg, Jt, JR
+
+    # -- stage 2
+    def local_patches(self, N, poses, xy, z, fx, fy, cx, cy):
+        F = poses.shape[0]
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        P = xy.shape[0]
+        out = np.zeros((F, P, 2))
+        f = self.fn("local_patches")
+        f.restype = C.c_int
+        f(C.c_int(N), C.c_int(F), _ptr(np.ascontiguousarray(poses), _dp), _ptr(xy, _dp), _ptr(z, _dp), C.c_int(P),
+          C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), _ptr(out, _dp))
+        return out
+
+    # -- whole evaluation
+    def evaluate(self, prob, level: int, knots_t=None, knots_R=None, flags=None, num_bad: int = 0,
+                 with_hessian: bool = True, want_patch_costs: bool = True):
+        lv = prob.levels[level]
+        kt = np.ascontiguousarray(prob.knots_t if knots_t is None else knots_t, dtype=np.float64)
+        kR = np.ascontiguousarray(prob.knots_R if knots_R is None else knots_R, dtype=np.float64)
+        n = kt.shape[0]
+        F = prob.F
+        cur = (C.c_void_p * F)(*[c.ctypes.data for c in lv.cur_I])
+        cost = C.c_double(0)
+        H = np.zeros((6 * n, 6 * n)) if with_hessian else None
+        g = np.zeros(6 * n) if with_hessian else None
+        pc = np.zeros((F, lv.P)) if want_patch_costs else None
+        fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+        seg = np.ascontiguousarray(prob.seg_start, dtype=np.int32)
+        f = self.fn("evaluate")
+        f.restype = C.c_int
+        common = [C.c_int(lv.N), C.c_int(F), _ptr(lv.ref_I, _u8p), _ptr(lv.ref_dIxy, _fp), cur,
+                  _ptr(np.ascontiguousarray(prob.cap), _dp), _ptr(np.ascontiguousarray(prob.exp), _dp),
+                  _ptr(lv.xy, _dp), _ptr(lv.z, _dp), C.c_int(lv.P), _ptr(lv.pattern, _ip), C.c_int(lv.S),
+                  _ptr(fl, _u8p), C.c_int(num_bad), C.c_double(lv.fx), C.c_double(lv.fy), C.c_double(lv.cx),
+                  C.c_double(lv.cy), C.c_int(lv.H), C.c_int(lv.W), C.c_int(prob.k), C.c_double(prob.t0),
+                  C.c_double(prob.dt), _ptr(kt, _dp), _ptr(kR, _dp)]
+        if self.prefix == "mbavo_ref_":
+            rc = f(*common, _ptr(seg, _ip), C.c_int(n), C.c_double(prob.huber_a), C.byref(cost), _ptr(H, _dp),
+                   _ptr(g, _dp), _ptr(pc, _dp))
+        else:
+            rc = f(*common, C.c_int(n), C.c_double(prob.huber_a), C.byref(cost), _ptr(H, _dp), _ptr(g, _dp),
+                   _ptr(pc, _dp))
+        if rc != 0:
+            raise RuntimeError(f"{self.prefix}evaluate rc={rc}")
+        return cost.value, H, g, pc
+
+
+class OracleLib(_Lib):
+    def __init__(self):
+        path = os.path.join(_HERE, "libmbavo_oracle.so")
+        if not os.path.exists(path):
+            build()
+        super().__init__(path, "mbavo_oracle_")
+
+    def pixel_residuals(self, prob, level: int, knots_t=None, knots_R=None, with_jacobian=True):
+        lv = prob.levels[level]
+        kt = np.ascontiguousarray(prob.knots_t if knots_t is None else knots_t, dtype=np.float64)
+        kR = np.ascontiguousarray(prob.knots_R if knots_R is None else knots_R, dtype=np.float64)
+        n = kt.shape[0]
+        F = prob.F
+        cur = (C.c_void_p * F)(*[c.ctypes.data for c in lv.cur_I])
+        r = np.zeros((F, lv.P, lv.S))
+        cap_cols = 6 * n
+        J = np.zeros((F, lv.P, lv.S, cap_cols)) if with_jacobian else None
+        kmin, NK = C.c_int(0), C.c_int(0)
+        f = self.fn("pixel_residuals")
+        f.restype = C.c_int
+        # the C side writes rows of width 6*NK contiguously; allocate for the worst case and reshape afterwards
+        rc = f(C.c_int(lv.N), C.c_int(F), _ptr(lv.ref_I, _u8p), _ptr(lv.ref_dIxy, _fp), cur,
+               _ptr(np.ascontiguousarray(prob.cap), _dp), _ptr(np.ascontiguousarray(prob.exp), _dp), _ptr(lv.xy, _dp),
+               _ptr(lv.z, _dp), C.c_int(lv.P), _ptr(lv.pattern, _ip), C.c_int(lv.S), C.c_double(lv.fx),
+               C.c_double(lv.fy), C.c_double(lv.cx), C.c_double(lv.cy), C.c_int(lv.H), C.c_int(lv.W), C.c_int(prob.k),
+               C.c_double(prob.t0), C.c_double(prob.dt), _ptr(kt, _dp), _ptr(kR, _dp), C.c_int(n), C.byref(kmin),
+               C.byref(NK), _ptr(r, _dp), _ptr(J, _dp), C.c_int(cap_cols))
+        if rc != 0:
+            raise RuntimeError(f"mbavo_oracle_pixel_residuals rc={rc}")
+        if J is not None:
+            d = 6 * NK.value
+            J = J.reshape(-1)[: F * lv.P * lv.S * d].reshape(F, lv.P, lv.S, d)
+        return r, J, kmin.value, NK.value
+
+    def pixel_intensity(self, I, dIxy, pose, D, fx, fy, cx, cy, X, Y, want_J=True):
+        H, W = I.shape
+        inten = C.c_double(0)
+        J = np.zeros(7) if want_J else None
+        f = self.fn("pixel_intensity")
+        f.restype = C.c_int
+        ok = f(_ptr(I, _u8p), _ptr(dIxy, _fp), C.c_int(H), C.c_int(W), _ptr(np.ascontiguousarray(pose, dtype=np.float64), _dp),
+               C.c_double(D), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), C.c_double(X),
+               C.c_double(Y), C.byref(inten), _ptr(J, _dp))
+        return bool(ok), inten.value, J
+
+    def image_gradient(self, I):
+        H, W = I.shape
+        out = np.zeros((H, W, 2), dtype=np.float32)
+        self.fn("image_gradient")(_ptr(np.ascontiguousarray(I), _u8p), C.c_int(H), C.c_int(W), _ptr(out, _fp))
+        return out
+
+    def pyramid_down(self, I):
+        H, W = I.shape
+        out = np.zeros((H // 2, W // 2), dtype=np.uint8)
+        self.fn("pyramid_down")(_ptr(np.ascontiguousarray(I), _u8p), C.c_int(H), C.c_int(W), _ptr(out, _u8p))
+        return out
+
+    def synthesize_blurred(self, I, D, fx, fy, cx, cy, k, t0, dt, knots_t, knots_R, cap, exp, num_samples):
+        H, W = I.shape
+        kt = np.ascontiguousarray(knots_t, dtype=np.float64)
+        kR = np.ascontiguousarray(knots_R, dtype=np.float64)
+        out = np.zeros((H, W), dtype=np.uint8)
+        f = self.fn("synthesize_blurred")
+        f.restype = C.c_int
+        rc = f(_ptr(np.ascontiguousarray(I), _u8p), C.c_int(H), C.c_int(W), C.c_double(D), C.c_double(fx),
+               C.c_double(fy), C.c_double(cx), C.c_double(cy), C.c_int(k), C.c_double(t0), C.c_double(dt),
+               _ptr(kt, _dp), _ptr(kR, _dp), C.c_int(kt.shape[0]), C.c_double(cap), C.c_double(exp),
+               C.c_int(num_samples), _ptr(out, _u8p))
+        if rc != 0:
+            raise RuntimeError(f"synthesize_blurred rc={rc}")
+        return out
+
+
+class RefLib(_Lib):
+    """oracle/_ref/libmbavo_ref.so — present only where it was built from /root/reference (or shipped prebuilt)."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libmbavo_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        super().__init__(path, "mbavo_ref_")
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(os.path.join(_HERE, "_ref", "libmbavo_ref.so"))
+
+    def synthesize_blurred(self, I, D, fx, fy, cx, cy, k, t0, dt, knots_t, knots_R, cap, exp, num_samples):
+        H, W = I.shape
+        kt = np.ascontiguousarray(knots_t, dtype=np.float64)
+        kR = np.ascontiguousarray(knots_R, dtype=np.float64)
+        out = np.zeros((H, W), dtype=np.uint8)
+        f = self.fn("synthesize_blurred")
+        f.restype = C.c_int
+        f(_ptr(np.ascontiguousarray(I), _u8p), C.c_int(H), C.c_int(W), C.c_double(D), C.c_double(fx), C.c_double(fy),
+          C.c_double(cx), C.c_double(cy), C.c_int(k), C.c_double(t0), C.c_double(dt), _ptr(kt, _dp), _ptr(kR, _dp),
+          C.c_double(cap), C.c_double(exp), C.c_int(num_samples), _ptr(out, _u8p))
+        return out
+
+
+def best_cpu_lib() -> _Lib:
+    """oracle/_ref when present (kind 'reference'), else the C port (kind 'port')."""
+    return RefLib() if RefLib.available() else OracleLib()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-side solver logic (numpy)
+# ---------------------------------------------------------------------------------------------------------
+def q_mul(a, b):
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def so3_exp_quat(w):
+    """Sophus::SO3d::exp(w).unit_quaternion() (Spline.h:302, 326): half-angle exponential map, Taylor branch for
+    tiny angles (Sophus uses theta^2 < eps^2 with the same series)."""
+    w = np.asarray(w, dtype=np.float64)
+    t2 = float(w @ w)
+    if t2 < 1e-20:
+        t4 = t2 * t2
+        return np.concatenate([(0.5 - t2 / 48.0 + t4 / 3840.0) * w, [1.0 - t2 / 8.0 + t4 / 384.0]])
+    t = np.sqrt(t2)
+    return np.concatenate([np.sin(0.5 * t) / t * w, [np.cos(0.5 * t)]])
+
+
+def plus(knots_t, knots_R, delta):
+    """Spline.h:307-330: candidate = knots [+] delta, delta = [dt_0..dt_{n-1}, dw_0..dw_{n-1}]; no re-normalisation."""
+    n = knots_t.shape[0]
+    ct = knots_t + delta[: 3 * n].reshape(n, 3)
+    cR = np.stack([q_mul(knots_R[i], so3_exp_quat(delta[3 * n + 3 * i: 3 * n + 3 * i + 3])) for i in range(n)])
+    return ct, cR
+
+
+def solve_normal_equation(A, b, solver_type: str = "SVD_JACOBI"):
+    """solve_normal_equation.h:16-34: x = -A^-1 b by SVD (type 0) or LDL^T (type 1)."""
+    if solver_type == "SVD_JACOBI":
+        U, s, Vt = np.linalg.svd(A)
+        # Eigen's JacobiSVD::solve drops singular values below eps * max(rows, cols) * s_max
+        tol = np.finfo(np.float64).eps * max(A.shape) * s[0]
+        inv = np.where(s > tol, 1.0 / np.where(s > tol, s, 1.0), 0.0)
+        x = Vt.T @ (inv * (U.T @ b))
+    elif solver_type == "LDLT":
+        x = np.linalg.solve(A, b)
+    else:
+        raise ValueError(solver_type)
+    return -x
+
+
+def trust_region_step(H, g, radius, solver_type="SVD_JACOBI"):
+    """tracker.cpp:799-831.  H is damped IN PLACE (the damping compounds over rejected steps)."""
+    d = np.diag_indices_from(H)
+    H[d] += H[d] * (1.0 / radius)
+    step = solve_normal_equation(H, g, solver_type)
+    model = -(g @ step + 0.5 * step @ H @ step)
+    return step, model
+
+
+class LMStrategy:
+    """levenberg_marquardt_strategy.cpp:9-44"""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.radius, self.min_radius, self.max_radius, self.decrease = 1e4, 10.0, 1e32, 2.0
+
+    def accepted(self, q):
+        self.radius = self.radius / max(1.0 / 3.0, 1.0 - (2.0 * q - 1.0) ** 3)
+        self.radius = max(min(self.max_radius, self.radius), self.min_radius)
+        self.decrease = 2.0
+
+    def rejected(self):
+        self.radius = self.radius / self.decrease
+        self.radius = max(min(self.max_radius, self.radius), self.min_radius)
+        self.decrease *= 2.0
+
+
+class StepEvaluator:
+    """trust_region_step_evaluator.cpp:45-126 (Ceres' non-monotonic step evaluator)."""
+
+    def __init__(self, max_nonmonotonic=5):
+        self.max_nonmonotonic = max_nonmonotonic
+
+    def reset(self, c):
+        self.minimum = self.current = self.reference = self.candidate = c
+        self.acc_ref = self.acc_cand = 0.0
+        self.n_nonmono = 0
+
+    def quality(self, cost, model):
+        if cost >= np.finfo(np.float64).max:
+            return np.finfo(np.float64).min
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rel = (self.current - cost) / model
+            hist = (self.reference - cost) / (self.acc_ref + model)
+        return max(rel, hist)
+
+    def accepted(self, cost, model):
+        self.current = cost
+        self.acc_cand += model
+        self.acc_ref += model
+        if self.current < self.minimum:
+            self.minimum = self.current
+            self.n_nonmono = 0
+            self.candidate = self.current
+            self.acc_cand = 0.0
+        else:
+            self.n_nonmono += 1
+            if self.current > self.candidate:
+                self.candidate = self.current
+                self.acc_cand = 0.0
+        if self.n_nonmono == self.max_nonmonotonic:
+            self.reference = self.candidate
+            self.acc_ref = self.acc_cand
+
+
+def detect_outliers(patch_costs, flags, k_sigma):
+    """tracker.cpp:639-699: mean / variance over patches with cost >= 1e-8, flag every patch (zero-cost ones included)
+    with |c - mu| > k_sigma * sqrtf(var).  Flags are sticky; returns the number flagged in THIS call."""
+    c = np.asarray(patch_costs, dtype=np.float64).reshape(-1)
+    sel = c[c >= 1e-8]
+    mu = sel.sum() / sel.size
+    var = ((sel - mu) ** 2).sum() / sel.size
+    bad = np.abs(c - mu) > k_sigma * float(np.sqrt(np.float32(var)))
+    flags[bad] = 1
+    return int(bad.sum())
+
+
+@dataclass
+class LMTrace:
+    costs: List[float] = field(default_factory=list)        # evaluation-point cost after every accepted step
+    decisions: List[str] = field(default_factory=list)      # 'A' accepted, 'R' rejected, 'I' invalid step
+    qualities: List[float] = field(default_factory=list)
+    first_step: Optional[np.ndarray] = None
+    num_iterations: int = 0
+    num_bad: int = 0
+
+
+def optimize_level(lib: _Lib, prob, level: int, knots_t, knots_R, max_num_iterations=50, min_step_quality=0.5,
+                   min_abs_cost_decrease=1e-3, solver_type="SVD_JACOBI", max_nonmonotonic=5):
+    """optimizePyramidLevel (tracker.cpp:590-637) with evaluate() supplied by `lib`."""
+    lv = prob.levels[level]
+    kt, kR = knots_t.copy(), knots_R.copy()
+    flags = np.zeros(lv.P, dtype=np.uint8)
+    num_bad = 0
+    trace = LMTrace()
+    eval_cost, H, g, _ = lib.evaluate(prob, level, kt, kR, flags, num_bad, with_hessian=True)
+    lm, ev = LMStrategy(), StepEvaluator(max_nonmonotonic)
+    ev.reset(eval_cost)
+    trace.costs.append(eval_cost)
+    it, abs_decrease = 0, 1e10
+    while True:
+        it += 1                                     # finalizeIterationAndCheckIfMinimizerCanContinue, :910-924
+        if it > max_num_iterations or abs_decrease < min_abs_cost_decrease:
+            break
+        step, model = trust_region_step(H, g, lm.radius, solver_type)
+        if trace.first_step is None:
+            trace.first_step = step.copy()
+        if model < 0:
+            lm.rejected()
+            trace.decisions.append("I")
+            continue
+        ct, cR = plus(kt, kR, step)
+        cand_cost, _, _, pc = lib.evaluate(prob, level, ct, cR, flags, num_bad, with_hessian=False)
+        abs_decrease = eval_cost - cand_cost
+        q = ev.quality(cand_cost, model)
+        trace.qualities.append(q)
+        if q > min_step_quality and cand_cost < eval_cost:
+            num_bad = detect_outliers(pc, flags, prob.max_chi_square_error)
+            kt, kR = ct, cR
+            eval_cost, H, g, _ = lib.evaluate(prob, level, kt, kR, flags, num_bad, with_hessian=True)
+            lm.accepted(q)
+            ev.accepted(eval_cost, model)
+            trace.decisions.append("A")
+            trace.costs.append(eval_cost)
+        else:
+            lm.rejected()
+            trace.decisions.append("R")
+    trace.num_iterations = it - 1
+    trace.num_bad = num_bad
+    return kt, kR, trace
+
+
+def optimize_trajectory(lib: _Lib, prob, **kw):
+    """optimizeTrajectory (tracker.cpp:544-588): coarse -> fine over the pyramid."""
+    kt, kR = prob.knots_t.copy(), prob.knots_R.copy()
+    traces = []
+    for level in reversed(range(len(prob.levels))):
+        kt, kR, tr = optimize_level(lib, prob, level, kt, kR, **kw)
+        traces.append(tr)
+    return kt, kR, traces
