@@ -1,0 +1,219 @@
+/*
+ * mbavo.h — C-ABI of the B200-native blur-aware photometric tracking hot path (MBA-VO src/ba_tracker).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference tree, ethliup/MBA-VO @ 161e1af).  All functions return
+ * 0 on success and a negative MBAVO_E* code otherwise, never throw and never exit; mbavo_last_error() returns a
+ * thread-local description of the last failure.
+ *
+ * A context (mbavo_ctx) owns all device scratch, pinned result buffers, one CUDA stream and the captured CUDA
+ * graphs of one logical tracker on one GPU; it is not thread-safe.  Calls are blocking like the reference's
+ * (results are valid on return) unless named *_async.
+ *
+ * Unknown ordering everywhere: [dt_0 .. dt_{n-1}, dw_0 .. dw_{n-1}] (merge_hessian_gradient_cost.cpp:52-62), rotations
+ * updated on the right, R_j <- R_j Exp(dw_j) (Spline.h:317-330); quaternions are stored (x, y, z, w).
+ */
+#ifndef MBAVO_H_
+#define MBAVO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBAVO_VERSION 100
+
+#define MBAVO_OK 0
+#define MBAVO_EINVAL (-1)      /* bad argument / unsupported configuration */
+#define MBAVO_ECUDA (-2)       /* a CUDA runtime / driver call failed */
+#define MBAVO_ERANGE (-3)      /* an exposure sample needs a control knot outside [0, n_knots) */
+#define MBAVO_ECAPACITY (-4)   /* exceeds the limits the context was created with */
+#define MBAVO_ENOTREADY (-5)   /* level / frame times not set */
+#define MBAVO_ENCCL (-6)       /* NCCL unavailable or failed */
+
+#define MBAVO_MAX_LEVELS 8     /* BlurAwareDirectTrackerOptions per-level arrays, blur_aware_direct_tracker.h:17-31 */
+#define MBAVO_MAX_FRAMES 16
+#define MBAVO_MAX_KNOT_WINDOW 8 /* control knots touched by one evaluation (k .. k + segments - 1) */
+
+typedef struct mbavo_ctx mbavo_ctx;
+
+/* Capacity of a context — initialize_shared_cuda_storages(max_num_frames, max_num_virtual_poses_per_frame,
+ * max_num_keypoints, max_patch_size, max_num_ctrl_knots, spline_deg_k, storages), spline_update_step.cpp:9-58 */
+typedef struct mbavo_limits
+{
+    int device;                          /* CUDA device ordinal, -1 = current */
+    int max_num_frames;                  /* <= MBAVO_MAX_FRAMES */
+    int max_num_virtual_poses_per_frame; /* exposure samples N per frame */
+    int max_num_keypoints;               /* host-map points per level */
+    int max_patch_size;                  /* residual-pattern pixels per point */
+    int max_num_ctrl_knots;
+} mbavo_limits;
+
+#define MBAVO_MEM_HOST 0
+#define MBAVO_MEM_DEVICE 1
+
+/* One pyramid level of inputs — what BlurAwareDirectTracker::uploadDataToGpu(int) (blur_aware_direct_tracker.cpp:721-751)
+ * and the image arguments of evaluate_cost_hessian_gradient (spline_update_step.h:62-68) provide.
+ * With MBAVO_MEM_HOST the data is copied (borrowed for the call); with MBAVO_MEM_DEVICE the pointers are device
+ * pointers that must stay valid until the level is replaced. */
+typedef struct mbavo_level
+{
+    int mem;                       /* MBAVO_MEM_HOST or MBAVO_MEM_DEVICE, applies to every pointer below */
+    int H, W;                      /* im_size_HW of this level */
+    double fx, fy, cx, cy;         /* intrinsics of this level (already divided by 2^level, tracker.cpp:766-776) */
+    const unsigned char *ref_I;    /* keyframe image, H*W row-major            (cuda_ref_img) */
+    const float *ref_dIxy;         /* keyframe gradient, H*W*2 interleaved      (cuda_dIxy_ref) */
+    const unsigned char *const *cur_I; /* n_frames live images, H*W each; the ARRAY is always in host memory   */
+    int n_frames;
+    const void *keypoint_xy;       /* num_keypoints records holding (x, y) as two doubles */
+    int keypoint_xy_stride;        /* bytes between records: 16 for packed double2, 24 for Core::Vector2d */
+    int keypoint_xy_offset;        /* byte offset of x inside a record: 0, or 8 for Core::Vector2d (Vector.h:12-16) */
+    const double *keypoint_z;      /* num_keypoints depths                       (cuda_keypoint_depth_z) */
+    int num_keypoints;
+    const int *pattern_xy;         /* patch_size (dx, dy) pairs                  (cuda_local_patch_pattern_xy) */
+    int patch_size;
+    int num_virtual_poses;         /* exposure samples per frame at this level   (num_virtual_poses_per_frame[level]) */
+    /* Optional, device memory, for callers that own the reference's storages (host/spline_update_step.h): */
+    unsigned char *ext_outlier_flags; /* use this flag array (cuda_keypoints_outlier_flags) instead of the context's own;
+                                         it is NOT cleared by mbavo_set_level */
+    double *ext_patch_cost;        /* write patch costs here (cuda_patch_cost_gradient_hessian_tR) ... */
+    int ext_patch_cost_stride;     /* ... with this stride in doubles ((6k+1)(6k+2)/2 in the reference) */
+} mbavo_level;
+
+/* Spline state of one evaluation — the spline arguments of evaluate_cost_hessian_gradient (spline_update_step.h:69-75)
+ * plus the knot data the tracker memcpy's into the storages first (blur_aware_direct_tracker.cpp:755-763, 838-846). */
+typedef struct mbavo_spline
+{
+    int spline_deg_k;              /* control knots per segment: 2 (linear) or 4 (cubic cumulative B-spline) */
+    double start_time;             /* spline_start_time */
+    double sample_dt;              /* spline_sample_dt (knot spacing) */
+    int num_ctrl_knots;            /* n */
+    const double *knots_t;         /* host, 3n */
+    const double *knots_R;         /* host, 4n, quaternion (x, y, z, w) */
+} mbavo_spline;
+
+const char *mbavo_last_error(void);
+int mbavo_version(void);
+
+/* initialize_shared_cuda_storages / free_shared_cuda_storages (spline_update_step.cpp:9-95) */
+int mbavo_create(const mbavo_limits *limits, mbavo_ctx **out);
+int mbavo_destroy(mbavo_ctx *ctx);
+
+/* Run all work of this context on `stream` (a cudaStream_t) instead of the context's own stream; NULL restores it.
+ * Used to share a stream with a caller that owns device memory (e.g. a torch stream). */
+int mbavo_set_stream(mbavo_ctx *ctx, void *stream);
+
+/* BlurAwareDirectTracker::uploadDataToGpu() (blur_aware_direct_tracker.cpp:701-719): capture / exposure time per frame */
+int mbavo_set_frame_times(mbavo_ctx *ctx, int n_frames, const double *cap_time, const double *exp_time);
+
+/* BlurAwareDirectTracker::uploadDataToGpu(int pyra_level) (blur_aware_direct_tracker.cpp:721-751).  Also clears the
+ * level's outlier flags (optimizePyramidLevel, :600-601). */
+int mbavo_set_level(mbavo_ctx *ctx, int level, const mbavo_level *data);
+
+/* Outlier flags of a level: cuda_keypoints_outlier_flags + num_bad_keypoints (spline_update_step.h:25-26).
+ * flags == NULL clears them.  flags is a host array of num_keypoints bytes (1 = outlier). */
+int mbavo_set_outliers(mbavo_ctx *ctx, int level, const unsigned char *flags, int num_bad_keypoints);
+
+/* num_bad_keypoints alone (CudaSharedStorages::num_bad_keypoints, read at spline_update_step.cpp:116) when the flag
+ * array is owned by the caller (ext_outlier_flags). */
+int mbavo_set_num_bad(mbavo_ctx *ctx, int level, int num_bad_keypoints);
+
+/* evaluate_cost_hessian_gradient (spline_update_step.h:60-87, .cpp:97-349).
+ *   total_cost : sum of Huber costs / num_residuals
+ *   hessian    : 6n x 6n doubles (symmetric, so row- and column-major coincide) or NULL for the cost-only branch
+ *   gradient   : 6n doubles, NULL iff hessian is NULL
+ * Unlike the reference, each exposure sample's Jacobian goes to that sample's own spline segment, so an exposure
+ * window may straddle control knots (up to MBAVO_MAX_KNOT_WINDOW knots touched per evaluation). */
+int mbavo_evaluate(mbavo_ctx *ctx, int level, const mbavo_spline *spline, double huber_a, double *total_cost,
+                   double *hessian, double *gradient);
+
+/* Per-patch costs of the LAST evaluation of `level`: element 0 of every patch vector of
+ * cuda_patch_cost_gradient_hessian_tR (read by detectOutliersAndUploadToGpu, blur_aware_direct_tracker.cpp:646-657).
+ * out: host, n_frames * num_keypoints doubles. */
+int mbavo_patch_costs(mbavo_ctx *ctx, int level, double *out);
+
+/* detectOutliersAndUploadToGpu (blur_aware_direct_tracker.cpp:639-699) without the P*E D2H: statistics and flags are
+ * computed on the device from the last evaluation's patch costs.  Flags are sticky; *num_bad_keypoints receives the
+ * number of patches flagged by THIS call and becomes the level's num_bad_keypoints. */
+int mbavo_detect_outliers(mbavo_ctx *ctx, int level, double max_chi_square_error, int *num_bad_keypoints);
+
+/* ---- device-resident variants (multi-GPU plumbing, CUDA-graph friendly) ------------------------------------ */
+
+/* Length of the packed window vector [cost, g(6 NK), triu(H) row-major] for a knot window of NK knots */
+int mbavo_packed_len(int knot_window);
+
+/* Launch one evaluation without synchronising: the packed window vector of THIS context's points (already scaled by
+ * 1 / num_residuals_global) is left in device memory at `packed_dev` (>= mbavo_packed_len(NK) doubles) on the
+ * context's stream.  kmin / knot_window receive the window.  num_residuals_global <= 0 means "this context's own".
+ * Summing the vectors of all shards (e.g. ncclAllReduce) and calling mbavo_unpack gives the global result. */
+int mbavo_evaluate_async(mbavo_ctx *ctx, int level, const mbavo_spline *spline, double huber_a, int with_hessian,
+                         long long num_residuals_global, double *packed_dev, int *kmin, int *knot_window);
+
+/* merge_hessian_gradient_cost (merge_hessian_gradient_cost.cpp:8-87): scatter a packed window vector (host memory)
+ * into the dense H (6n x 6n), g (6n) and cost.  hessian/gradient NULL => cost only. */
+int mbavo_unpack(const double *packed_host, int kmin, int knot_window, int num_ctrl_knots, double *total_cost,
+                 double *hessian, double *gradient);
+
+/* ---- host-side solver, mirrors of the tracker's LM loop ------------------ */
+
+#define MBAVO_SOLVER_SVD_JACOBI 0 /* solve_normal_equation.h:18-23 */
+#define MBAVO_SOLVER_LDLT 1       /* solve_normal_equation.h:24-28 */
+
+/* computeTrustRegionStep (blur_aware_direct_tracker.cpp:799-831): damps the diagonal of `hessian` IN PLACE by
+ * (1 + 1/radius), step = -H^-1 g, *model_cost_change = -(g^T s + s^T H s / 2).  dim = 6n. */
+int mbavo_trust_region_step(double *hessian, const double *gradient, int dim, double radius, int solver_type,
+                            double *step, double *model_cost_change);
+
+/* SplineSE3::Plus_t / Plus_R (src/core/common/Spline.h:307-330): candidate = knots [+] step */
+int mbavo_spline_plus(int num_ctrl_knots, const double *knots_t, const double *knots_R, const double *step,
+                      double *cand_t, double *cand_R);
+
+typedef struct mbavo_lm_options
+{
+    int max_num_iterations;                 /* 50   blur_aware_direct_tracker.h:39 */
+    double min_step_quality;                /* 0.5  :40 */
+    double min_abs_cost_decrease;           /* 1e-3 :41 */
+    int solver_type;                        /* MBAVO_SOLVER_SVD_JACOBI  :42 */
+    int max_consecutive_nonmonotonic_steps; /* 5    :38 */
+    double max_chi_square_error;            /* outlier threshold in sigmas :55 */
+    double huber_a;                         /* huber_k :35 */
+} mbavo_lm_options;
+
+typedef struct mbavo_lm_summary
+{
+    int num_iterations;
+    int num_accepted;
+    int num_rejected;
+    int num_invalid;
+    int num_evaluations;     /* device evaluations issued (Hessian + cost-only) */
+    int num_bad_keypoints;
+    double initial_cost;
+    double final_cost;
+    double first_step[6 * 16]; /* first trust-region step (parity quantity) */
+    char decisions[64];        /* 'A' accepted / 'R' rejected / 'I' invalid, NUL-terminated */
+} mbavo_lm_summary;
+
+void mbavo_lm_default_options(mbavo_lm_options *opt);
+
+/* BlurAwareDirectTracker::optimizePyramidLevel (blur_aware_direct_tracker.cpp:590-637): the whole LM loop of one
+ * level.  knots_t (3n) / knots_R (4n) are updated in place with the committed control knots. */
+int mbavo_optimize_level(mbavo_ctx *ctx, int level, int spline_deg_k, double start_time, double sample_dt,
+                         int num_ctrl_knots, double *knots_t, double *knots_R, const mbavo_lm_options *opt,
+                         mbavo_lm_summary *summary);
+
+/* ---- introspection for benchmarks ---------------------------------------------------------------------------- */
+
+/* Number of kernels this library has launched on behalf of ctx since creation (graph replays counted per node) */
+long long mbavo_kernel_launches(const mbavo_ctx *ctx);
+
+/* Device time in milliseconds of the tracking kernel of the last mbavo_evaluate* call on `level` (CUDA events
+ * recorded around that kernel on the context's stream); < 0 if timing is disabled. */
+int mbavo_enable_kernel_timing(mbavo_ctx *ctx, int enable);
+float mbavo_last_kernel_ms(mbavo_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBAVO_H_ */

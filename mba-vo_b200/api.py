@@ -1,0 +1,305 @@
+"""ctypes binding of include/mbavo.h — one Python method per C entry point, no logic of its own."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+MAX_LEVELS = 8
+MAX_FRAMES = 16
+MEM_HOST, MEM_DEVICE = 0, 1
+SOLVER_SVD_JACOBI, SOLVER_LDLT = 0, 1
+
+# every symbol include/mbavo.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "mbavo_last_error", "mbavo_version", "mbavo_create", "mbavo_destroy", "mbavo_set_stream", "mbavo_set_frame_times",
+    "mbavo_set_level", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
+    "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
+    "mbavo_spline_plus", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
+    "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms",
+]
+
+
+class MbavoError(RuntimeError):
+    pass
+
+
+class _Limits(C.Structure):
+    _fields_ = [("device", C.c_int), ("max_num_frames", C.c_int), ("max_num_virtual_poses_per_frame", C.c_int),
+                ("max_num_keypoints", C.c_int), ("max_patch_size", C.c_int), ("max_num_ctrl_knots", C.c_int)]
+
+
+class _Level(C.Structure):
+    _fields_ = [("mem", C.c_int), ("H", C.c_int), ("W", C.c_int), ("fx", C.c_double), ("fy", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double), ("ref_I", C.c_void_p), ("ref_dIxy", C.c_void_p),
+                ("cur_I", C.POINTER(C.c_void_p)), ("n_frames", C.c_int), ("keypoint_xy", C.c_void_p),
+                ("keypoint_xy_stride", C.c_int), ("keypoint_xy_offset", C.c_int), ("keypoint_z", C.c_void_p),
+                ("num_keypoints", C.c_int), ("pattern_xy", C.c_void_p), ("patch_size", C.c_int),
+                ("num_virtual_poses", C.c_int), ("ext_outlier_flags", C.c_void_p), ("ext_patch_cost", C.c_void_p),
+                ("ext_patch_cost_stride", C.c_int)]
+
+
+class _Spline(C.Structure):
+    _fields_ = [("spline_deg_k", C.c_int), ("start_time", C.c_double), ("sample_dt", C.c_double),
+                ("num_ctrl_knots", C.c_int), ("knots_t", C.POINTER(C.c_double)), ("knots_R", C.POINTER(C.c_double))]
+
+
+class _LmOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int), ("min_step_quality", C.c_double), ("min_abs_cost_decrease", C.c_double),
+                ("solver_type", C.c_int), ("max_consecutive_nonmonotonic_steps", C.c_int),
+                ("max_chi_square_error", C.c_double), ("huber_a", C.c_double)]
+
+
+class _LmSummary(C.Structure):
+    _fields_ = [("num_iterations", C.c_int), ("num_accepted", C.c_int), ("num_rejected", C.c_int),
+                ("num_invalid", C.c_int), ("num_evaluations", C.c_int), ("num_bad_keypoints", C.c_int),
+                ("initial_cost", C.c_double), ("final_cost", C.c_double), ("first_step", C.c_double * 96),
+                ("decisions", C.c_char * 64)]
+
+
+@dataclass
+class Limits:
+    max_num_frames: int = 1
+    max_num_virtual_poses_per_frame: int = 64
+    max_num_keypoints: int = 500
+    max_patch_size: int = 128
+    max_num_ctrl_knots: int = 16
+    device: int = -1
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "lib", "libmbavo_b200.so")
+
+
+_LIB = None
+
+
+def load_library() -> C.CDLL:
+    """Load lib/libmbavo_b200.so.  Raises if it has not been built — there is no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise MbavoError(f"{path} is missing: build it with `make -C mba-vo_b200` or __graft_entry__.build()")
+    lib = C.CDLL(path)
+    lib.mbavo_last_error.restype = C.c_char_p
+    lib.mbavo_kernel_launches.restype = C.c_longlong
+    lib.mbavo_last_kernel_ms.restype = C.c_float
+    for name in EXPORTED_SYMBOLS:
+        getattr(lib, name)
+    _LIB = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Context:
+    """One mbavo_ctx: one logical tracker on one GPU."""
+
+    def __init__(self, limits: Limits):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        lim = _Limits(limits.device, limits.max_num_frames, limits.max_num_virtual_poses_per_frame,
+                      limits.max_num_keypoints, limits.max_patch_size, limits.max_num_ctrl_knots)
+        self._check(self.lib.mbavo_create(C.byref(lim), C.byref(self._h)))
+        self.limits = limits
+        self._keep = {}
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise MbavoError(f"mbavo error {rc}: {self.lib.mbavo_last_error().decode()}")
+
+    def close(self):
+        if self._h:
+            self.lib.mbavo_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- inputs -------------------------------------------------------------------------------------------
+    def set_stream(self, stream_ptr: Optional[int]):
+        self._check(self.lib.mbavo_set_stream(self._h, C.c_void_p(stream_ptr or 0)))
+
+    def set_frame_times(self, cap: Sequence[float], exp: Sequence[float]):
+        cap = np.ascontiguousarray(cap, dtype=np.float64)
+        exp = np.ascontiguousarray(exp, dtype=np.float64)
+        self._check(self.lib.mbavo_set_frame_times(self._h, C.c_int(cap.shape[0]), _dp(cap), _dp(exp)))
+
+    def set_level(self, level: int, lv, point_slice: Optional[slice] = None):
+        """Upload one synth.Level (host memory).  point_slice selects a shard of the host-map points."""
+        xy = lv.xy if point_slice is None else np.ascontiguousarray(lv.xy[point_slice])
+        z = lv.z if point_slice is None else np.ascontiguousarray(lv.z[point_slice])
+        F = len(lv.cur_I)
+        cur = (C.c_void_p * F)(*[c.ctypes.data for c in lv.cur_I])
+        d = _Level(MEM_HOST, lv.H, lv.W, lv.fx, lv.fy, lv.cx, lv.cy, lv.ref_I.ctypes.data, lv.ref_dIxy.ctypes.data, cur, F,
+                   xy.ctypes.data, 16, 0, z.ctypes.data, xy.shape[0], lv.pattern.ctypes.data, lv.S, lv.N, None, None, 0)
+        self._check(self.lib.mbavo_set_level(self._h, C.c_int(level), C.byref(d)))
+
+    def set_level_device(self, level: int, H, W, fx, fy, cx, cy, ref_I_ptr, ref_dIxy_ptr, cur_I_ptrs, xy_ptr, xy_stride,
+                         xy_offset, z_ptr, P, pattern_ptr, S, N, ext_flags_ptr=None, ext_patch_cost_ptr=None,
+                         ext_patch_cost_stride=0):
+        """Device-pointer variant (pointers stay owned by the caller, e.g. torch tensors)."""
+        F = len(cur_I_ptrs)
+        cur = (C.c_void_p * F)(*cur_I_ptrs)
+        d = _Level(MEM_DEVICE, H, W, fx, fy, cx, cy, ref_I_ptr, ref_dIxy_ptr, cur, F, xy_ptr, xy_stride, xy_offset, z_ptr, P,
+                   pattern_ptr, S, N, ext_flags_ptr, ext_patch_cost_ptr, ext_patch_cost_stride)
+        self._check(self.lib.mbavo_set_level(self._h, C.c_int(level), C.byref(d)))
+
+    def set_outliers(self, level: int, flags: Optional[np.ndarray], num_bad: int = 0):
+        if flags is None:
+            self._check(self.lib.mbavo_set_outliers(self._h, C.c_int(level), None, C.c_int(0)))
+        else:
+            fl = np.ascontiguousarray(flags, dtype=np.uint8)
+            self._check(self.lib.mbavo_set_outliers(self._h, C.c_int(level), fl.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                                    C.c_int(num_bad)))
+
+    def set_num_bad(self, level: int, num_bad: int):
+        self._check(self.lib.mbavo_set_num_bad(self._h, C.c_int(level), C.c_int(num_bad)))
+
+    # -- evaluation ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _spline(k, t0, dt, knots_t, knots_R):
+        kt = np.ascontiguousarray(knots_t, dtype=np.float64).reshape(-1)
+        kR = np.ascontiguousarray(knots_R, dtype=np.float64).reshape(-1)
+        n = kt.shape[0] // 3
+        return _Spline(k, t0, dt, n, _dp(kt), _dp(kR)), kt, kR, n
+
+    def evaluate(self, level: int, k: int, t0: float, dt: float, knots_t, knots_R, huber_a: float,
+                 with_hessian: bool = True):
+        """mbavo_evaluate -> (cost, H, g); H, g are None for the cost-only branch."""
+        sp, kt, kR, n = self._spline(k, t0, dt, knots_t, knots_R)
+        cost = C.c_double(0)
+        if with_hessian:
+            H = np.zeros((6 * n, 6 * n))
+            g = np.zeros(6 * n)
+            self._check(self.lib.mbavo_evaluate(self._h, C.c_int(level), C.byref(sp), C.c_double(huber_a), C.byref(cost),
+                                                _dp(H), _dp(g)))
+            return cost.value, H, g
+        self._check(self.lib.mbavo_evaluate(self._h, C.c_int(level), C.byref(sp), C.c_double(huber_a), C.byref(cost), None,
+                                            None))
+        return cost.value, None, None
+
+    def evaluate_async(self, level: int, k, t0, dt, knots_t, knots_R, huber_a, with_hessian: bool,
+                       num_residuals_global: int, packed_dev_ptr: int):
+        """mbavo_evaluate_async -> (kmin, knot_window); the packed vector is left at packed_dev_ptr (device)."""
+        sp, kt, kR, n = self._spline(k, t0, dt, knots_t, knots_R)
+        kmin, nk = C.c_int(0), C.c_int(0)
+        self._check(self.lib.mbavo_evaluate_async(self._h, C.c_int(level), C.byref(sp), C.c_double(huber_a),
+                                                  C.c_int(1 if with_hessian else 0), C.c_longlong(num_residuals_global),
+                                                  C.c_void_p(packed_dev_ptr), C.byref(kmin), C.byref(nk)))
+        return kmin.value, nk.value
+
+    def packed_len(self, knot_window: int) -> int:
+        return int(self.lib.mbavo_packed_len(C.c_int(knot_window)))
+
+    def unpack(self, packed: np.ndarray, kmin: int, knot_window: int, n_knots: int, with_hessian: bool = True):
+        packed = np.ascontiguousarray(packed, dtype=np.float64)
+        cost = C.c_double(0)
+        H = np.zeros((6 * n_knots, 6 * n_knots)) if with_hessian else None
+        g = np.zeros(6 * n_knots) if with_hessian else None
+        self._check(self.lib.mbavo_unpack(_dp(packed), C.c_int(kmin), C.c_int(knot_window), C.c_int(n_knots), C.byref(cost),
+                                          _dp(H) if with_hessian else None, _dp(g) if with_hessian else None))
+        return cost.value, H, g
+
+    def patch_costs(self, level: int, n_frames: int, num_keypoints: int) -> np.ndarray:
+        out = np.zeros((n_frames, num_keypoints))
+        self._check(self.lib.mbavo_patch_costs(self._h, C.c_int(level), _dp(out)))
+        return out
+
+    def detect_outliers(self, level: int, max_chi_square_error: float) -> int:
+        nb = C.c_int(0)
+        self._check(self.lib.mbavo_detect_outliers(self._h, C.c_int(level), C.c_double(max_chi_square_error), C.byref(nb)))
+        return nb.value
+
+    # -- host-side solver -----------------------------------------------------------------------------------
+    def trust_region_step(self, H: np.ndarray, g: np.ndarray, radius: float, solver_type: int = SOLVER_SVD_JACOBI):
+        """Damps H in place (as the reference does) and returns (step, model_cost_change)."""
+        assert H.flags.c_contiguous and H.dtype == np.float64
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        step = np.zeros_like(g)
+        model = C.c_double(0)
+        self._check(self.lib.mbavo_trust_region_step(_dp(H), _dp(g), C.c_int(g.shape[0]), C.c_double(radius),
+                                                     C.c_int(solver_type), _dp(step), C.byref(model)))
+        return step, model.value
+
+    def spline_plus(self, knots_t, knots_R, step):
+        kt = np.ascontiguousarray(knots_t, dtype=np.float64)
+        kR = np.ascontiguousarray(knots_R, dtype=np.float64)
+        st = np.ascontiguousarray(step, dtype=np.float64)
+        n = kt.shape[0]
+        ct, cR = np.zeros_like(kt), np.zeros_like(kR)
+        self._check(self.lib.mbavo_spline_plus(C.c_int(n), _dp(kt), _dp(kR), _dp(st), _dp(ct), _dp(cR)))
+        return ct, cR
+
+    def optimize_level(self, level: int, k: int, t0: float, dt: float, knots_t, knots_R, huber_a: float = 10.0,
+                       max_chi_square_error: float = 3.0, solver_type: int = SOLVER_SVD_JACOBI, **overrides):
+        """mbavo_optimize_level -> (knots_t, knots_R, summary dict)."""
+        kt = np.array(knots_t, dtype=np.float64, order="C")
+        kR = np.array(knots_R, dtype=np.float64, order="C")
+        n = kt.shape[0]
+        opt = _LmOptions()
+        self.lib.mbavo_lm_default_options(C.byref(opt))
+        opt.huber_a, opt.max_chi_square_error, opt.solver_type = huber_a, max_chi_square_error, solver_type
+        for k_, v in overrides.items():
+            setattr(opt, k_, v)
+        summ = _LmSummary()
+        self._check(self.lib.mbavo_optimize_level(self._h, C.c_int(level), C.c_int(k), C.c_double(t0), C.c_double(dt),
+                                                  C.c_int(n), _dp(kt), _dp(kR), C.byref(opt), C.byref(summ)))
+        s = {f: getattr(summ, f) for f, _ in _LmSummary._fields_ if f not in ("first_step", "decisions")}
+        s["first_step"] = np.array(summ.first_step[: 6 * n])
+        s["decisions"] = summ.decisions.decode()
+        return kt, kR, s
+
+    # -- introspection ----------------------------------------------------------------------------------------
+    def kernel_launches(self) -> int:
+        return int(self.lib.mbavo_kernel_launches(self._h))
+
+    def enable_kernel_timing(self, on: bool):
+        self._check(self.lib.mbavo_enable_kernel_timing(self._h, C.c_int(1 if on else 0)))
+
+    def last_kernel_ms(self) -> float:
+        return float(self.lib.mbavo_last_kernel_ms(self._h))
+
+
+def limits_for(prob, n_frames: Optional[int] = None) -> Limits:
+    return Limits(max_num_frames=n_frames or prob.F,
+                  max_num_virtual_poses_per_frame=max(lv.N for lv in prob.levels),
+                  max_num_keypoints=max(lv.P for lv in prob.levels),
+                  max_patch_size=max(lv.S for lv in prob.levels),
+                  max_num_ctrl_knots=max(prob.n_knots, 2))
+
+
+def upload_problem(ctx: Context, prob) -> None:
+    ctx.set_frame_times(prob.cap, prob.exp)
+    for l, lv in enumerate(prob.levels):
+        ctx.set_level(l, lv)
+
+
+def optimize_trajectory(ctx: Context, prob, **kw):
+    """BlurAwareDirectTracker::optimizeTrajectory (blur_aware_direct_tracker.cpp:544-588): coarse -> fine over the
+    pyramid levels already uploaded into ctx."""
+    kt, kR = prob.knots_t.copy(), prob.knots_R.copy()
+    summaries: List[dict] = []
+    for level in reversed(range(len(prob.levels))):
+        kt, kR, s = ctx.optimize_level(level, prob.k, prob.t0, prob.dt, kt, kR, huber_a=prob.huber_a,
+                                       max_chi_square_error=prob.max_chi_square_error, **kw)
+        summaries.append(s)
+    return kt, kR, summaries

@@ -1,0 +1,764 @@
+// C-ABI of the hot path (include/mbavo.h): context, level storage, evaluation orchestration.
+// Host side of evaluate_cost_hessian_gradient (src/ba_tracker/spline_update_step.cpp:97-349) re-designed:
+//   reference: 2 blocking H2D + 5 launches each followed by cudaDeviceSynchronize + 1 blocking D2H per evaluation
+//   here:      1 async H2D (pinned staging block) + pose kernel + fused tracking kernel + 1 async D2H (pinned),
+//              one stream, one synchronisation at the end; the sequence is replayed as a CUDA graph.
+#include "../../include/mbavo.h"
+#include "mbavo_device.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <vector>
+
+namespace mbavo
+{
+    cudaError_t launch_pose_kernel(int K, const EvalStage *stage_dev, int total_samples, int with_jacobian, float *samples,
+                                   double *mid, int *seg_end, cudaStream_t stream);
+    cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, dim3 grid, size_t smem,
+                                    cudaStream_t stream, int *query_occupancy);
+    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, int N, int S, int TP);
+} // namespace mbavo
+
+using namespace mbavo;
+
+namespace
+{
+    thread_local char g_err[512] = "";
+
+    int fail(int code, const char *fmt, ...)
+    {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(g_err, sizeof g_err, fmt, ap);
+        va_end(ap);
+        return code;
+    }
+
+#define CUDA_TRY(expr)                                                                                      \
+    do                                                                                                      \
+    {                                                                                                       \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(MBAVO_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+    struct LevelStore
+    {
+        bool set = false;
+        bool owns = false;      // buffers below were allocated by us (MBAVO_MEM_HOST)
+        LevelDev dev{};         // what the kernel sees
+        // owned buffers
+        unsigned char *ref_I = nullptr;
+        float *ref_dIxy = nullptr;
+        unsigned char *cur_I[kMaxFrames] = {};
+        double *xy = nullptr, *z = nullptr;
+        size_t cap_pix = 0, cap_pts = 0; // capacities of the owned buffers (pixels per image, points)
+        int cap_frames = 0;
+        // always owned
+        int2 *pattern = nullptr;
+        unsigned char *flags = nullptr;
+        double *patch_cost = nullptr;
+        int num_bad = 0;
+        int last_eval_frames = 0;
+    };
+
+    struct GraphKey
+    {
+        int level, K, NK, with_h, N, F, P, S;
+        unsigned long long gen; // level generation (pointers may change on set_level)
+        bool operator<(const GraphKey &o) const
+        {
+            return std::tie(level, K, NK, with_h, N, F, P, S, gen) <
+                   std::tie(o.level, o.K, o.NK, o.with_h, o.N, o.F, o.P, o.S, o.gen);
+        }
+    };
+} // namespace
+
+struct mbavo_ctx
+{
+    int device = 0;
+    mbavo_limits lim{};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int num_sms = 148;
+
+    double cap[kMaxFrames] = {}, exp_time[kMaxFrames] = {};
+    int n_frames_times = 0;
+
+    LevelStore levels[MBAVO_MAX_LEVELS];
+    unsigned long long level_gen[MBAVO_MAX_LEVELS] = {};
+
+    EvalStage *stage_host = nullptr, *stage_dev = nullptr; // pinned / device
+    float *samples = nullptr;
+    double *mid = nullptr;
+    int *seg_end = nullptr;
+    double *block_partials = nullptr;
+    size_t block_partials_cap = 0;
+    unsigned int *counter = nullptr;
+    double *packed_dev = nullptr, *packed_host = nullptr; // E_max doubles, device / pinned
+    int *outlier_result_dev = nullptr, *outlier_result_host = nullptr;
+
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    bool use_graphs = true;
+
+    long long launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = -1.f;
+};
+
+namespace
+{
+    struct DeviceGuard
+    {
+        int prev = -1;
+        explicit DeviceGuard(int dev)
+        {
+            cudaGetDevice(&prev);
+            if (prev != dev)
+                cudaSetDevice(dev);
+            else
+                prev = -1;
+        }
+        ~DeviceGuard()
+        {
+            if (prev >= 0)
+                cudaSetDevice(prev);
+        }
+    };
+
+    void free_level(LevelStore &L)
+    {
+        if (L.owns)
+        {
+            cudaFree(L.ref_I);
+            cudaFree(L.ref_dIxy);
+            for (auto &c : L.cur_I)
+            {
+                cudaFree(c);
+                c = nullptr;
+            }
+            cudaFree(L.xy);
+            cudaFree(L.z);
+        }
+        L.ref_I = nullptr, L.ref_dIxy = nullptr, L.xy = nullptr, L.z = nullptr;
+        L.cap_pix = L.cap_pts = 0, L.cap_frames = 0;
+        L.owns = false;
+    }
+
+    void drop_graphs(mbavo_ctx *ctx, int level)
+    {
+        for (auto it = ctx->graphs.begin(); it != ctx->graphs.end();)
+        {
+            if (level < 0 || it->first.level == level)
+            {
+                cudaGraphExecDestroy(it->second);
+                it = ctx->graphs.erase(it);
+            }
+            else
+                ++it;
+        }
+    }
+
+    // detectOutliersAndUploadToGpu (blur_aware_direct_tracker.cpp:650-698) on the device: one block, fixed-order tree sums.
+    // result[0] = number flagged by this call.
+    __global__ void outlier_kernel(const double *__restrict__ cost, int P, int stride, double k_sigma,
+                                   unsigned char *__restrict__ flags, int *__restrict__ result)
+    {
+        __shared__ double s_a[1024];
+        __shared__ double s_b[1024];
+        const int tid = threadIdx.x;
+        double sum = 0, cnt = 0;
+        for (int i = tid; i < P; i += blockDim.x)
+        {
+            const double c = cost[(size_t)i * stride];
+            if (c >= 1e-8)
+                sum += c, cnt += 1;
+        }
+        s_a[tid] = sum, s_b[tid] = cnt;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1)
+        {
+            if (tid < o)
+                s_a[tid] += s_a[tid + o], s_b[tid] += s_b[tid + o];
+            __syncthreads();
+        }
+        const double n = s_b[0], mu = s_a[0] / n;
+        __syncthreads();
+        double var = 0;
+        for (int i = tid; i < P; i += blockDim.x)
+        {
+            const double c = cost[(size_t)i * stride];
+            if (c >= 1e-8)
+                var += (c - mu) * (c - mu);
+        }
+        s_a[tid] = var;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1)
+        {
+            if (tid < o)
+                s_a[tid] += s_a[tid + o];
+            __syncthreads();
+        }
+        const double thr = k_sigma * (double)sqrtf((float)(s_a[0] / n)); // `max_chi_square_error * sqrtf(var)`, :687
+        __syncthreads();
+        double bad = 0;
+        for (int i = tid; i < P; i += blockDim.x)
+        {
+            const double c = cost[(size_t)i * stride];
+            if (fabs(c - mu) > thr)
+            {
+                flags[i] = 1;
+                bad += 1;
+            }
+        }
+        s_a[tid] = bad;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1)
+        {
+            if (tid < o)
+                s_a[tid] += s_a[tid + o];
+            __syncthreads();
+        }
+        if (tid == 0)
+            result[0] = (int)s_a[0];
+    }
+
+    // Sample time and segment of (frame, sample): compute_virtual_camera_poses.cu:33 + SplineFunctor.h:13-19.  The device
+    // recomputes the same expression with explicit round-to-nearest ops; volatile keeps the host from contracting.
+    int segment_of_sample(double cap, double expo, int i, int N, double t0, double dt)
+    {
+        volatile double a = expo * 0.5;
+        volatile double b = (double)i * expo;
+        volatile double c = b / ((double)(N - 1) + 1e-8);
+        volatile double t = (cap - a) + c;
+        volatile double s = (t - t0) / dt;
+        return (int)s;
+    }
+
+    struct EvalPlan
+    {
+        int K, NK, kmin, N, F, P, S, TP, batches_per_frame;
+        bool with_h;
+        dim3 grid;
+        size_t smem;
+        int E;
+    };
+
+    int plan_evaluation(mbavo_ctx *ctx, int level, const mbavo_spline *sp, bool with_h, EvalPlan &pl)
+    {
+        if (!ctx || level < 0 || level >= MBAVO_MAX_LEVELS || !sp)
+            return fail(MBAVO_EINVAL, "bad context / level / spline");
+        LevelStore &L = ctx->levels[level];
+        if (!L.set)
+            return fail(MBAVO_ENOTREADY, "level %d has not been set", level);
+        if (ctx->n_frames_times < L.dev.F)
+            return fail(MBAVO_ENOTREADY, "frame times set for %d frames, level has %d", ctx->n_frames_times, L.dev.F);
+        if (sp->spline_deg_k != 2 && sp->spline_deg_k != 4)
+            return fail(MBAVO_EINVAL, "spline_deg_k must be 2 or 4 (got %d)", sp->spline_deg_k);
+        if (sp->num_ctrl_knots < sp->spline_deg_k || sp->num_ctrl_knots > 16 || sp->num_ctrl_knots > ctx->lim.max_num_ctrl_knots)
+            return fail(MBAVO_ECAPACITY, "num_ctrl_knots %d outside [k, min(16, max_num_ctrl_knots)]", sp->num_ctrl_knots);
+        if (!(sp->sample_dt > 0))
+            return fail(MBAVO_EINVAL, "sample_dt must be positive");
+        pl.K = sp->spline_deg_k;
+        pl.N = L.dev.N, pl.F = L.dev.F, pl.P = L.dev.P, pl.S = L.dev.S;
+        pl.with_h = with_h;
+
+        EvalStage *st = ctx->stage_host;
+        int lo = 1 << 30, hi = -(1 << 30);
+        for (int f = 0; f < pl.F; ++f)
+            for (int i = 0; i < pl.N; ++i)
+            {
+                const int idx = segment_of_sample(ctx->cap[f], ctx->exp_time[f], i, pl.N, sp->start_time, sp->sample_dt);
+                if (idx < 0 || idx + pl.K > sp->num_ctrl_knots)
+                    return fail(MBAVO_ERANGE, "frame %d sample %d lies in segment %d, outside the %d control knots", f, i, idx,
+                                sp->num_ctrl_knots);
+                st->seg_idx[f * pl.N + i] = idx;
+                lo = idx < lo ? idx : lo;
+                hi = idx > hi ? idx : hi;
+            }
+        pl.kmin = lo;
+        pl.NK = hi - lo + pl.K;
+        if (pl.NK > MBAVO_MAX_KNOT_WINDOW || (pl.K == 2 && pl.NK > 6) || (pl.K == 4 && pl.NK > 7))
+            return fail(MBAVO_ECAPACITY, "exposure windows touch %d control knots; at most %d are supported for k=%d", pl.NK,
+                        pl.K == 2 ? 6 : 7, pl.K);
+        pl.E = with_h ? packed_len(pl.NK) : 1;
+        pl.TP = 32 / pl.S > 0 ? 32 / pl.S : 1;
+        pl.batches_per_frame = (pl.P + pl.TP - 1) / pl.TP;
+        pl.smem = track_kernel_smem_bytes(pl.K, pl.NK, with_h, pl.N, pl.S, pl.TP);
+        if (pl.smem > 200 * 1024)
+            return fail(MBAVO_ECAPACITY, "shared memory need %zu B exceeds 200 KiB (N=%d, S=%d, window=%d)", pl.smem, pl.N, pl.S,
+                        pl.NK);
+        int occ = 1;
+        cudaError_t e = launch_track_kernel(pl.K, pl.NK, with_h, TrackParams{}, dim3(), pl.smem, nullptr, &occ);
+        if (e != cudaSuccess)
+            return fail(MBAVO_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+        int want = (pl.batches_per_frame + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        int cap_blocks = ctx->num_sms * occ / pl.F;
+        if (cap_blocks < 1)
+            cap_blocks = 1;
+        pl.grid = dim3(want < cap_blocks ? want : cap_blocks, pl.F, 1);
+
+        // staging block
+        std::memcpy(st->knots_t, sp->knots_t, sizeof(double) * 3 * sp->num_ctrl_knots);
+        std::memcpy(st->knots_R, sp->knots_R, sizeof(double) * 4 * sp->num_ctrl_knots);
+        std::memcpy(st->cap, ctx->cap, sizeof(double) * pl.F);
+        std::memcpy(st->exp_time, ctx->exp_time, sizeof(double) * pl.F);
+        st->t0 = sp->start_time, st->dt = sp->sample_dt;
+        st->n_knots = sp->num_ctrl_knots, st->K = pl.K, st->N = pl.N, st->F = pl.F, st->kmin = pl.kmin, st->NK = pl.NK;
+        return MBAVO_OK;
+    }
+
+    // Enqueue H2D(stage) -> pose kernel -> tracking kernel [-> D2H(packed)] on ctx->stream (direct or under capture).
+    int enqueue_evaluation(mbavo_ctx *ctx, int level, const EvalPlan &pl, double *packed_dev_out, bool copy_back)
+    {
+        LevelStore &L = ctx->levels[level];
+        cudaStream_t s = ctx->stream;
+        CUDA_TRY(cudaMemcpyAsync(ctx->stage_dev, ctx->stage_host, sizeof(EvalStage), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage_dev, pl.N * pl.F, pl.with_h ? 1 : 0, ctx->samples, ctx->mid, ctx->seg_end, s));
+        TrackParams prm{};
+        prm.lv = L.dev;
+        prm.samples = ctx->samples;
+        prm.mid = ctx->mid;
+        prm.seg_end = ctx->seg_end;
+        prm.stage = ctx->stage_dev;
+        prm.TP = pl.TP;
+        prm.batches_per_frame = pl.batches_per_frame;
+        prm.block_partials = ctx->block_partials;
+        prm.counter = ctx->counter;
+        prm.packed_out = packed_dev_out;
+        if (ctx->timing)
+            CUDA_TRY(cudaEventRecord(ctx->ev0, s));
+        CUDA_TRY(launch_track_kernel(pl.K, pl.NK, pl.with_h, prm, pl.grid, pl.smem, s, nullptr));
+        if (ctx->timing)
+            CUDA_TRY(cudaEventRecord(ctx->ev1, s));
+        if (copy_back)
+            CUDA_TRY(cudaMemcpyAsync(ctx->packed_host, packed_dev_out, sizeof(double) * pl.E, cudaMemcpyDeviceToHost, s));
+        return MBAVO_OK;
+    }
+
+    int run_evaluation(mbavo_ctx *ctx, int level, const EvalPlan &pl, double *packed_dev_out, bool copy_back)
+    {
+        LevelStore &L = ctx->levels[level];
+        size_t need = (size_t)pl.grid.x * pl.grid.y * pl.E;
+        if (need > ctx->block_partials_cap)
+        {
+            drop_graphs(ctx, -1);
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->block_partials);
+            ctx->block_partials = nullptr;
+            CUDA_TRY(cudaMalloc(&ctx->block_partials, need * sizeof(double)));
+            ctx->block_partials_cap = need;
+        }
+        L.last_eval_frames = pl.F;
+        ctx->launches += 2;
+        // graphs only for the blocking path with the context's own buffers (fixed addresses) and without event timing
+        const bool graphable = ctx->use_graphs && !ctx->timing && packed_dev_out == ctx->packed_dev && copy_back;
+        if (!graphable)
+            return enqueue_evaluation(ctx, level, pl, packed_dev_out, copy_back);
+
+        GraphKey key{level, pl.K, pl.NK, pl.with_h ? 1 : 0, pl.N, pl.F, pl.P, pl.S, ctx->level_gen[level]};
+        auto it = ctx->graphs.find(key);
+        if (it == ctx->graphs.end())
+        {
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_evaluation(ctx, level, pl, packed_dev_out, copy_back);
+            cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc != MBAVO_OK)
+            {
+                if (graph)
+                    cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (e != cudaSuccess)
+                return fail(MBAVO_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            cudaGraphExec_t exec = nullptr;
+            e = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess)
+                return fail(MBAVO_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+            it = ctx->graphs.emplace(key, exec).first;
+        }
+        CUDA_TRY(cudaGraphLaunch(it->second, ctx->stream));
+        return MBAVO_OK;
+    }
+} // namespace
+
+extern "C"
+{
+    const char *mbavo_last_error(void) { return g_err; }
+    int mbavo_version(void) { return MBAVO_VERSION; }
+    int mbavo_packed_len(int knot_window) { return packed_len(knot_window); }
+
+    int mbavo_create(const mbavo_limits *lim, mbavo_ctx **out)
+    {
+        if (!lim || !out)
+            return fail(MBAVO_EINVAL, "null argument");
+        if (lim->max_num_frames < 1 || lim->max_num_frames > MBAVO_MAX_FRAMES)
+            return fail(MBAVO_ECAPACITY, "max_num_frames must be in [1, %d]", MBAVO_MAX_FRAMES);
+        if (lim->max_num_virtual_poses_per_frame < 1 || lim->max_num_virtual_poses_per_frame > 64)
+            return fail(MBAVO_ECAPACITY, "max_num_virtual_poses_per_frame must be in [1, 64]");
+        if (lim->max_num_keypoints < 1 || lim->max_patch_size < 1 || lim->max_patch_size > 128)
+            return fail(MBAVO_ECAPACITY, "max_num_keypoints >= 1 and max_patch_size in [1, 128] required");
+        if (lim->max_num_ctrl_knots < 2 || lim->max_num_ctrl_knots > 16)
+            return fail(MBAVO_ECAPACITY, "max_num_ctrl_knots must be in [2, 16]");
+        int dev = lim->device;
+        if (dev < 0)
+            CUDA_TRY(cudaGetDevice(&dev));
+        int count = 0;
+        CUDA_TRY(cudaGetDeviceCount(&count));
+        if (dev >= count)
+            return fail(MBAVO_EINVAL, "device %d out of range (%d devices)", dev, count);
+        DeviceGuard guard(dev);
+
+        mbavo_ctx *ctx = new mbavo_ctx();
+        ctx->device = dev;
+        ctx->lim = *lim;
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+        ctx->num_sms = prop.multiProcessorCount;
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
+        CUDA_TRY(cudaMallocHost(&ctx->stage_host, sizeof(EvalStage)));
+        std::memset(ctx->stage_host, 0, sizeof(EvalStage));
+        CUDA_TRY(cudaMalloc(&ctx->stage_dev, sizeof(EvalStage)));
+        const size_t nsamp = (size_t)lim->max_num_frames * lim->max_num_virtual_poses_per_frame;
+        CUDA_TRY(cudaMalloc(&ctx->samples, nsamp * sample_rec_floats(4) * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&ctx->mid, sizeof(double) * kMidDoubles * kMaxFrames));
+        CUDA_TRY(cudaMalloc(&ctx->seg_end, sizeof(int) * kMaxSegments * kMaxFrames));
+        CUDA_TRY(cudaMalloc(&ctx->counter, sizeof(unsigned int)));
+        CUDA_TRY(cudaMemset(ctx->counter, 0, sizeof(unsigned int)));
+        const int emax = packed_len(MBAVO_MAX_KNOT_WINDOW);
+        CUDA_TRY(cudaMalloc(&ctx->packed_dev, sizeof(double) * emax));
+        CUDA_TRY(cudaMallocHost(&ctx->packed_host, sizeof(double) * emax));
+        CUDA_TRY(cudaMalloc(&ctx->outlier_result_dev, sizeof(int) * 4));
+        CUDA_TRY(cudaMallocHost(&ctx->outlier_result_host, sizeof(int) * 4));
+        CUDA_TRY(cudaEventCreate(&ctx->ev0));
+        CUDA_TRY(cudaEventCreate(&ctx->ev1));
+        const char *g = getenv("MBAVO_NO_GRAPHS");
+        ctx->use_graphs = !(g && g[0] == '1');
+        *out = ctx;
+        return MBAVO_OK;
+    }
+
+    int mbavo_destroy(mbavo_ctx *ctx)
+    {
+        if (!ctx)
+            return MBAVO_OK;
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        drop_graphs(ctx, -1);
+        for (auto &L : ctx->levels)
+        {
+            free_level(L);
+            cudaFree(L.pattern);
+            cudaFree(L.flags);
+            cudaFree(L.patch_cost);
+        }
+        cudaFreeHost(ctx->stage_host);
+        cudaFree(ctx->stage_dev);
+        cudaFree(ctx->samples);
+        cudaFree(ctx->mid);
+        cudaFree(ctx->seg_end);
+        cudaFree(ctx->block_partials);
+        cudaFree(ctx->counter);
+        cudaFree(ctx->packed_dev);
+        cudaFreeHost(ctx->packed_host);
+        cudaFree(ctx->outlier_result_dev);
+        cudaFreeHost(ctx->outlier_result_host);
+        cudaEventDestroy(ctx->ev0);
+        cudaEventDestroy(ctx->ev1);
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return MBAVO_OK;
+    }
+
+    int mbavo_set_stream(mbavo_ctx *ctx, void *stream)
+    {
+        if (!ctx)
+            return fail(MBAVO_EINVAL, "null context");
+        DeviceGuard guard(ctx->device);
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        drop_graphs(ctx, -1);
+        ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+        return MBAVO_OK;
+    }
+
+    int mbavo_set_frame_times(mbavo_ctx *ctx, int n_frames, const double *cap_time, const double *exp_time)
+    {
+        if (!ctx || !cap_time || !exp_time)
+            return fail(MBAVO_EINVAL, "null argument");
+        if (n_frames < 1 || n_frames > ctx->lim.max_num_frames)
+            return fail(MBAVO_ECAPACITY, "n_frames %d outside [1, %d]", n_frames, ctx->lim.max_num_frames);
+        for (int f = 0; f < n_frames; ++f)
+            ctx->cap[f] = cap_time[f], ctx->exp_time[f] = exp_time[f];
+        ctx->n_frames_times = n_frames;
+        return MBAVO_OK;
+    }
+
+    int mbavo_set_level(mbavo_ctx *ctx, int level, const mbavo_level *d)
+    {
+        if (!ctx || !d || level < 0 || level >= MBAVO_MAX_LEVELS)
+            return fail(MBAVO_EINVAL, "bad context / level");
+        if (d->mem != MBAVO_MEM_HOST && d->mem != MBAVO_MEM_DEVICE)
+            return fail(MBAVO_EINVAL, "mem must be MBAVO_MEM_HOST or MBAVO_MEM_DEVICE");
+        if (d->H < 2 || d->W < 2 || !d->ref_I || !d->ref_dIxy || !d->cur_I || !d->keypoint_xy || !d->keypoint_z || !d->pattern_xy)
+            return fail(MBAVO_EINVAL, "level needs H,W >= 2 and non-null image / keypoint / pattern pointers");
+        if (d->n_frames < 1 || d->n_frames > ctx->lim.max_num_frames)
+            return fail(MBAVO_ECAPACITY, "n_frames %d outside [1, %d]", d->n_frames, ctx->lim.max_num_frames);
+        if (d->num_keypoints < 1 || d->num_keypoints > ctx->lim.max_num_keypoints)
+            return fail(MBAVO_ECAPACITY, "num_keypoints %d outside [1, %d]", d->num_keypoints, ctx->lim.max_num_keypoints);
+        if (d->patch_size < 1 || d->patch_size > ctx->lim.max_patch_size)
+            return fail(MBAVO_ECAPACITY, "patch_size %d outside [1, %d]", d->patch_size, ctx->lim.max_patch_size);
+        if (d->num_virtual_poses < 1 || d->num_virtual_poses > ctx->lim.max_num_virtual_poses_per_frame)
+            return fail(MBAVO_ECAPACITY, "num_virtual_poses %d outside [1, %d]", d->num_virtual_poses,
+                        ctx->lim.max_num_virtual_poses_per_frame);
+        if (d->keypoint_xy_stride < 16 || d->keypoint_xy_offset < 0 || d->keypoint_xy_offset + 16 > d->keypoint_xy_stride ||
+            d->keypoint_xy_stride % 8 != 0 || d->keypoint_xy_offset % 8 != 0)
+            return fail(MBAVO_EINVAL, "keypoint_xy stride/offset must describe two aligned doubles per record");
+        if (!(d->fx > 0) || !(d->fy > 0))
+            return fail(MBAVO_EINVAL, "fx, fy must be positive");
+        DeviceGuard guard(ctx->device);
+        LevelStore &L = ctx->levels[level];
+        cudaStream_t s = ctx->stream;
+        CUDA_TRY(cudaStreamSynchronize(s)); // nothing in flight may still read the buffers we are about to replace
+        const size_t npix = (size_t)d->H * d->W;
+        const int P = d->num_keypoints, F = d->n_frames;
+
+        if (!L.pattern)
+        {
+            CUDA_TRY(cudaMalloc(&L.pattern, sizeof(int2) * ctx->lim.max_patch_size));
+            CUDA_TRY(cudaMalloc(&L.flags, ctx->lim.max_num_keypoints));
+            CUDA_TRY(cudaMalloc(&L.patch_cost, sizeof(double) * (size_t)ctx->lim.max_num_keypoints * ctx->lim.max_num_frames));
+        }
+        const LevelDev before = L.dev;
+        bool realloc = false;
+        if (d->mem == MBAVO_MEM_HOST)
+        {
+            if (!L.owns || L.cap_pix < npix || L.cap_pts < (size_t)P || L.cap_frames < F)
+            {
+                free_level(L);
+                CUDA_TRY(cudaMalloc(&L.ref_I, npix));
+                CUDA_TRY(cudaMalloc(&L.ref_dIxy, npix * 2 * sizeof(float)));
+                for (int f = 0; f < F; ++f)
+                    CUDA_TRY(cudaMalloc(&L.cur_I[f], npix));
+                CUDA_TRY(cudaMalloc(&L.xy, sizeof(double) * 2 * P));
+                CUDA_TRY(cudaMalloc(&L.z, sizeof(double) * P));
+                L.owns = true, L.cap_pix = npix, L.cap_pts = P, L.cap_frames = F;
+                realloc = true;
+            }
+            CUDA_TRY(cudaMemcpyAsync(L.ref_I, d->ref_I, npix, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(L.ref_dIxy, d->ref_dIxy, npix * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+            for (int f = 0; f < F; ++f)
+                CUDA_TRY(cudaMemcpyAsync(L.cur_I[f], d->cur_I[f], npix, cudaMemcpyHostToDevice, s));
+            // compact the records to packed double2 on the way in
+            CUDA_TRY(cudaMemcpy2DAsync(L.xy, 16, (const char *)d->keypoint_xy + d->keypoint_xy_offset, d->keypoint_xy_stride, 16, P,
+                                       cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(L.z, d->keypoint_z, sizeof(double) * P, cudaMemcpyHostToDevice, s));
+            L.dev.ref_I = L.ref_I, L.dev.ref_dIxy = reinterpret_cast<const float2 *>(L.ref_dIxy);
+            for (int f = 0; f < F; ++f)
+                L.dev.cur_I[f] = L.cur_I[f];
+            L.dev.xy = reinterpret_cast<const char *>(L.xy), L.dev.xy_stride = 16, L.dev.xy_offset = 0;
+            L.dev.z = L.z;
+        }
+        else
+        {
+            if (L.owns)
+                free_level(L);
+            L.dev.ref_I = d->ref_I, L.dev.ref_dIxy = reinterpret_cast<const float2 *>(d->ref_dIxy);
+            for (int f = 0; f < F; ++f)
+                L.dev.cur_I[f] = d->cur_I[f];
+            L.dev.xy = reinterpret_cast<const char *>(d->keypoint_xy);
+            L.dev.xy_stride = d->keypoint_xy_stride, L.dev.xy_offset = d->keypoint_xy_offset;
+            L.dev.z = d->keypoint_z;
+        }
+        for (int f = F; f < kMaxFrames; ++f)
+            L.dev.cur_I[f] = nullptr;
+        CUDA_TRY(cudaMemcpyAsync(L.pattern, d->pattern_xy, sizeof(int2) * d->patch_size, cudaMemcpyDefault, s));
+        if (!d->ext_outlier_flags)
+        {
+            CUDA_TRY(cudaMemsetAsync(L.flags, 0, ctx->lim.max_num_keypoints, s)); // blur_aware_direct_tracker.cpp:600-601
+            L.num_bad = 0;
+        }
+        L.dev.H = d->H, L.dev.W = d->W;
+        L.dev.fx = d->fx, L.dev.fy = d->fy, L.dev.cx = d->cx, L.dev.cy = d->cy;
+        L.dev.P = P, L.dev.S = d->patch_size, L.dev.N = d->num_virtual_poses, L.dev.F = F;
+        L.dev.pattern = L.pattern;
+        L.dev.flags = d->ext_outlier_flags ? d->ext_outlier_flags : L.flags;
+        if (d->ext_patch_cost)
+        {
+            if (d->ext_patch_cost_stride < 1)
+                return fail(MBAVO_EINVAL, "ext_patch_cost_stride must be >= 1");
+            L.dev.patch_cost = d->ext_patch_cost, L.dev.patch_cost_stride = d->ext_patch_cost_stride;
+        }
+        else
+            L.dev.patch_cost = L.patch_cost, L.dev.patch_cost_stride = 1;
+        L.set = true;
+        // launch parameters are baked into captured graphs: a new generation whenever any of them changed
+        if (realloc || std::memcmp(&before, &L.dev, sizeof(LevelDev)) != 0)
+        {
+            ++ctx->level_gen[level];
+            drop_graphs(ctx, level);
+        }
+        CUDA_TRY(cudaStreamSynchronize(s)); // host buffers are only borrowed for the call
+        return MBAVO_OK;
+    }
+
+    int mbavo_set_outliers(mbavo_ctx *ctx, int level, const unsigned char *flags, int num_bad)
+    {
+        if (!ctx || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
+            return fail(MBAVO_ENOTREADY, "level not set");
+        DeviceGuard guard(ctx->device);
+        LevelStore &L = ctx->levels[level];
+        if (num_bad < 0 || num_bad >= L.dev.P)
+            return fail(MBAVO_EINVAL, "num_bad_keypoints %d outside [0, %d)", num_bad, L.dev.P);
+        unsigned char *dst = const_cast<unsigned char *>(L.dev.flags);
+        if (flags)
+            CUDA_TRY(cudaMemcpyAsync(dst, flags, L.dev.P, cudaMemcpyHostToDevice, ctx->stream));
+        else
+            CUDA_TRY(cudaMemsetAsync(dst, 0, L.dev.P, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        L.num_bad = flags ? num_bad : 0;
+        return MBAVO_OK;
+    }
+
+    int mbavo_set_num_bad(mbavo_ctx *ctx, int level, int num_bad)
+    {
+        if (!ctx || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
+            return fail(MBAVO_ENOTREADY, "level not set");
+        if (num_bad < 0 || num_bad >= ctx->levels[level].dev.P)
+            return fail(MBAVO_EINVAL, "num_bad_keypoints %d outside [0, %d)", num_bad, ctx->levels[level].dev.P);
+        ctx->levels[level].num_bad = num_bad;
+        return MBAVO_OK;
+    }
+
+    int mbavo_unpack(const double *packed, int kmin, int NK, int n_knots, double *total_cost, double *H, double *g)
+    {
+        if (!packed || !total_cost || NK < 1 || kmin < 0 || kmin + NK > n_knots)
+            return fail(MBAVO_EINVAL, "bad window [%d, %d) for %d knots", kmin, kmin + NK, n_knots);
+        *total_cost = packed[0];
+        if (!H)
+            return MBAVO_OK;
+        if (!g)
+            return fail(MBAVO_EINVAL, "gradient must be given with hessian");
+        // merge_hessian_gradient_cost.cpp:25-86 for a window of NK knots: t-block -> 3 (kmin + j), w-block -> 3 (n + kmin + j)
+        const int n = 6 * NK + 1, Wd = 6 * n_knots;
+        std::memset(H, 0, sizeof(double) * Wd * Wd);
+        std::memset(g, 0, sizeof(double) * Wd);
+        const int off_t = 3 * kmin, off_w = 3 * (n_knots + kmin) - 3 * NK;
+        const double *ptr = packed + n;
+        for (int j = 0; j < n - 1; ++j)
+        {
+            const int rr = j + (j < 3 * NK ? off_t : off_w);
+            g[rr] += packed[j + 1];
+            for (int c = j; c < n - 1; ++c, ++ptr)
+            {
+                const int cc = c + (c < 3 * NK ? off_t : off_w);
+                H[(size_t)rr * Wd + cc] += *ptr;
+                if (cc != rr)
+                    H[(size_t)cc * Wd + rr] += *ptr;
+            }
+        }
+        return MBAVO_OK;
+    }
+
+    int mbavo_evaluate(mbavo_ctx *ctx, int level, const mbavo_spline *sp, double huber_a, double *total_cost, double *H, double *g)
+    {
+        if (!total_cost)
+            return fail(MBAVO_EINVAL, "total_cost is null");
+        if ((H == nullptr) != (g == nullptr))
+            return fail(MBAVO_EINVAL, "hessian and gradient must both be given or both be null");
+        if (!ctx)
+            return fail(MBAVO_EINVAL, "null context");
+        DeviceGuard guard(ctx->device);
+        EvalPlan pl;
+        int rc = plan_evaluation(ctx, level, sp, H != nullptr, pl);
+        if (rc != MBAVO_OK)
+            return rc;
+        LevelStore &L = ctx->levels[level];
+        const long long nres = (long long)(pl.P - L.num_bad) * pl.F * pl.S; // spline_update_step.cpp:116
+        ctx->stage_host->inv_num_residuals = 1.0 / (double)nres;
+        ctx->stage_host->huber_a = (float)huber_a;
+        rc = run_evaluation(ctx, level, pl, ctx->packed_dev, true);
+        if (rc != MBAVO_OK)
+            return rc;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->timing)
+            cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
+        return mbavo_unpack(ctx->packed_host, pl.kmin, pl.NK, sp->num_ctrl_knots, total_cost, H, g);
+    }
+
+    int mbavo_evaluate_async(mbavo_ctx *ctx, int level, const mbavo_spline *sp, double huber_a, int with_hessian,
+                             long long num_residuals_global, double *packed_dev, int *kmin, int *knot_window)
+    {
+        if (!ctx || !packed_dev)
+            return fail(MBAVO_EINVAL, "null argument");
+        DeviceGuard guard(ctx->device);
+        EvalPlan pl;
+        int rc = plan_evaluation(ctx, level, sp, with_hessian != 0, pl);
+        if (rc != MBAVO_OK)
+            return rc;
+        LevelStore &L = ctx->levels[level];
+        const long long nres = num_residuals_global > 0 ? num_residuals_global : (long long)(pl.P - L.num_bad) * pl.F * pl.S;
+        // the staging block is reused by the next call: wait for the previous H2D of it to be consumed
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->stage_host->inv_num_residuals = 1.0 / (double)nres;
+        ctx->stage_host->huber_a = (float)huber_a;
+        if (kmin)
+            *kmin = pl.kmin;
+        if (knot_window)
+            *knot_window = pl.NK;
+        return run_evaluation(ctx, level, pl, packed_dev, false);
+    }
+
+    int mbavo_patch_costs(mbavo_ctx *ctx, int level, double *out)
+    {
+        if (!ctx || !out || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
+            return fail(MBAVO_ENOTREADY, "level not set");
+        DeviceGuard guard(ctx->device);
+        LevelStore &L = ctx->levels[level];
+        if (L.last_eval_frames == 0)
+            return fail(MBAVO_ENOTREADY, "no evaluation has run on level %d", level);
+        CUDA_TRY(cudaMemcpy2DAsync(out, sizeof(double), L.dev.patch_cost, sizeof(double) * L.dev.patch_cost_stride, sizeof(double),
+                                   (size_t)L.dev.P * L.dev.F, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return MBAVO_OK;
+    }
+
+    int mbavo_detect_outliers(mbavo_ctx *ctx, int level, double k_sigma, int *num_bad)
+    {
+        if (!ctx || !num_bad || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
+            return fail(MBAVO_ENOTREADY, "level not set");
+        DeviceGuard guard(ctx->device);
+        LevelStore &L = ctx->levels[level];
+        if (L.last_eval_frames == 0)
+            return fail(MBAVO_ENOTREADY, "no evaluation has run on level %d", level);
+        // "only works for tracking one frame" (blur_aware_direct_tracker.cpp:641): statistics over frame 0's patches
+        outlier_kernel<<<1, 1024, 0, ctx->stream>>>(L.dev.patch_cost, L.dev.P, L.dev.patch_cost_stride, k_sigma,
+                                                    const_cast<unsigned char *>(L.dev.flags), ctx->outlier_result_dev);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(ctx->outlier_result_host, ctx->outlier_result_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        L.num_bad = ctx->outlier_result_host[0];
+        *num_bad = L.num_bad;
+        return MBAVO_OK;
+    }
+
+    long long mbavo_kernel_launches(const mbavo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+    int mbavo_enable_kernel_timing(mbavo_ctx *ctx, int enable)
+    {
+        if (!ctx)
+            return fail(MBAVO_EINVAL, "null context");
+        ctx->timing = enable != 0;
+        ctx->last_ms = -1.f;
+        return MBAVO_OK;
+    }
+
+    float mbavo_last_kernel_ms(mbavo_ctx *ctx) { return ctx ? ctx->last_ms : -1.f; }
+}

@@ -1,0 +1,77 @@
+// Internal device-side data layout shared by the pose kernel, the tracking kernels and the host API.
+#ifndef MBAVO_DEVICE_H_
+#define MBAVO_DEVICE_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mbavo
+{
+    constexpr int kMaxFrames = 16;
+    constexpr int kMaxKnotWindow = 8;  // NK
+    constexpr int kMaxSegments = 7;    // NK - k + 1 for k = 2
+    constexpr int kWarpsPerBlock = 8;
+    constexpr int kThreads = kWarpsPerBlock * 32;
+
+    // One exposure sample (virtual pose) as the tracking kernel consumes it, fp32, 16-byte aligned records:
+    //   [0..8]   R      rotation matrix of the pose quaternion, row-major   (compute_virtual_camera_poses.cu:102-109)
+    //   [9..11]  t      translation
+    //   [12..12+K)      wt[j]     translation blend weight of the segment's knot j        (SplineFunctor.h:30-40, 74-91)
+    //   [12+K .. 12+K+9K)  Theta[j] (3x3 row-major) = d theta / d w_j, theta the right perturbation of the pose
+    //                   rotation: dq/dw_j = L(q) [I/2; 0] Theta_j                           (SplineFunctor.h:178-213, 274-361)
+    //   then 1 int      segment offset inside the knot window (idx_i - kmin)
+    __host__ __device__ constexpr int sample_rec_floats(int K) { return ((12 + K + 9 * K + 1) + 3) / 4 * 4; }
+
+    // per-frame fp64 data for the patch centre (compute_local_patches_xy.cu:26-49): R_r2c (9) and t_r2c (3)
+    constexpr int kMidDoubles = 12;
+
+    // Staging block copied host -> device once per evaluation (pinned source).
+    struct EvalStage
+    {
+        double knots_t[3 * 16];
+        double knots_R[4 * 16];
+        double cap[kMaxFrames];
+        double exp_time[kMaxFrames];
+        double t0, dt;
+        int n_knots, K, N, F, kmin, NK;
+        double inv_num_residuals;     // 1 / ((P - num_bad) F S)            spline_update_step.cpp:116-117
+        float huber_a;
+        int pad_;
+        int seg_idx[kMaxFrames * 64]; // host-computed segment start knot of every sample (authoritative)
+    };
+
+    struct LevelDev
+    {
+        const unsigned char *ref_I;
+        const float2 *ref_dIxy;
+        const unsigned char *cur_I[kMaxFrames];
+        int H, W;
+        double fx, fy, cx, cy;
+        const char *xy;     // records with two doubles at byte offset xy_offset, stride xy_stride
+        int xy_stride, xy_offset;
+        const double *z;
+        int P, S, N, F;
+        const int2 *pattern;
+        const unsigned char *flags; // 1 = outlier
+        double *patch_cost;         // [F * P * patch_cost_stride]
+        int patch_cost_stride;
+    };
+
+    struct TrackParams
+    {
+        LevelDev lv;
+        const float *samples;     // [F * N * rec] sample records
+        const double *mid;        // [F * kMidDoubles]
+        const int *seg_end;       // [F * kMaxSegments]: one past the last sample index of every segment offset
+        const EvalStage *stage;   // huber_a and inv_num_residuals live here so that launch parameters never change
+        int TP;                   // points per warp batch
+        int batches_per_frame;
+        double *block_partials;   // [gridDim.x * gridDim.y * E]
+        unsigned int *counter;    // last-block-done ticket
+        double *packed_out;       // [E]
+    };
+
+    __host__ __device__ constexpr int packed_len(int NK) { return (6 * NK + 1) * (6 * NK + 2) / 2; }
+} // namespace mbavo
+
+#endif

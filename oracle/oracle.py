@@ -100,7 +100,9 @@ class _Lib:
 
     # -- whole evaluation
     def evaluate(self, prob, level: int, knots_t=None, knots_R=None, flags=None, num_bad: int = 0,
-                 with_hessian: bool = True, want_patch_costs: bool = True):
+                 with_hessian: bool = True, want_patch_costs: bool = True, centres_in=None, centres_out=None):
+        """-> (cost, H, g, patch_costs).  centres_in / centres_out ([F, P, 2], oracle port only) hold the patch centres
+        fixed / report them (finite-difference checks)."""
         lv = prob.levels[level]
         kt = np.ascontiguousarray(prob.knots_t if knots_t is None else knots_t, dtype=np.float64)
         kR = np.ascontiguousarray(prob.knots_R if knots_R is None else knots_R, dtype=np.float64)
@@ -124,6 +126,12 @@ class _Lib:
         if self.prefix == "mbavo_ref_":
             rc = f(*common, _ptr(seg, _ip), C.c_int(n), C.c_double(prob.huber_a), C.byref(cost), _ptr(H, _dp),
                    _ptr(g, _dp), _ptr(pc, _dp))
+        elif centres_in is not None or centres_out is not None:
+            f = self.fn("evaluate_fixed_centres")
+            f.restype = C.c_int
+            ci = None if centres_in is None else np.ascontiguousarray(centres_in, dtype=np.float64)
+            rc = f(*common, C.c_int(n), C.c_double(prob.huber_a), C.byref(cost), _ptr(H, _dp), _ptr(g, _dp),
+                   _ptr(pc, _dp), _ptr(ci, _dp), _ptr(centres_out, _dp))
         else:
             rc = f(*common, C.c_int(n), C.c_double(prob.huber_a), C.byref(cost), _ptr(H, _dp), _ptr(g, _dp),
                    _ptr(pc, _dp))
