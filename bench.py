@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the blur-aware tracking hot path (BASELINE.json metric: point-sample residuals/s).
+
+Workload (config.workload): BASELINE.json configs[1] — synthetic 640x480, 4-level pyramid, 20k points at level 0
+(halved per level), 16 exposure samples, 2 control poses (k = 2).  One STEP = one Gauss–Newton iteration at every
+pyramid level, coarse to fine: Hessian-pass evaluation at the current knots -> damped solve on the host (first LM
+radius) -> cost-only evaluation at the candidate knots; i.e. 8 evaluations of the fused kernel and 4 solves.
+A point-sample = one host-map point at one exposure sub-step (= 8 pixel samples); a step processes
+sum_l 2 * P_l * N of them.
+
+Legs (own arm):
+  value     inputs resident in HBM, K steps through the C-ABI (mbavo_evaluate), device-timed
+  e2e       the same K steps, but every step first re-uploads every level (images, gradients, points) from PINNED host
+            buffers through mbavo_set_level, and reads H, g, cost back: host<->device copies inside the timed region
+  roofline  per-kernel durations of the same steps (CUDA events around the tracking kernel, on its stream)
+  cpu_baseline  the reference's arithmetic on the host cores (oracle/_ref, else the oracle port), bounded sample
+
+`--impl reference` times that CPU implementation alone (rank 0 only).
+For N > 1 (torchrun, one rank per GPU): every rank holds its own 20k-point shard of an N-times larger point set
+(weak scaling), the packed [cost, g, H] vector is all-reduced over NCCL once per evaluation.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C2: synthetic 640x480, 4-level pyramid, 20k points (halved per level), 16 exposure samples, 2 control poses"
+ALGO_BYTES_H = 288.0   # algorithmic bytes per point-sample, Hessian pass (8 px * (4 B + 32 B))
+ALGO_BYTES_C = 32.0    # cost-only pass
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU with NVML while the measurement runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        nv = self.nv
+        names = {"hw_slowdown": "nvmlClocksEventReasonHwSlowdown", "hw_thermal_slowdown": "nvmlClocksEventReasonHwThermalSlowdown",
+                 "sw_thermal_slowdown": "nvmlClocksEventReasonSwThermalSlowdown", "sw_power_cap": "nvmlClocksEventReasonSwPowerCap"}
+        masks = {}
+        for k, v in names.items():
+            m = getattr(nv, v, None) or getattr(nv, v.replace("ClocksEventReason", "ClocksThrottleReason"), None)
+            if m is not None:
+                masks[k] = m
+        while not self.stop:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, m in masks.items():
+                    if r & m:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        if self.nv:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def point_samples_per_step(prob):
+    return sum(2 * lv.P * lv.N * prob.F for lv in prob.levels)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU implementation (reference arm and cpu_baseline)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_step(lib, O, prob):
+    """The same step on the host: per level H-pass, damped solve, candidate, cost-only pass."""
+    kt, kR = prob.knots_t, prob.knots_R
+    for level in reversed(range(len(prob.levels))):
+        c, H, g, _ = lib.evaluate(prob, level, kt, kR, want_patch_costs=False)
+        step, model = O.trust_region_step(H, g, 1e4)
+        ct, cR = O.plus(kt, kR, step)
+        lib.evaluate(prob, level, ct, cR, with_hessian=False, want_patch_costs=False)
+
+
+def run_reference(args, pkg):
+    from oracle import oracle as O
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib = O.best_cpu_lib()
+    prob = pkg.synth.make_config("C2")
+    for _ in range(args.warmup):
+        cpu_step(lib, O, prob)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(lib, O, prob)
+    dt = time.perf_counter() - t
+    ps = point_samples_per_step(prob)
+    value = ps * args.steps / dt
+    line = {"impl": "reference", "metric": "point_sample_residuals_per_s", "value": value, "unit": "point-samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "step": "1 GN iteration per pyramid level (H pass + solve + cost pass)",
+                       "point_samples_per_step": ps},
+            "gn_iters_per_s": len(prob.levels) * args.steps / dt,
+            "cpu_baseline": {"value": value, "unit": "point-samples/s", "cores": lib.num_threads(), "kind": lib.kind,
+                             "sample": f"{args.steps} full steps of the workload, OpenMP over points"},
+            "e2e": {"value": value, "unit": "point-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# own arm
+# ----------------------------------------------------------------------------------------------------------------
+def gpu_step(ctx, prob, lib_ctx_eval, solve, plus):
+    kt, kR = prob.knots_t, prob.knots_R
+    out = None
+    for level in reversed(range(len(prob.levels))):
+        c, H, g = lib_ctx_eval(level, kt, kR, True)
+        step, model = solve(H, g, 1e4)
+        ct, cR = plus(kt, kR, step)
+        c2, _, _ = lib_ctx_eval(level, ct, cR, False)
+        out = (c, c2)
+    return out
+
+
+def run_own(args, pkg):
+    import torch
+    import torch.distributed as dist
+
+    from mbavo_b200.api import Limits
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # every rank generates the same images / spline; its points are its own seeded draw (weak scaling: 20k per rank)
+    prob = pkg.synth.make_config("C2")
+    if world > 1:
+        rng = np.random.default_rng(9000 + rank)
+        for lv in prob.levels:
+            lo = lv.xy.min(0)
+            hi = lv.xy.max(0)
+            lv.xy = np.ascontiguousarray(rng.uniform(lo, hi, lv.xy.shape))
+    ps_step = point_samples_per_step(prob) * world
+    lim = Limits(max_num_frames=1, max_num_virtual_poses_per_frame=16, max_num_keypoints=prob.levels[0].P, max_patch_size=8,
+                 max_num_ctrl_knots=2, device=local_rank)
+    ctx = pkg.Context(lim)
+    # one non-default stream for everything: the library's kernels, torch's events / L2 flush, and the NCCL all-reduce
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_frame_times(prob.cap, prob.exp)
+
+    # pinned host copies of every level (the e2e leg uploads from these)
+    pinned = []
+    for lv in prob.levels:
+        def pin(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return t.numpy()
+        pinned.append(pkg.synth.Level(H=lv.H, W=lv.W, fx=lv.fx, fy=lv.fy, cx=lv.cx, cy=lv.cy, ref_I=pin(lv.ref_I),
+                                      ref_dIxy=pin(lv.ref_dIxy), cur_I=[pin(c) for c in lv.cur_I], xy=pin(lv.xy), z=pin(lv.z),
+                                      pattern=pin(lv.pattern), N=lv.N))
+    h2d_step = sum(lv.ref_I.nbytes + lv.ref_dIxy.nbytes + sum(c.nbytes for c in lv.cur_I) + lv.xy.nbytes + lv.z.nbytes +
+                   lv.pattern.nbytes for lv in prob.levels) + 2 * len(prob.levels) * (7 * prob.n_knots * 8 + 2048)
+    d2h_step = len(prob.levels) * (91 * 8 + 8)
+
+    def upload_all():
+        for l, lv in enumerate(pinned):
+            ctx.set_level(l, lv)
+
+    upload_all()
+    if world > 1:
+        # same dataflow as mbavo_b200.parallel.ShardedEvaluator: the fused kernel leaves this rank's packed vector in
+        # `packed`, NCCL sums it in place on the same stream, one D2H brings the global result back
+        packed = torch.zeros(ctx.packed_len(8), dtype=torch.float64, device=dev)
+        prob_global_P = [lv.P * world for lv in prob.levels]  # global normaliser: world * P points per level
+
+        def evaluate(level, kt, kR, with_h):
+            lv = prob.levels[level]
+            nres = prob_global_P[level] * prob.F * lv.S
+            kmin, nk = ctx.evaluate_async(level, prob.k, prob.t0, prob.dt, kt, kR, prob.huber_a, with_h, nres,
+                                          packed.data_ptr())
+            E = ctx.packed_len(nk) if with_h else 1
+            buf = packed[:E]
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            return ctx.unpack(buf.cpu().numpy(), kmin, nk, prob.n_knots, with_h)
+    else:
+        def evaluate(level, kt, kR, with_h):
+            return ctx.evaluate(level, prob.k, prob.t0, prob.dt, kt, kR, prob.huber_a, with_h)
+
+    def solve(H, g, radius):
+        return ctx.trust_region_step(H, g, radius)
+
+    def plus(kt, kR, step):
+        return ctx.spline_plus(kt, kR, step)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def timed(nsteps, with_upload):
+        """Device time (ms) of nsteps steps: CUDA events on the stream the kernels run on, L2 flushed (not timed) between
+        steps; max over ranks."""
+        total = 0.0
+        for _ in range(nsteps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            e0.record(stream)
+            if with_upload:
+                upload_all()
+            gpu_step(ctx, prob, evaluate, solve, plus)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            total += e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([total], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total
+
+    with ClockSampler(local_rank) as clocks:
+        timed(max(args.warmup, 3), False)
+        l0 = ctx.kernel_launches()
+        ms_value = timed(args.steps, False)
+        launches = ctx.kernel_launches() - l0
+        timed(max(args.warmup, 3), True)
+        ms_e2e = timed(args.steps, True)
+
+        # roofline leg: per-kernel durations of the same steps (graph replay off while events bracket the kernel)
+        ctx.enable_kernel_timing(True)
+        kms = {}
+        for it in range(max(3, min(args.steps, 50)) + 3):
+            flush.zero_()
+            kt, kR = prob.knots_t, prob.knots_R
+            for level in reversed(range(len(prob.levels))):
+                c, H, g = evaluate(level, kt, kR, True)
+                if it >= 3:
+                    kms.setdefault((level, "H"), []).append(ctx.last_kernel_ms())
+                step, _ = solve(H, g, 1e4)
+                ct, cR = plus(kt, kR, step)
+                evaluate(level, ct, cR, False)
+                if it >= 3:
+                    kms.setdefault((level, "C"), []).append(ctx.last_kernel_ms())
+        ctx.enable_kernel_timing(False)
+    clk = clocks.summary()
+
+    value = ps_step * args.steps / (ms_value * 1e-3)
+    e2e_value = ps_step * args.steps / (ms_e2e * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    avg = {k: sum(v) / len(v) for k, v in kms.items()}
+    kernel_ms_per_step = sum(avg.values())
+    dom = max(avg, key=lambda k: avg[k])  # dominant kernel launch: level-0 Hessian pass
+    lv = prob.levels[dom[0]]
+    algo_bytes = (ALGO_BYTES_H if dom[1] == "H" else ALGO_BYTES_C) * lv.P * lv.N * prob.F
+    achieved = algo_bytes / (avg[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("track_kernel_L0_H_dram_bytes")
+    except Exception:
+        pass
+
+    line = {"metric": "point_sample_residuals_per_s", "value": value, "unit": "point-samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_value / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "step": "1 GN iteration per pyramid level (H pass + solve + cost pass)",
+                       "point_samples_per_step": ps_step, "points_per_gpu_level0": prob.levels[0].P,
+                       "l2": "flushed between steps with a 256 MiB memset (not timed); working set (4 MB) is L2-resident within a step",
+                       "parallelism": f"point-sharded x{world}, 1 NCCL all-reduce of the packed H/g/cost per evaluation" if world > 1 else "single GPU",
+                       "accumulation": "fp32 per sample, fp64 across pixels"},
+            "gn_iters_per_s": len(prob.levels) * args.steps / (ms_value * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "point-samples/s", "h2d_bytes_per_step": int(h2d_step),
+                    "d2h_bytes_per_step": int(d2h_step), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": f"track_kernel<k=2,window=2,{'hessian' if dom[1] == 'H' else 'cost'}> level {dom[0]}",
+                         "kernel_ms": avg[dom], "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                         "kernel_ms_per_step_all_launches": kernel_ms_per_step,
+                         "kernel_share_of_step": kernel_ms_per_step / (ms_value / args.steps),
+                         "note": "algorithmic bytes = 288 B per point-sample (SURVEY §8d); the images are L2-resident, so DRAM traffic is far below it"}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+
+        lib = O.best_cpu_lib()
+        cprob = pkg.synth.make_config("C2")
+        cpu_step(lib, O, cprob)
+        t0, n = time.perf_counter(), 0
+        while n < 3 or (time.perf_counter() - t0 < 12.0 and n < 2000):
+            cpu_step(lib, O, cprob)
+            n += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": point_samples_per_step(cprob) * n / dt, "unit": "point-samples/s",
+                                "cores": lib.num_threads(), "kind": lib.kind, "ms_per_step": dt / n * 1e3,
+                                "sample": f"{n} full steps of the same workload in {dt:.1f} s (OpenMP over points)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    import __graft_entry__ as ge
+
+    pkg = ge.load_package()
+    if args.impl == "reference":
+        run_reference(args, pkg)
+    else:
+        run_own(args, pkg)
+
+
+if __name__ == "__main__":
+    main()

@@ -271,6 +271,7 @@ def make_problem(name: str, W: int, H: int, levels: int, P0: int, N: int, n_knot
             for f in range(F)]
 
     # blur length in level-0 pixels bounds the margin that keeps every sample inside the image
+    explicit_margin = margin is not None
     if margin is None:
         flow = 0.0
         for corner in ([0, 0], [W - 1, 0], [0, H - 1], [W - 1, H - 1], [W / 2, H / 2]):
@@ -293,7 +294,7 @@ def make_problem(name: str, W: int, H: int, levels: int, P0: int, N: int, n_knot
         sc = 2 ** l
         Hl, Wl = H // sc, W // sc
         Pl = max(P0 >> l, 1)
-        mg = max(margin // sc + 4, 5)
+        mg = max(margin // sc, 0) if explicit_margin else max(margin // sc + 4, 5)
         xy = np.stack([rng.uniform(mg, Wl - 1 - mg, Pl), rng.uniform(mg, Hl - 1 - mg, Pl)], axis=1)
         z = rng.uniform(5.0, 10.0, Pl) if depth_mode == "random" else np.full(Pl, plane_z)
         lv.append(Level(H=Hl, W=Wl, fx=fx0 / sc, fy=fy0 / sc, cx=cx0 / sc, cy=cy0 / sc, ref_I=np.ascontiguousarray(I_l),

@@ -98,6 +98,18 @@ class _Lib:
           C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), _ptr(out, _dp))
         return out
 
+    # -- one sample: compute_pixel_intensity<double>
+    def pixel_intensity(self, I, dIxy, pose, D, fx, fy, cx, cy, X, Y, want_J=True):
+        H, W = I.shape
+        inten = C.c_double(0)
+        J = np.zeros(7) if want_J else None
+        f = self.fn("pixel_intensity")
+        f.restype = C.c_int
+        ok = f(_ptr(I, _u8p), _ptr(dIxy, _fp), C.c_int(H), C.c_int(W), _ptr(np.ascontiguousarray(pose, dtype=np.float64), _dp),
+               C.c_double(D), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), C.c_double(X),
+               C.c_double(Y), C.byref(inten), _ptr(J, _dp))
+        return bool(ok), inten.value, J
+
     # -- whole evaluation
     def evaluate(self, prob, level: int, knots_t=None, knots_R=None, flags=None, num_bad: int = 0,
                  with_hessian: bool = True, want_patch_costs: bool = True, centres_in=None, centres_out=None):
@@ -173,17 +185,6 @@ class OracleLib(_Lib):
             d = 6 * NK.value
             J = J.reshape(-1)[: F * lv.P * lv.S * d].reshape(F, lv.P, lv.S, d)
         return r, J, kmin.value, NK.value
-
-    def pixel_intensity(self, I, dIxy, pose, D, fx, fy, cx, cy, X, Y, want_J=True):
-        H, W = I.shape
-        inten = C.c_double(0)
-        J = np.zeros(7) if want_J else None
-        f = self.fn("pixel_intensity")
-        f.restype = C.c_int
-        ok = f(_ptr(I, _u8p), _ptr(dIxy, _fp), C.c_int(H), C.c_int(W), _ptr(np.ascontiguousarray(pose, dtype=np.float64), _dp),
-               C.c_double(D), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), C.c_double(X),
-               C.c_double(Y), C.byref(inten), _ptr(J, _dp))
-        return bool(ok), inten.value, J
 
     def image_gradient(self, I):
         H, W = I.shape

@@ -404,6 +404,17 @@ extern "C"
         return mbavo_ref_merge(F, k, frame_packed.data(), seg_start, n_knots, total_cost, H, g);
     }
 
+    // compute_pixel_intensity<double> itself (compute_pixel_intensity.h:91-209); pose = [t(3), q(x,y,z,w)]
+    int mbavo_ref_pixel_intensity(const unsigned char *I_ref, const float *dIxy, int H, int W, const double *pose, double D,
+                                  double fx, double fy, double cx, double cy, double X, double Y, double *intensity,
+                                  double *J7)
+    {
+        Core::VectorX<double, 2> cur;
+        cur.values[0] = X;
+        cur.values[1] = Y;
+        return VO::compute_pixel_intensity<double>(I_ref, dIxy, H, W, pose + 3, pose, D, fx, fy, cx, cy, cur, intensity, J7) ? 1 : 0;
+    }
+
     // generate_synthetic_data.cpp:127-180 (warp_image + synthesize_motion_blurred_img) with the pose supplied by
     // the reference spline functors (SplineSE3::GetPose uses the same functors, Spline.h:120-170).
     int mbavo_ref_synthesize_blurred(const unsigned char *I_ref, int H, int W, double plane_depth,

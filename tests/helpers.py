@@ -1,0 +1,37 @@
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def problem_from_golden(z, synth):
+    """Rebuild a synth.Problem from the arrays stored by tests/golden/make_golden.py."""
+    ref_I = np.ascontiguousarray(z["ref_I"])
+    lv = synth.Level(H=int(z["H"]), W=int(z["W"]), fx=float(z["fx"]), fy=float(z["fy"]), cx=float(z["cx"]), cy=float(z["cy"]),
+                     ref_I=ref_I, ref_dIxy=synth.image_gradient(ref_I), cur_I=[np.ascontiguousarray(c) for c in z["cur_I"]],
+                     xy=np.ascontiguousarray(z["xy"]), z=np.ascontiguousarray(z["z"]),
+                     pattern=np.ascontiguousarray(z["pattern"]), N=int(z["N"]))
+    return synth.Problem(name="golden", levels=[lv], cap=z["cap"].copy(), exp=z["exp"].copy(), k=int(z["k"]), t0=float(z["t0"]),
+                         dt=float(z["dt"]), knots_t=z["knots_t"].copy(), knots_R=z["knots_R"].copy(),
+                         gt_knots_t=z["knots_t"].copy(), gt_knots_R=z["knots_R"].copy(), huber_a=float(z["huber_a"]),
+                         seg_start=z["seg_start"].copy())
+
+
+def first_step(O, H, g):
+    """First LM step at radius 1e4: H_ii (1 + 1e-4), delta = -H^-1 g."""
+    Hd = H.copy()
+    step, _ = O.trust_region_step(Hd, g, 1e4)
+    return step
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
+
+
+def max_rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max())

@@ -1,0 +1,60 @@
+"""GPU test of the drop-in boundary: a C++ program (tests/cpp/dropin_main.cpp) that uses the reference's API surface —
+CudaSharedStorages + initialize_shared_cuda_storages + evaluate_cost_hessian_gradient, storages poked with raw
+cudaMemcpy and Core::Vector2d records exactly as blur_aware_direct_tracker.cpp does — linked against the product library.
+Its results must match the oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import first_step, max_rel, rel
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "dropin_main")
+
+
+def build_dropin():
+    libdir = os.path.join(ROOT, "mba-vo_b200", "lib")
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++14", os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"), "-I/usr/local/cuda/include",
+           "-L" + libdir, "-L/usr/local/cuda/lib64", "-lmbavo_b200", "-lcudart", "-Wl,-rpath," + libdir,
+           "-Wl,-rpath,/usr/local/cuda/lib64", "-o", BIN]
+    subprocess.run(cmd, check=True, capture_output=True)
+
+
+@pytest.mark.parametrize("k,n_knots", [(2, 2), (4, 4)])
+def test_reference_api_drop_in(pkg, O, orc, synth, tmp_path, k, n_knots):
+    if not os.path.exists(BIN):
+        build_dropin()
+    prob = synth.make_problem("dropin", W=192, H=144, levels=1, P0=700, N=8, n_knots=n_knots, k=k, seed=31, margin=16)
+    lv = prob.levels[0]
+    flags = np.zeros(lv.P, dtype=np.uint8)
+    flags[2::13] = 1
+    path = os.path.join(str(tmp_path), "problem.bin")
+    with open(path, "wb") as f:
+        np.array([lv.H, lv.W, lv.P, lv.S, lv.N, prob.n_knots, prob.k, int(flags.sum())], dtype=np.int32).tofile(f)
+        np.array([lv.fx, lv.fy, lv.cx, lv.cy, prob.cap[0], prob.exp[0], prob.t0, prob.dt, prob.huber_a], dtype=np.float64).tofile(f)
+        lv.ref_I.tofile(f)
+        lv.ref_dIxy.tofile(f)
+        lv.cur_I[0].tofile(f)
+        lv.xy.tofile(f)
+        lv.z.tofile(f)
+        lv.pattern.tofile(f)
+        prob.knots_t.tofile(f)
+        prob.knots_R.tofile(f)
+        flags.tofile(f)
+    r = subprocess.run([BIN, path], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout)
+    c, H, g, pc = orc.evaluate(prob, 0)
+    Hg = np.array(got["H"]).reshape(H.shape)
+    gg = np.array(got["g"])
+    assert abs(got["cost"] - c) <= 1e-5 * c and abs(got["cost_only"] - c) <= 1e-5 * c
+    assert max_rel(Hg, H) <= 1e-4 and max_rel(gg, g) <= 1e-4
+    assert rel(first_step(O, Hg, gg), first_step(O, H, g)) <= 1e-4
+    assert np.abs(np.array(got["patch_costs"]) - pc[0]).max() <= 1e-4 * pc.max()
+    cf = orc.evaluate(prob, 0, flags=flags, num_bad=int(flags.sum()), with_hessian=False)[0]
+    assert abs(got["cost_flagged"] - cf) <= 1e-5 * cf

@@ -1,0 +1,261 @@
+"""GPU parity tests (run with -m gpu on the B200): the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs and against the committed golden vectors.
+
+Gates (BASELINE.md §3.4 — the north star's floating-point tolerances):
+    first LM step   ||delta - delta_ref|| / ||delta_ref|| <= 1e-4     (radius 1e4)
+    cost            |c - c_ref| / |c_ref|                 <= 1e-5
+    H, g            max |x - x_ref| / max |x_ref|         <= 1e-4 / 1e-4 (element-wise, informational gate of §8d: 1e-5 of max)
+"""
+import numpy as np
+import pytest
+
+from helpers import first_step, golden, max_rel, problem_from_golden, rel
+
+pytestmark = pytest.mark.gpu
+
+COST_TOL = 1e-5
+DELTA_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def api(pkg):
+    from mbavo_b200 import api as a
+
+    return a
+
+
+def gpu_eval(pkg, api, prob, level=0, knots=None, with_hessian=True, flags=None, num_bad=0, ctx=None):
+    own = ctx is None
+    if own:
+        ctx = pkg.Context(api.limits_for(prob))
+        api.upload_problem(ctx, prob)
+    try:
+        if flags is not None:
+            ctx.set_outliers(level, flags, num_bad)
+        kt, kR = (prob.knots_t, prob.knots_R) if knots is None else knots
+        c, H, g = ctx.evaluate(level, prob.k, prob.t0, prob.dt, kt, kR, prob.huber_a, with_hessian)
+        pc = ctx.patch_costs(level, prob.F, prob.levels[level].P)
+        return c, H, g, pc
+    finally:
+        if own:
+            ctx.close()
+
+
+def check_parity(O, got, want, cost_tol=COST_TOL, delta_tol=DELTA_TOL):
+    c, H, g, pc = got
+    c_ref, H_ref, g_ref, pc_ref = want
+    assert abs(c - c_ref) <= cost_tol * abs(c_ref), ("cost", c, c_ref)
+    assert np.abs(pc - pc_ref).max() <= 1e-4 * max(pc_ref.max(), 1e-12), "patch costs"
+    if H is not None:
+        assert np.array_equal(H, H.T)
+        assert max_rel(H, H_ref) <= 1e-4 and max_rel(g, g_ref) <= 1e-4, (max_rel(H, H_ref), max_rel(g, g_ref))
+        d, d_ref = first_step(O, H, g), first_step(O, H_ref, g_ref)
+        assert rel(d, d_ref) <= delta_tol, ("delta", rel(d, d_ref))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["k2", "k4"])
+def test_golden_reference_vectors(pkg, api, O, synth, tag):
+    """Against outputs of the reference's own arithmetic (tests/golden, generated from oracle/_ref)."""
+    z = golden(f"evaluate_{tag}.npz")
+    prob = problem_from_golden(z, synth)
+    check_parity(O, gpu_eval(pkg, api, prob), (float(z["cost"]), z["Hessian"], z["gradient"], z["patch_costs"]))
+    c2 = gpu_eval(pkg, api, prob, with_hessian=False)[0]
+    assert abs(c2 - float(z["cost_only"])) <= COST_TOL * float(z["cost_only"])
+    flags = z["flags"]
+    check_parity(O, gpu_eval(pkg, api, prob, flags=flags, num_bad=int(flags.sum())),
+                 (float(z["cost_flagged"]), z["H_flagged"], z["g_flagged"], z["patch_costs_flagged"]))
+
+
+@pytest.mark.parametrize("name,levels", [("tiny", None), ("C1", None), ("C2", None), ("C3", [0, 4]), ("C5", None),
+                                         ("C5cubic", None)])
+def test_baseline_configs_against_oracle(pkg, api, O, orc, synth, name, levels):
+    """BASELINE.json configs (C3's middle levels skipped to bound the CPU time): Hessian pass and cost-only pass."""
+    prob = synth.make_config(name)
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        for level in (levels if levels is not None else range(len(prob.levels))):
+            want = orc.evaluate(prob, level)
+            check_parity(O, gpu_eval(pkg, api, prob, level, ctx=ctx), want)
+            c2 = gpu_eval(pkg, api, prob, level, with_hessian=False, ctx=ctx)
+            assert abs(c2[0] - want[0]) <= COST_TOL * want[0]
+            assert np.abs(c2[3] - want[3]).max() <= 1e-4 * want[3].max()
+
+
+@pytest.mark.parametrize("P,S,N", [(1, 8, 4), (3, 8, 5), (301, 8, 7), (257, 1, 8), (130, 5, 3), (77, 12, 16), (33, 40, 9),
+                                   (64, 33, 1), (500, 8, 64), (129, 128, 2)])
+def test_ragged_shapes(pkg, api, O, orc, synth, P, S, N):
+    """Point counts that do not fill a warp batch, patch sizes that are not 8 / not a power of two / larger than a warp,
+    sample counts that are not powers of two (the reference requires powers of two: reduction.h:13-55)."""
+    rng = np.random.default_rng(P * 1000 + S * 10 + N)
+    pattern = None
+    if S != 8:
+        pattern = np.stack([rng.integers(-3, 4, S), rng.integers(-3, 4, S)], axis=1).astype(np.int32)
+    prob = synth.make_problem("ragged", W=192, H=144, levels=1, P0=P, N=N, n_knots=2, k=2, seed=P + S + N, pattern=pattern,
+                              margin=14)
+    check_parity(O, gpu_eval(pkg, api, prob), orc.evaluate(prob, 0))
+    c2 = gpu_eval(pkg, api, prob, with_hessian=False)[0]
+    assert abs(c2 - orc.evaluate(prob, 0, with_hessian=False)[0]) <= COST_TOL * c2
+
+
+def test_image_borders_and_invalid_samples(pkg, api, O, orc, synth):
+    """Points right up to the image border: pixels outside the live image give r = 0, J = 0; samples that leave the
+    keyframe contribute 0 with the divisor kept at N (…cost.cu:74-78, 107-121)."""
+    prob = synth.make_problem("border", W=160, H=120, levels=1, P0=4000, N=8, n_knots=2, k=2, seed=77, margin=0, motion_scale=2.0)
+    lv = prob.levels[0]
+    r, _, _, _ = orc.pixel_residuals(prob, 0, with_jacobian=False)
+    assert (r == 0).sum() > 50, "the case must actually contain invalid pixels"
+    got, want = gpu_eval(pkg, api, prob), orc.evaluate(prob, 0)
+    # a sample within fp32 rounding of the validity boundary may flip: allow a few patches to differ, nothing else
+    diff = np.abs(got[3] - want[3])
+    assert (diff > 1e-4 * want[3].max()).mean() < 2e-3
+    assert abs(got[0] - want[0]) <= 1e-4 * want[0]
+    assert rel(first_step(O, got[1], got[2]), first_step(O, want[1], want[2])) <= 1e-3
+    # last row / column taps (weight 0) must not read out of bounds: a point whose warp lands on x = W-1 exactly
+    prob2 = synth.make_problem("edge", W=64, H=48, levels=1, P0=1, N=2, n_knots=2, k=2, seed=1, margin=4)
+    prob2.knots_t[:] = 0
+    prob2.knots_R[:] = [0, 0, 0, 1]
+    prob2.levels[0].xy[0] = [62.9999, 46.9999]
+    prob2.levels[0].pattern = np.array([[0, 0], [1, 1], [0, 1], [1, 0]], dtype=np.int32)
+    check_parity(O, gpu_eval(pkg, api, prob2), orc.evaluate(prob2, 0), cost_tol=1e-5, delta_tol=1.0)
+
+
+def test_multiple_frames(pkg, api, O, orc, synth):
+    """n_frames > 1 with frames in different segments (the merge of overlapping frames, test_merge…:1060-1181)."""
+    prob = synth.make_problem("frames", W=160, H=120, levels=1, P0=300, N=8, n_knots=3, k=2, seed=8, margin=14, F=2)
+    prob.dt = 1.0
+    prob.cap, prob.exp = np.array([0.5, 1.45]), np.array([0.8, 0.8])
+    check_parity(O, gpu_eval(pkg, api, prob), orc.evaluate(prob, 0))
+
+
+def test_outlier_flags_and_device_side_detection(pkg, api, O, orc, synth):
+    prob = synth.make_config("tiny")
+    lv = prob.levels[0]
+    flags = np.zeros(lv.P, dtype=np.uint8)
+    flags[5::9] = 1
+    nbad = int(flags.sum())
+    check_parity(O, gpu_eval(pkg, api, prob, flags=flags, num_bad=nbad), orc.evaluate(prob, 0, flags=flags, num_bad=nbad))
+    # detectOutliersAndUploadToGpu on the device == the restatement applied to the same patch costs
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        kt = prob.knots_t + 0.05  # a bad pose so that there is a spread of patch costs
+        c, _, _ = ctx.evaluate(0, prob.k, prob.t0, prob.dt, kt, prob.knots_R, prob.huber_a, False)
+        pc = ctx.patch_costs(0, prob.F, lv.P)
+        for k_sigma in (3.0, 1.0):
+            want_flags = np.zeros(lv.P, dtype=np.uint8)
+            want_n = O.detect_outliers(pc, want_flags, k_sigma)
+            ctx.set_outliers(0, None)
+            got_n = ctx.detect_outliers(0, k_sigma)
+            assert got_n == want_n and want_n > 0
+            # the flags took effect: the next evaluation equals the oracle's with the same flags
+            got = ctx.evaluate(0, prob.k, prob.t0, prob.dt, kt, prob.knots_R, prob.huber_a, True)
+            want = orc.evaluate(prob, 0, kt, prob.knots_R, flags=want_flags, num_bad=want_n)
+            assert abs(got[0] - want[0]) <= COST_TOL * want[0]
+            assert max_rel(got[1], want[1]) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["tiny", "C2"])
+def test_lm_loop_matches_oracle(pkg, api, O, orc, synth, name):
+    """optimizePyramidLevel (tracker.cpp:590-637) coarse to fine: same accept / reject sequence, same final knots."""
+    prob = synth.make_config(name)
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        kt, kR, summ = pkg.optimize_trajectory(ctx, prob)
+    kt_o, kR_o, traces = O.optimize_trajectory(orc, prob)
+    for s, tr in zip(summ, traces):
+        # the very first step of every level is the parity quantity
+        assert rel(s["first_step"], tr.first_step) <= DELTA_TOL
+        same = s["decisions"] == "".join(tr.decisions)
+        if same:
+            assert abs(s["final_cost"] - tr.costs[-1]) <= 1e-4 * tr.costs[-1]
+            assert s["num_bad_keypoints"] == tr.num_bad
+        else:  # a decision may differ only at a near-tie; then the final cost decides
+            assert abs(s["final_cost"] - tr.costs[-1]) <= 1e-3 * tr.costs[-1]
+    assert np.abs(kt - kt_o).max() <= 1e-4 and np.abs(kR - kR_o).max() <= 1e-5
+    if name == "C2":  # converged towards the ground-truth trajectory (plane scene)
+        assert np.abs(kt - prob.gt_knots_t).max() < np.abs(prob.knots_t - prob.gt_knots_t).max() * 5 + 0.02
+
+
+def test_deterministic_and_graph_replay(pkg, api, synth, monkeypatch):
+    """Fixed-order reductions: bit-identical results run to run, and with / without CUDA-graph replay."""
+    prob = synth.make_config("C1")
+    a = gpu_eval(pkg, api, prob)
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        runs = [gpu_eval(pkg, api, prob, ctx=ctx) for _ in range(3)]
+    for r in runs:
+        assert r[0] == a[0] and np.array_equal(r[1], a[1]) and np.array_equal(r[2], a[2]) and np.array_equal(r[3], a[3])
+    monkeypatch.setenv("MBAVO_NO_GRAPHS", "1")
+    b = gpu_eval(pkg, api, prob)
+    assert b[0] == a[0] and np.array_equal(b[1], a[1]) and np.array_equal(b[2], a[2])
+
+
+def test_error_codes(pkg, api, synth):
+    prob = synth.make_config("tiny")
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        with pytest.raises(pkg.MbavoError, match="-5"):  # MBAVO_ENOTREADY: level not set
+            ctx.evaluate(0, 2, 0.0, 1.0, prob.knots_t, prob.knots_R, 10.0)
+        api.upload_problem(ctx, prob)
+        with pytest.raises(pkg.MbavoError, match="-3"):  # MBAVO_ERANGE: exposure window leaves the spline
+            ctx.evaluate(0, 2, 0.0, 0.5, prob.knots_t, prob.knots_R, 10.0)
+        with pytest.raises(pkg.MbavoError, match="-3"):
+            ctx.evaluate(0, 2, 2.0, 1.0, prob.knots_t, prob.knots_R, 10.0)
+        with pytest.raises(pkg.MbavoError, match="-1"):  # MBAVO_EINVAL: spline order
+            ctx.evaluate(0, 3, 0.0, 1.0, prob.knots_t, prob.knots_R, 10.0)
+        big = synth.make_problem("big", W=64, H=48, levels=1, P0=prob.levels[0].P + 1, N=4, n_knots=2, seed=1, margin=10)
+        with pytest.raises(pkg.MbavoError, match="-4"):  # MBAVO_ECAPACITY
+            ctx.set_level(0, big.levels[0])
+        # the context is still usable after errors
+        assert ctx.evaluate(0, 2, prob.t0, prob.dt, prob.knots_t, prob.knots_R, 10.0)[0] > 0
+
+
+def test_full_size_properties(pkg, api, O, synth):
+    """BASELINE C3 at full size (1280x720, 80k points, 32 samples, 3 knots) through size-independent properties:
+    cost-only pass == cost of the Hessian pass; H symmetric positive semi-definite; linearity: the packed vectors of two
+    point shards (global normaliser) sum to the unsharded result; g.delta < 0 (descent direction)."""
+    import torch
+
+    prob = synth.make_config("C3", levels=1)
+    lv = prob.levels[0]
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        c, H, g = ctx.evaluate(0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, True)
+        c2, _, _ = ctx.evaluate(0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, False)
+        pc = ctx.patch_costs(0, 1, lv.P)
+    assert abs(c - c2) <= 1e-9 * c
+    assert abs(pc.sum() - c) <= 1e-9 * c          # checksum of checksums: patch costs add up to the total
+    assert np.array_equal(H, H.T) and np.linalg.eigvalsh(H).min() >= -1e-9 * np.abs(H).max()
+    d = first_step(O, H, g)
+    assert g @ d < 0
+    total = None
+    half = lv.P // 2 + 3
+    nres = lv.P * prob.F * lv.S
+    for sl in (slice(0, half), slice(half, lv.P)):
+        with pkg.Context(api.limits_for(prob)) as ctx:
+            ctx.set_frame_times(prob.cap, prob.exp)
+            ctx.set_level(0, lv, sl)
+            buf = torch.zeros(ctx.packed_len(8), dtype=torch.float64, device="cuda")
+            kmin, nk = ctx.evaluate_async(0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, True, nres,
+                                          buf.data_ptr())
+            torch.cuda.synchronize()
+            v = buf[: ctx.packed_len(nk)].cpu().numpy()
+            total = v if total is None else total + v
+            unpack = ctx.unpack
+            cs, Hs, gs = unpack(total, kmin, nk, prob.n_knots)
+    assert abs(cs - c) <= 1e-12 * c and max_rel(Hs, H) <= 1e-12 and max_rel(gs, g) <= 1e-12
+
+
+def test_sharded_evaluator_single_rank(pkg, api, synth):
+    """mbavo_b200.parallel.ShardedEvaluator with world_size 1 on a torch stream == the blocking C-ABI call."""
+    import torch
+
+    from mbavo_b200.parallel import ShardedEvaluator
+
+    prob = synth.make_config("tiny")
+    want = gpu_eval(pkg, api, prob)
+    torch.cuda.set_device(0)
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        ev = ShardedEvaluator(ctx, prob, 0, 1)
+        c, H, g = ev.evaluate(0, prob.knots_t, prob.knots_R, True)
+        c2, _, _ = ev.evaluate(0, prob.knots_t, prob.knots_R, False)
+    assert c == want[0] and np.array_equal(H, want[1]) and np.array_equal(g, want[2]) and c2 == c
