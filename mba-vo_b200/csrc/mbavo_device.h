@@ -14,7 +14,8 @@ namespace mbavo
     constexpr int kThreads = kWarpsPerBlock * 32;
 
     // One exposure sample (virtual pose) as the tracking kernel consumes it, fp32, 16-byte aligned records:
-    //   [0..8]   R      rotation matrix of the pose quaternion, row-major   (compute_virtual_camera_poses.cu:102-109)
+    //   [0..8]   R - I  rotation matrix of the pose quaternion minus identity, row-major, rounded after the
+    //                   subtraction                                              (compute_virtual_camera_poses.cu:102-109)
     //   [9..11]  t      translation
     //   [12..12+K)      wt[j]     translation blend weight of the segment's knot j        (SplineFunctor.h:30-40, 74-91)
     //   [12+K .. 12+K+9K)  Theta[j] (3x3 row-major) = d theta / d w_j, theta the right perturbation of the pose

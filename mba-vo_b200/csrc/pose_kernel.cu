@@ -277,8 +277,10 @@ namespace mbavo
             rotation_matrix(q, R);
             constexpr int REC = sample_rec_floats(K);
             float *rec = samples + (size_t)g * REC;
+            // R - I, rounded AFTER the subtraction: the tracking kernel works with the small deviation of the warp from
+            // the identity so that its fp32 reference coordinates keep ~1e-6 px accuracy (track_kernel.cu, sample_step)
             for (int e = 0; e < 9; ++e)
-                rec[e] = (float)R[e];
+                rec[e] = (float)(R[e] - ((e & 3) == 0 ? 1.0 : 0.0));
             for (int e = 0; e < 3; ++e)
                 rec[9 + e] = (float)tt[e];
             for (int j = 0; j < K; ++j)

@@ -35,7 +35,8 @@ namespace mbavo
         {
             float rx, ry;     // ray of the live pixel, (X - cx)/fx, (Y - cy)/fy (z = 1; the result is scale-invariant)
             float D;          // plane depth of the point
-            float kx, ky;     // fx / (D + 1e-8), fy / (D + 1e-8): projection with P_z == D
+            float iD;         // 1 / (D + 1e-8): projection with P_z == D        compute_pixel_intensity.h:137
+            int X, Y;         // live pixel (also the origin of the reference coordinate, see sample_step)
             float icur;       // live-image intensity at the pixel
             bool valid;       // pixel inside the live image and point slot in range
         };
@@ -49,7 +50,8 @@ namespace mbavo
             ps.valid = false;
             ps.rx = ps.ry = 0.f;
             ps.D = 1.f;
-            ps.kx = ps.ky = 0.f;
+            ps.iD = 1.f;
+            ps.X = ps.Y = 0;
             ps.icur = 0.f;
             if (p >= lv.P)
                 return ps;
@@ -70,39 +72,50 @@ namespace mbavo
             if (X < 0 || X > lv.W - 1 || Y < 0 || Y > lv.H - 1)
                 return ps;
             ps.valid = true;
+            ps.X = X, ps.Y = Y;
             ps.rx = (float)(((double)X - lv.cx) / lv.fx);
             ps.ry = (float)(((double)Y - lv.cy) / lv.fy);
             ps.D = (float)z;
-            ps.kx = (float)(lv.fx / (z + 1e-8));
-            ps.ky = (float)(lv.fy / (z + 1e-8));
+            ps.iD = (float)(1.0 / (z + 1e-8));
             ps.icur = u8_to_float(__ldg(lv.cur_I[f] + (size_t)Y * lv.W + X));
             return ps;
         }
 
         // One exposure sample of one pixel.  K knots per segment; OFF = segment offset inside the knot window.
         // Accumulates sumI and, if WITH_J, the 1 x 6NK row (Jt: translation block, Jw: rotation block).
+        //
+        // Reference coordinate.  compute_pixel_intensity.h:108-144 evaluates u = fx P_x / (D + 1e-8) + c_x in fp64 and
+        // rounds only the fractional part to fp32.  A plain fp32 evaluation of u loses ~W * 2^-24 px (4e-5 px at VGA),
+        // which is what limits the parity of H, g and the step.  Here the coordinate is evaluated RELATIVE TO THE LIVE
+        // PIXEL X:  with A = (R - I) ray (small), m = ray + A, tau = t_z / (D + 1e-8),
+        //     u - X = fx [ (A_x - r_x A_z - tau m_x) / m_z + t_x / (D + 1e-8) ]
+        // in which every term is of the size of the blur, so fp32 keeps ~1e-6 px; the integer tap is X + floor(u - X).
         template <int K, int NK, bool WITH_J, int OFF>
         __device__ __forceinline__ void sample_step(const float *__restrict__ rec, const PixelState &ps, const LevelDev &lv,
-                                                    float cxf, float cyf, float wmax, float hmax, float &sumI,
+                                                    float fxf, float fyf, float &sumI,
                                                     float (&Jt)[WITH_J ? NK : 1][3], float (&Jw)[WITH_J ? NK : 1][3])
         {
-            const float4 a0 = *reinterpret_cast<const float4 *>(rec);      // R0 R1 R2 R3
-            const float4 a1 = *reinterpret_cast<const float4 *>(rec + 4);  // R4 R5 R6 R7
-            const float4 a2 = *reinterpret_cast<const float4 *>(rec + 8);  // R8 tx ty tz
-            const float m0 = fmaf(a0.x, ps.rx, fmaf(a0.y, ps.ry, a0.z));
-            const float m1 = fmaf(a0.w, ps.rx, fmaf(a1.x, ps.ry, a1.y));
-            const float m2 = fmaf(a1.z, ps.rx, fmaf(a1.w, ps.ry, a2.x));
+            const float4 a0 = *reinterpret_cast<const float4 *>(rec);      // Rm0 Rm1 Rm2 Rm3   (Rm = R - I)
+            const float4 a1 = *reinterpret_cast<const float4 *>(rec + 4);  // Rm4 Rm5 Rm6 Rm7
+            const float4 a2 = *reinterpret_cast<const float4 *>(rec + 8);  // Rm8 tx ty tz
+            const float A0 = fmaf(a0.x, ps.rx, fmaf(a0.y, ps.ry, a0.z));
+            const float A1 = fmaf(a0.w, ps.rx, fmaf(a1.x, ps.ry, a1.y));
+            const float A2 = fmaf(a1.z, ps.rx, fmaf(a1.w, ps.ry, a2.x));
+            const float m0 = ps.rx + A0, m1 = ps.ry + A1, m2 = 1.0f + A2;
             const float il = __frcp_rn(m2);                     // 1 / lambda
-            const float s = (ps.D - a2.w) * il;                 // (D - t_z) / lambda       compute_pixel_intensity.h:128
-            const float Px = fmaf(s, m0, a2.y), Py = fmaf(s, m1, a2.z);
-            const float u = fmaf(ps.kx, Px, cxf), v = fmaf(ps.ky, Py, cyf); // :137-144 with P_z == D
-            if (!(u >= 0.f && u <= wmax && v >= 0.f && v <= hmax))
-                return; // invalid sample: contributes nothing, divisor stays N (…cost.cu:107-110)
+            const float tau = a2.w * ps.iD;
+            const float du = fxf * fmaf(fmaf(-tau, m0, fmaf(-ps.rx, A2, A0)), il, a2.y * ps.iD);
+            const float dv = fyf * fmaf(fmaf(-tau, m1, fmaf(-ps.ry, A2, A1)), il, a2.z * ps.iD);
+            // inside [0, W-1] x [0, H-1] (compute_pixel_intensity.h:35); an invalid sample contributes nothing while the
+            // divisor stays N (…cost.cu:107-110)
+            const float xf = floorf(du), yf = floorf(dv);
+            const float dx = du - xf, dy = dv - yf; // exact
+            const int xi = ps.X + (int)xf, yi = ps.Y + (int)yf;
+            if (!(xi >= 0 && yi >= 0 && (xi < lv.W - 1 || (xi == lv.W - 1 && dx == 0.f)) &&
+                  (yi < lv.H - 1 || (yi == lv.H - 1 && dy == 0.f)) && du == du && dv == dv))
+                return;
 
             // bilinear_interpolation, compute_pixel_intensity.h:40-68
-            const float xf = floorf(u), yf = floorf(v);
-            const float dx = u - xf, dy = v - yf;
-            const int xi = (int)xf, yi = (int)yf;
             const float dxdy = dx * dy;
             const float w00 = 1.0f - dx - dy + dxdy, w01 = dx - dxdy, w10 = dy - dxdy, w11 = dxdy;
             // the +1 taps carry weight 0 on the last column / row; clamp them instead of reading out of bounds
@@ -118,14 +131,15 @@ namespace mbavo
                 const float2 g10 = __ldg(lv.ref_dIxy + i10), g11 = __ldg(lv.ref_dIxy + i11);
                 const float gx = w11 * g11.x + w10 * g10.x + w01 * g01.x + w00 * g00.x;
                 const float gy = w11 * g11.y + w10 * g10.y + w01 * g01.y + w00 * g00.y;
+                const float s = (ps.D - a2.w) * il;                 // (D - t_z) / lambda       compute_pixel_intensity.h:128
                 // dI/dt = dI/dP (I - m e_z^T / lambda)                                   compute_pixel_intensity.h:196-202
-                const float gtx = gx * ps.kx, gty = gy * ps.ky;
+                const float gtx = gx * (fxf * ps.iD), gty = gy * (fyf * ps.iD);
                 const float gtz = -(gtx * m0 + gty * m1) * il;
                 // dI/dtheta = s (r x R^T dI/dt): right perturbation R <- R Exp(theta) of the pose rotation; equals
                 // dI/dq (compute_pixel_intensity.h:179-206) contracted with dq/dtheta = L(q)[I/2;0]
-                const float b0 = fmaf(a0.x, gtx, fmaf(a0.w, gty, a1.z * gtz));
-                const float b1 = fmaf(a0.y, gtx, fmaf(a1.x, gty, a1.w * gtz));
-                const float b2 = fmaf(a0.z, gtx, fmaf(a1.y, gty, a2.x * gtz));
+                const float b0 = gtx + fmaf(a0.x, gtx, fmaf(a0.w, gty, a1.z * gtz));
+                const float b1 = gty + fmaf(a0.y, gtx, fmaf(a1.x, gty, a1.w * gtz));
+                const float b2 = gtz + fmaf(a0.z, gtx, fmaf(a1.y, gty, a2.x * gtz));
                 const float v0 = s * (ps.ry * b2 - b1);
                 const float v1 = s * (b0 - ps.rx * b2);
                 const float v2 = s * (ps.rx * b1 - ps.ry * b0);
@@ -148,17 +162,17 @@ namespace mbavo
         struct SegmentLoop
         {
             __device__ __forceinline__ static void run(const float *__restrict__ samples_s, const int *__restrict__ seg_end_s,
-                                                       int &i, const PixelState &ps, const LevelDev &lv, float cxf, float cyf,
-                                                       float wmax, float hmax, float &sumI, float (&Jt)[WITH_J ? NK : 1][3],
+                                                       int &i, const PixelState &ps, const LevelDev &lv, float fxf, float fyf,
+                                                       float &sumI, float (&Jt)[WITH_J ? NK : 1][3],
                                                        float (&Jw)[WITH_J ? NK : 1][3])
             {
                 constexpr int REC = sample_rec_floats(K);
                 const int end = seg_end_s[OFF];
                 for (; i < end; ++i)
-                    sample_step<K, NK, WITH_J, OFF>(samples_s + i * REC, ps, lv, cxf, cyf, wmax, hmax, sumI, Jt, Jw);
+                    sample_step<K, NK, WITH_J, OFF>(samples_s + i * REC, ps, lv, fxf, fyf, sumI, Jt, Jw);
                 if constexpr (OFF + 1 <= NK - K)
-                    SegmentLoop<K, NK, WITH_J, (OFF + 1 <= NK - K ? OFF + 1 : OFF)>::run(samples_s, seg_end_s, i, ps, lv, cxf,
-                                                                                      cyf, wmax, hmax, sumI, Jt, Jw);
+                    SegmentLoop<K, NK, WITH_J, (OFF + 1 <= NK - K ? OFF + 1 : OFF)>::run(samples_s, seg_end_s, i, ps, lv, fxf,
+                                                                                      fyf, sumI, Jt, Jw);
             }
         };
 
@@ -224,8 +238,7 @@ namespace mbavo
             __syncthreads();
 
             const double *mid = prm.mid + f * kMidDoubles;
-            const float cxf = (float)lv.cx, cyf = (float)lv.cy;
-            const float wmax = (float)(lv.W - 1), hmax = (float)(lv.H - 1);
+            const float fxf = (float)lv.fx, fyf = (float)lv.fy;
             const float inv_N = 1.0f / (float)N;
             const float huber_a = prm.stage->huber_a;
             const double inv_num_residuals = prm.stage->inv_num_residuals;
@@ -260,12 +273,12 @@ namespace mbavo
                         if constexpr (WITH_J)
                         {
                             int i = 0;
-                            SegmentLoop<K, NK, true, 0>::run(samples_s, seg_end_s, i, ps, lv, cxf, cyf, wmax, hmax, sumI, Jt, Jw);
+                            SegmentLoop<K, NK, true, 0>::run(samples_s, seg_end_s, i, ps, lv, fxf, fyf, sumI, Jt, Jw);
                         }
                         else
                         {
                             for (int i = 0; i < N; ++i) // cost only: the segment of a sample is irrelevant
-                                sample_step<K, NK, false, 0>(samples_s + i * REC, ps, lv, cxf, cyf, wmax, hmax, sumI, Jt, Jw);
+                                sample_step<K, NK, false, 0>(samples_s + i * REC, ps, lv, fxf, fyf, sumI, Jt, Jw);
                         }
                     }
 
