@@ -153,13 +153,18 @@ def run_reference(args, pkg):
 # own arm
 # ----------------------------------------------------------------------------------------------------------------
 def gpu_step(ctx, prob, lib_ctx_eval, solve, plus):
+    """One GN iteration per pyramid level, coarse to fine.  Single GPU: the whole iteration is one C-ABI call
+    (mbavo_gn_iteration).  Point-sharded: the same sequence with the NCCL all-reduce between kernel and solve."""
     kt, kR = prob.knots_t, prob.knots_R
     out = None
     for level in reversed(range(len(prob.levels))):
-        c, H, g = lib_ctx_eval(level, kt, kR, True)
-        step, model = solve(H, g, 1e4)
-        ct, cR = plus(kt, kR, step)
-        c2, _, _ = lib_ctx_eval(level, ct, cR, False)
+        if lib_ctx_eval is None:
+            c, c2, _, _, _ = ctx.gn_iteration(level, prob.k, prob.t0, prob.dt, kt, kR, prob.huber_a, 1e4)
+        else:
+            c, H, g = lib_ctx_eval(level, kt, kR, True)
+            step, model = solve(H, g, 1e4)
+            ct, cR = plus(kt, kR, step)
+            c2, _, _ = lib_ctx_eval(level, ct, cR, False)
         out = (c, c2)
     return out
 
@@ -254,7 +259,7 @@ def run_own(args, pkg):
             e0.record(stream)
             if with_upload:
                 upload_all()
-            gpu_step(ctx, prob, evaluate, solve, plus)
+            gpu_step(ctx, prob, evaluate if world > 1 else None, solve, plus)
             e1.record(stream)
             torch.cuda.synchronize(dev)
             total += e0.elapsed_time(e1)

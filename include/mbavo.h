@@ -170,6 +170,15 @@ int mbavo_trust_region_step(double *hessian, const double *gradient, int dim, do
 int mbavo_spline_plus(int num_ctrl_knots, const double *knots_t, const double *knots_R, const double *step,
                       double *cand_t, double *cand_R);
 
+/* One Gauss-Newton / LM iteration of optimizePyramidLevel (blur_aware_direct_tracker.cpp:609-637) without the
+ * accept / reject bookkeeping: Hessian pass at the knots -> computeTrustRegionStep at `radius` -> Plus_t / Plus_R ->
+ * cost-only pass at the candidate.  step_out (6n), cand_t (3n), cand_R (4n) may be NULL.  This is the benchmark's unit
+ * of work ("GN iteration"). */
+int mbavo_gn_iteration(mbavo_ctx *ctx, int level, int spline_deg_k, double start_time, double sample_dt,
+                       int num_ctrl_knots, const double *knots_t, const double *knots_R, double radius, double huber_a,
+                       int solver_type, double *cost, double *candidate_cost, double *step_out, double *cand_t,
+                       double *cand_R);
+
 typedef struct mbavo_lm_options
 {
     int max_num_iterations;                 /* 50   blur_aware_direct_tracker.h:39 */
@@ -207,6 +216,11 @@ int mbavo_optimize_level(mbavo_ctx *ctx, int level, int spline_deg_k, double sta
 
 /* Number of kernels this library has launched on behalf of ctx since creation (graph replays counted per node) */
 long long mbavo_kernel_launches(const mbavo_ctx *ctx);
+
+/* 1 if the kernels of `level` read the keyframe through the packed fp16 texels built by mbavo_set_level (every
+ * gradient value exactly representable in fp16 — always the case for Gradient.h's central differences of an 8-bit
+ * image), 0 if they gather ref_I / ref_dIxy directly, -1 if the level is not set.  Results are identical either way. */
+int mbavo_level_uses_texels(const mbavo_ctx *ctx, int level);
 
 /* Device time in milliseconds of the tracking kernel of the last mbavo_evaluate* call on `level` (CUDA events
  * recorded around that kernel on the context's stream); < 0 if timing is disabled. */

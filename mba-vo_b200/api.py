@@ -20,8 +20,8 @@ EXPORTED_SYMBOLS = [
     "mbavo_last_error", "mbavo_version", "mbavo_create", "mbavo_destroy", "mbavo_set_stream", "mbavo_set_frame_times",
     "mbavo_set_level", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
-    "mbavo_spline_plus", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
-    "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms",
+    "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
+    "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels",
 ]
 
 
@@ -73,7 +73,8 @@ class Limits:
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "lib", "libmbavo_b200.so")
+    """lib/libmbavo_b200.so; MBAVO_LIBRARY selects another build of the same sources (kernel-tuning experiments)."""
+    return os.environ.get("MBAVO_LIBRARY") or os.path.join(_HERE, "lib", "libmbavo_b200.so")
 
 
 _LIB = None
@@ -249,6 +250,17 @@ class Context:
         self._check(self.lib.mbavo_spline_plus(C.c_int(n), _dp(kt), _dp(kR), _dp(st), _dp(ct), _dp(cR)))
         return ct, cR
 
+    def gn_iteration(self, level: int, k: int, t0: float, dt: float, knots_t, knots_R, huber_a: float, radius: float = 1e4,
+                     solver_type: int = SOLVER_SVD_JACOBI):
+        """mbavo_gn_iteration -> (cost, candidate_cost, step, cand_t, cand_R)."""
+        sp, kt, kR, n = self._spline(k, t0, dt, knots_t, knots_R)
+        cost, cand = C.c_double(0), C.c_double(0)
+        step, ct, cR = np.zeros(6 * n), np.zeros((n, 3)), np.zeros((n, 4))
+        self._check(self.lib.mbavo_gn_iteration(self._h, C.c_int(level), C.c_int(k), C.c_double(t0), C.c_double(dt), C.c_int(n),
+                                                _dp(kt), _dp(kR), C.c_double(radius), C.c_double(huber_a), C.c_int(solver_type),
+                                                C.byref(cost), C.byref(cand), _dp(step), _dp(ct), _dp(cR)))
+        return cost.value, cand.value, step, ct, cR
+
     def optimize_level(self, level: int, k: int, t0: float, dt: float, knots_t, knots_R, huber_a: float = 10.0,
                        max_chi_square_error: float = 3.0, solver_type: int = SOLVER_SVD_JACOBI, **overrides):
         """mbavo_optimize_level -> (knots_t, knots_R, summary dict)."""
@@ -271,6 +283,9 @@ class Context:
     # -- introspection ----------------------------------------------------------------------------------------
     def kernel_launches(self) -> int:
         return int(self.lib.mbavo_kernel_launches(self._h))
+
+    def level_uses_texels(self, level: int) -> int:
+        return int(self.lib.mbavo_level_uses_texels(self._h, C.c_int(level)))
 
     def enable_kernel_timing(self, on: bool):
         self._check(self.lib.mbavo_enable_kernel_timing(self._h, C.c_int(1 if on else 0)))

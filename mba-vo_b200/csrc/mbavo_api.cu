@@ -21,6 +21,8 @@ namespace mbavo
     cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, dim3 grid, size_t smem,
                                     cudaStream_t stream, int *query_occupancy);
     size_t track_kernel_smem_bytes(int K, int NK, bool with_j, int N, int S, int TP);
+    cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,
+                                   int *inexact, cudaStream_t stream);
 } // namespace mbavo
 
 using namespace mbavo;
@@ -58,6 +60,10 @@ namespace
         double *xy = nullptr, *z = nullptr;
         size_t cap_pix = 0, cap_pts = 0; // capacities of the owned buffers (pixels per image, points)
         int cap_frames = 0;
+        // keyframe texels (LevelDev::ref_pair / ref_quad), rebuilt by every mbavo_set_level
+        uint4 *tex_pair = nullptr;
+        unsigned int *tex_quad = nullptr;
+        size_t cap_tex = 0;
         // always owned
         int2 *pattern = nullptr;
         unsigned char *flags = nullptr;
@@ -103,6 +109,10 @@ struct mbavo_ctx
 
     std::map<GraphKey, cudaGraphExec_t> graphs;
     bool use_graphs = true;
+    bool use_texels = true;  // MBAVO_NO_TEXELS=1: always gather ref_I / ref_dIxy directly
+    int force_phases = 0;    // MBAVO_PHASES=n: override the exposure-phase split (development / tests)
+    int phase_fast = 0;      // MBAVO_PHASE_FAST=1: phase-fastest lane order
+    int *inexact_dev = nullptr, *inexact_host = nullptr;
 
     long long launches = 0;
     bool timing = false;
@@ -241,7 +251,7 @@ namespace
 
     struct EvalPlan
     {
-        int K, NK, kmin, N, F, P, S, TP, batches_per_frame;
+        int K, NK, kmin, N, F, P, S, TP, PH, batches_per_frame;
         bool with_h;
         dim3 grid;
         size_t smem;
@@ -288,12 +298,23 @@ namespace
         pl.E = with_h ? packed_len(pl.NK) : 1;
         pl.TP = 32 / pl.S > 0 ? 32 / pl.S : 1;
         pl.batches_per_frame = (pl.P + pl.TP - 1) / pl.TP;
+        // lanes of a warp = PH exposure phases x 32/PH pixel slots.  PH = 1 (lane = pixel, samples walked sequentially in
+        // registers) measured fastest on every BASELINE config (profiles/r1c_variants.md); MBAVO_PHASES overrides it.
+        pl.PH = 1;
+        if (ctx->force_phases > 0)
+        {
+            pl.PH = ctx->force_phases;
+            while (pl.PH > pl.N)
+                pl.PH >>= 1;
+        }
         pl.smem = track_kernel_smem_bytes(pl.K, pl.NK, with_h, pl.N, pl.S, pl.TP);
         if (pl.smem > 200 * 1024)
             return fail(MBAVO_ECAPACITY, "shared memory need %zu B exceeds 200 KiB (N=%d, S=%d, window=%d)", pl.smem, pl.N, pl.S,
                         pl.NK);
         int occ = 1;
-        cudaError_t e = launch_track_kernel(pl.K, pl.NK, with_h, TrackParams{}, dim3(), pl.smem, nullptr, &occ);
+        TrackParams query{};
+        query.lv = L.dev; // selects the texel / direct-gather instantiation
+        cudaError_t e = launch_track_kernel(pl.K, pl.NK, with_h, query, dim3(), pl.smem, nullptr, &occ);
         if (e != cudaSuccess)
             return fail(MBAVO_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e));
         int want = (pl.batches_per_frame + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -326,6 +347,8 @@ namespace
         prm.seg_end = ctx->seg_end;
         prm.stage = ctx->stage_dev;
         prm.TP = pl.TP;
+        prm.PH = pl.PH;
+        prm.phase_fast = ctx->phase_fast;
         prm.batches_per_frame = pl.batches_per_frame;
         prm.block_partials = ctx->block_partials;
         prm.counter = ctx->counter;
@@ -439,8 +462,21 @@ extern "C"
         CUDA_TRY(cudaMallocHost(&ctx->outlier_result_host, sizeof(int) * 4));
         CUDA_TRY(cudaEventCreate(&ctx->ev0));
         CUDA_TRY(cudaEventCreate(&ctx->ev1));
+        CUDA_TRY(cudaMalloc(&ctx->inexact_dev, sizeof(int)));
+        CUDA_TRY(cudaMallocHost(&ctx->inexact_host, sizeof(int)));
         const char *g = getenv("MBAVO_NO_GRAPHS");
         ctx->use_graphs = !(g && g[0] == '1');
+        g = getenv("MBAVO_NO_TEXELS");
+        ctx->use_texels = !(g && g[0] == '1');
+        g = getenv("MBAVO_PHASE_FAST");
+        ctx->phase_fast = (g && g[0] == '1') ? 1 : 0;
+        g = getenv("MBAVO_PHASES");
+        if (g)
+        {
+            const int ph = atoi(g);
+            if (ph == 1 || ph == 2 || ph == 4 || ph == 8 || ph == 16 || ph == 32)
+                ctx->force_phases = ph;
+        }
         *out = ctx;
         return MBAVO_OK;
     }
@@ -458,7 +494,11 @@ extern "C"
             cudaFree(L.pattern);
             cudaFree(L.flags);
             cudaFree(L.patch_cost);
+            cudaFree(L.tex_pair);
+            cudaFree(L.tex_quad);
         }
+        cudaFree(ctx->inexact_dev);
+        cudaFreeHost(ctx->inexact_host);
         cudaFreeHost(ctx->stage_host);
         cudaFree(ctx->stage_dev);
         cudaFree(ctx->samples);
@@ -578,6 +618,29 @@ extern "C"
         }
         for (int f = F; f < kMaxFrames; ++f)
             L.dev.cur_I[f] = nullptr;
+        // keyframe texels: built from the device copies on every call (the caller may have changed the image content
+        // behind an unchanged pointer); kept only if every gradient value survives the fp16 round trip
+        L.dev.ref_pair = nullptr, L.dev.ref_quad = nullptr;
+        if (ctx->use_texels && npix < (size_t)1 << 27)
+        {
+            if (L.cap_tex < npix)
+            {
+                cudaFree(L.tex_pair);
+                cudaFree(L.tex_quad);
+                L.tex_pair = nullptr, L.tex_quad = nullptr, L.cap_tex = 0;
+                CUDA_TRY(cudaMalloc(&L.tex_pair, npix * sizeof(uint4)));
+                CUDA_TRY(cudaMalloc(&L.tex_quad, npix * sizeof(unsigned int)));
+                L.cap_tex = npix;
+            }
+            CUDA_TRY(cudaMemsetAsync(ctx->inexact_dev, 0, sizeof(int), s));
+            CUDA_TRY(launch_pack_kernel(L.dev.ref_I, reinterpret_cast<const float *>(L.dev.ref_dIxy), d->H, d->W, L.tex_pair,
+                                        L.tex_quad, ctx->inexact_dev, s));
+            ctx->launches += 1;
+            CUDA_TRY(cudaMemcpyAsync(ctx->inexact_host, ctx->inexact_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            if (*ctx->inexact_host == 0)
+                L.dev.ref_pair = L.tex_pair, L.dev.ref_quad = L.tex_quad;
+        }
         CUDA_TRY(cudaMemcpyAsync(L.pattern, d->pattern_xy, sizeof(int2) * d->patch_size, cudaMemcpyDefault, s));
         if (!d->ext_outlier_flags)
         {
@@ -750,6 +813,13 @@ extern "C"
     }
 
     long long mbavo_kernel_launches(const mbavo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+    int mbavo_level_uses_texels(const mbavo_ctx *ctx, int level)
+    {
+        if (!ctx || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
+            return -1;
+        return ctx->levels[level].dev.ref_pair != nullptr ? 1 : 0;
+    }
 
     int mbavo_enable_kernel_timing(mbavo_ctx *ctx, int enable)
     {

@@ -41,10 +41,20 @@ namespace mbavo
         int seg_idx[kMaxFrames * 64]; // host-computed segment start knot of every sample (authoritative)
     };
 
+    // Keyframe texels, built once per mbavo_set_level by pack_kernel (track_kernel.cu) from ref_I / ref_dIxy when every
+    // gradient value is exactly representable in fp16 (always true for Gradient.h's 0.5 * central differences of an
+    // 8-bit image: multiples of 0.5 up to 127.5).  They carry bit-identical values in a gather-friendly layout:
+    //   pair texel (16 B per pixel): 8 halves  I(x,y) gx(x,y) gy(x,y) I(x+1,y) gx(x+1,y) gy(x+1,y) 0 0
+    //                                — one 128-bit load per image ROW of the bilinear footprint instead of 2 + 2 loads
+    //   quad texel (4 B per pixel):  bytes     I(x,y) I(x+1,y) I(x,y+1) I(x+1,y+1)
+    //                                — the whole footprint of a cost-only sample in one 32-bit load
+    // x+1 / y+1 are clamped to the last column / row (those taps have weight 0 there).
     struct LevelDev
     {
         const unsigned char *ref_I;
         const float2 *ref_dIxy;
+        const uint4 *ref_pair;        // nullptr: gradients not fp16-exact -> the kernels gather ref_I / ref_dIxy directly
+        const unsigned int *ref_quad;
         const unsigned char *cur_I[kMaxFrames];
         int H, W;
         double fx, fy, cx, cy;
@@ -66,6 +76,8 @@ namespace mbavo
         const int *seg_end;       // [F * kMaxSegments]: one past the last sample index of every segment offset
         const EvalStage *stage;   // huber_a and inv_num_residuals live here so that launch parameters never change
         int TP;                   // points per warp batch
+        int PH;                   // exposure-sample phases per pixel: the 32 lanes of a warp are PH phases x 32/PH pixels
+        int phase_fast;           // lane = slot * PH + phase instead of phase * (32/PH) + slot
         int batches_per_frame;
         double *block_partials;   // [gridDim.x * gridDim.y * E]
         unsigned int *counter;    // last-block-done ticket

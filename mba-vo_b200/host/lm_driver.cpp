@@ -287,6 +287,35 @@ extern "C"
         opt->huber_a = 10.0;
     }
 
+    int mbavo_gn_iteration(mbavo_ctx *ctx, int level, int k, double t0, double dt, int n, const double *knots_t,
+                           const double *knots_R, double radius, double huber_a, int solver_type, double *cost,
+                           double *candidate_cost, double *step_out, double *cand_t, double *cand_R)
+    {
+        if (!ctx || !knots_t || !knots_R || !cost || !candidate_cost || n < 2 || n > 16)
+            return MBAVO_EINVAL;
+        const int dim = 6 * n;
+        double H[96 * 96], g[96], step[96], ct[3 * 16], cR[4 * 16], model = 0;
+        mbavo_spline sp{k, t0, dt, n, knots_t, knots_R};
+        int rc = mbavo_evaluate(ctx, level, &sp, huber_a, cost, H, g);
+        if (rc != MBAVO_OK)
+            return rc;
+        rc = mbavo_trust_region_step(H, g, dim, radius, solver_type, step, &model);
+        if (rc != MBAVO_OK)
+            return rc;
+        mbavo_spline_plus(n, knots_t, knots_R, step, ct, cR);
+        mbavo_spline cand{k, t0, dt, n, ct, cR};
+        rc = mbavo_evaluate(ctx, level, &cand, huber_a, candidate_cost, nullptr, nullptr);
+        if (rc != MBAVO_OK)
+            return rc;
+        if (step_out)
+            std::memcpy(step_out, step, sizeof(double) * dim);
+        if (cand_t)
+            std::memcpy(cand_t, ct, sizeof(double) * 3 * n);
+        if (cand_R)
+            std::memcpy(cand_R, cR, sizeof(double) * 4 * n);
+        return MBAVO_OK;
+    }
+
     int mbavo_optimize_level(mbavo_ctx *ctx, int level, int k, double t0, double dt, int n, double *knots_t, double *knots_R,
                              const mbavo_lm_options *opt, mbavo_lm_summary *sum)
     {

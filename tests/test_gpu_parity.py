@@ -126,6 +126,44 @@ def test_image_borders_and_invalid_samples(pkg, api, O, orc, synth):
     check_parity(O, gpu_eval(pkg, api, prob2), orc.evaluate(prob2, 0), cost_tol=1e-5, delta_tol=1.0)
 
 
+def test_keyframe_texels_and_direct_gather(pkg, api, O, orc, synth, monkeypatch):
+    """mbavo_set_level packs the keyframe into fp16 texels when every gradient value survives the fp16 round trip (always
+    for Gradient.h's central differences); the kernels then read bit-identical values through fewer, wider loads.  A
+    gradient image that fp16 cannot hold exactly makes the same kernels gather ref_I / ref_dIxy directly."""
+    prob = synth.make_config("C1")
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        assert ctx.level_uses_texels(0) == 1
+        a = gpu_eval(pkg, api, prob, ctx=ctx)
+        a_cost = gpu_eval(pkg, api, prob, ctx=ctx, with_hessian=False)[0]
+    monkeypatch.setenv("MBAVO_NO_TEXELS", "1")
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        assert ctx.level_uses_texels(0) == 0
+        b = gpu_eval(pkg, api, prob, ctx=ctx)
+        b_cost = gpu_eval(pkg, api, prob, ctx=ctx, with_hessian=False)[0]
+    monkeypatch.delenv("MBAVO_NO_TEXELS")
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert abs(a_cost - b_cost) <= 1e-7 * b_cost  # same tap values; only the FMA contraction of the blend may differ
+    # a gradient image fp16 cannot hold: scaled by 1/3
+    prob.levels[0].ref_dIxy = (prob.levels[0].ref_dIxy / np.float32(3.0)).astype(np.float32)
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        assert ctx.level_uses_texels(0) == 0
+        check_parity(O, gpu_eval(pkg, api, prob, ctx=ctx), orc.evaluate(prob, 0))
+
+
+@pytest.mark.parametrize("phases", [2, 4, 8, 32])
+def test_exposure_phase_split(pkg, api, O, orc, synth, monkeypatch, phases):
+    """MBAVO_PHASES: the lanes of a warp split into exposure phases x pixel slots (partial sums combined by warp shuffles)."""
+    monkeypatch.setenv("MBAVO_PHASES", str(phases))
+    for name in ("tiny", "C5cubic"):
+        prob = synth.make_config(name)
+        check_parity(O, gpu_eval(pkg, api, prob), orc.evaluate(prob, 0))
+        c2 = gpu_eval(pkg, api, prob, with_hessian=False)[0]
+        assert abs(c2 - orc.evaluate(prob, 0, with_hessian=False)[0]) <= COST_TOL * c2
+
+
 def test_multiple_frames(pkg, api, O, orc, synth):
     """n_frames > 1 with frames in different segments (the merge of overlapping frames, test_merge…:1060-1181)."""
     prob = synth.make_problem("frames", W=160, H=120, levels=1, P0=300, N=8, n_knots=3, k=2, seed=8, margin=14, F=2)
