@@ -6,8 +6,8 @@
  * 0 on success and a negative MBAVO_E* code otherwise, never throw and never exit; mbavo_last_error() returns a
  * thread-local description of the last failure.
  *
- * A context (mbavo_ctx) owns all device scratch, pinned result buffers, one CUDA stream and the captured CUDA
- * graphs of one logical tracker on one GPU; it is not thread-safe.  Calls are blocking like the reference's
+ * A context (mbavo_ctx) owns all device scratch, the mapped pinned result buffer and one CUDA stream of one logical
+ * tracker on one GPU; it is not thread-safe.  Calls are blocking like the reference's
  * (results are valid on return) unless named *_async.
  *
  * Unknown ordering everywhere: [dt_0 .. dt_{n-1}, dw_0 .. dw_{n-1}] (merge_hessian_gradient_cost.cpp:52-62), rotations
@@ -139,7 +139,7 @@ int mbavo_patch_costs(mbavo_ctx *ctx, int level, double *out);
  * number of patches flagged by THIS call and becomes the level's num_bad_keypoints. */
 int mbavo_detect_outliers(mbavo_ctx *ctx, int level, double max_chi_square_error, int *num_bad_keypoints);
 
-/* ---- device-resident variants (multi-GPU plumbing, CUDA-graph friendly) ------------------------------------ */
+/* ---- device-resident variants (multi-GPU plumbing) ----------------------------------------------------------- */
 
 /* Length of the packed window vector [cost, g(6 NK), triu(H) row-major] for a knot window of NK knots */
 int mbavo_packed_len(int knot_window);
@@ -214,7 +214,7 @@ int mbavo_optimize_level(mbavo_ctx *ctx, int level, int spline_deg_k, double sta
 
 /* ---- introspection for benchmarks ---------------------------------------------------------------------------- */
 
-/* Number of kernels this library has launched on behalf of ctx since creation (graph replays counted per node) */
+/* Number of kernels this library has launched on behalf of ctx since creation */
 long long mbavo_kernel_launches(const mbavo_ctx *ctx);
 
 /* 1 if the kernels of `level` read the keyframe through the packed fp16 texels built by mbavo_set_level (every

@@ -1,22 +1,23 @@
 // C-ABI of the hot path (include/mbavo.h): context, level storage, evaluation orchestration.
 // Host side of evaluate_cost_hessian_gradient (src/ba_tracker/spline_update_step.cpp:97-349) re-designed:
 //   reference: 2 blocking H2D + 5 launches each followed by cudaDeviceSynchronize + 1 blocking D2H per evaluation
-//   here:      1 async H2D (pinned staging block) + pose kernel + fused tracking kernel + 1 async D2H (pinned),
-//              one stream, one synchronisation at the end; the sequence is replayed as a CUDA graph.
+//   here:      pose kernel (the spline state travels as its launch parameter: no H2D copy) + fused tracking kernel whose
+//              last block stores [cost, g, triu(H)] straight into mapped pinned host memory and publishes a sequence
+//              number the host spins on: no D2H copy, no stream synchronisation, 2 launches per evaluation.
 #include "../../include/mbavo.h"
 #include "mbavo_device.h"
 
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
-#include <map>
-#include <tuple>
 #include <vector>
 
 namespace mbavo
 {
-    cudaError_t launch_pose_kernel(int K, const EvalStage *stage_dev, int total_samples, int with_jacobian, float *samples,
+    cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
                                    double *mid, int *seg_end, cudaStream_t stream);
     cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, dim3 grid, size_t smem,
                                     cudaStream_t stream, int *query_occupancy);
@@ -72,16 +73,6 @@ namespace
         int last_eval_frames = 0;
     };
 
-    struct GraphKey
-    {
-        int level, K, NK, with_h, N, F, P, S;
-        unsigned long long gen; // level generation (pointers may change on set_level)
-        bool operator<(const GraphKey &o) const
-        {
-            return std::tie(level, K, NK, with_h, N, F, P, S, gen) <
-                   std::tie(o.level, o.K, o.NK, o.with_h, o.N, o.F, o.P, o.S, o.gen);
-        }
-    };
 } // namespace
 
 struct mbavo_ctx
@@ -95,24 +86,31 @@ struct mbavo_ctx
     int n_frames_times = 0;
 
     LevelStore levels[MBAVO_MAX_LEVELS];
-    unsigned long long level_gen[MBAVO_MAX_LEVELS] = {};
 
-    EvalStage *stage_host = nullptr, *stage_dev = nullptr; // pinned / device
+    EvalStage stage{};       // spline state of the evaluation being issued (launch parameter of the pose kernel)
     float *samples = nullptr;
     double *mid = nullptr;
     int *seg_end = nullptr;
     double *block_partials = nullptr;
     size_t block_partials_cap = 0;
     unsigned int *counter = nullptr;
-    double *packed_dev = nullptr, *packed_host = nullptr; // E_max doubles, device / pinned
+    double *packed_dev = nullptr;                          // E_max doubles, device
+    double *result_host = nullptr, *result_map = nullptr;  // E_max doubles + sequence word: mapped pinned memory (host / device view)
+    unsigned long long seq = 0;
     int *outlier_result_dev = nullptr, *outlier_result_host = nullptr;
 
-    std::map<GraphKey, cudaGraphExec_t> graphs;
-    bool use_graphs = true;
     bool use_texels = true;  // MBAVO_NO_TEXELS=1: always gather ref_I / ref_dIxy directly
     int force_phases = 0;    // MBAVO_PHASES=n: override the exposure-phase split (development / tests)
     int phase_fast = 0;      // MBAVO_PHASE_FAST=1: phase-fastest lane order
     int *inexact_dev = nullptr, *inexact_host = nullptr;
+
+    struct OccEntry
+    {
+        int K, NK, with_h, packed;
+        size_t smem;
+        int occ;
+    };
+    std::vector<OccEntry> occ_cache;
 
     long long launches = 0;
     bool timing = false;
@@ -157,20 +155,6 @@ namespace
         L.ref_I = nullptr, L.ref_dIxy = nullptr, L.xy = nullptr, L.z = nullptr;
         L.cap_pix = L.cap_pts = 0, L.cap_frames = 0;
         L.owns = false;
-    }
-
-    void drop_graphs(mbavo_ctx *ctx, int level)
-    {
-        for (auto it = ctx->graphs.begin(); it != ctx->graphs.end();)
-        {
-            if (level < 0 || it->first.level == level)
-            {
-                cudaGraphExecDestroy(it->second);
-                it = ctx->graphs.erase(it);
-            }
-            else
-                ++it;
-        }
     }
 
     // detectOutliersAndUploadToGpu (blur_aware_direct_tracker.cpp:650-698) on the device: one block, fixed-order tree sums.
@@ -277,7 +261,8 @@ namespace
         pl.N = L.dev.N, pl.F = L.dev.F, pl.P = L.dev.P, pl.S = L.dev.S;
         pl.with_h = with_h;
 
-        EvalStage *st = ctx->stage_host;
+        EvalStage *st = &ctx->stage;
+        int seg[kMaxFrames * 64];
         int lo = 1 << 30, hi = -(1 << 30);
         for (int f = 0; f < pl.F; ++f)
             for (int i = 0; i < pl.N; ++i)
@@ -286,12 +271,14 @@ namespace
                 if (idx < 0 || idx + pl.K > sp->num_ctrl_knots)
                     return fail(MBAVO_ERANGE, "frame %d sample %d lies in segment %d, outside the %d control knots", f, i, idx,
                                 sp->num_ctrl_knots);
-                st->seg_idx[f * pl.N + i] = idx;
+                seg[f * pl.N + i] = idx;
                 lo = idx < lo ? idx : lo;
                 hi = idx > hi ? idx : hi;
             }
         pl.kmin = lo;
         pl.NK = hi - lo + pl.K;
+        for (int e = 0; e < pl.F * pl.N; ++e)
+            st->seg_off[e] = (unsigned char)(seg[e] - lo);
         if (pl.NK > MBAVO_MAX_KNOT_WINDOW || (pl.K == 2 && pl.NK > 6) || (pl.K == 4 && pl.NK > 7))
             return fail(MBAVO_ECAPACITY, "exposure windows touch %d control knots; at most %d are supported for k=%d", pl.NK,
                         pl.K == 2 ? 6 : 7, pl.K);
@@ -311,19 +298,27 @@ namespace
         if (pl.smem > 200 * 1024)
             return fail(MBAVO_ECAPACITY, "shared memory need %zu B exceeds 200 KiB (N=%d, S=%d, window=%d)", pl.smem, pl.N, pl.S,
                         pl.NK);
-        int occ = 1;
-        TrackParams query{};
-        query.lv = L.dev; // selects the texel / direct-gather instantiation
-        cudaError_t e = launch_track_kernel(pl.K, pl.NK, with_h, query, dim3(), pl.smem, nullptr, &occ);
-        if (e != cudaSuccess)
-            return fail(MBAVO_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+        int occ = 0;
+        const int packed = L.dev.ref_pair != nullptr ? 1 : 0;
+        for (const auto &c : ctx->occ_cache)
+            if (c.K == pl.K && c.NK == pl.NK && c.with_h == (with_h ? 1 : 0) && c.packed == packed && c.smem == pl.smem)
+                occ = c.occ;
+        if (occ == 0)
+        {
+            TrackParams query{};
+            query.lv = L.dev; // selects the texel / direct-gather instantiation
+            cudaError_t e = launch_track_kernel(pl.K, pl.NK, with_h, query, dim3(), pl.smem, nullptr, &occ);
+            if (e != cudaSuccess)
+                return fail(MBAVO_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+            ctx->occ_cache.push_back({pl.K, pl.NK, with_h ? 1 : 0, packed, pl.smem, occ});
+        }
         int want = (pl.batches_per_frame + kWarpsPerBlock - 1) / kWarpsPerBlock;
         int cap_blocks = ctx->num_sms * occ / pl.F;
         if (cap_blocks < 1)
             cap_blocks = 1;
         pl.grid = dim3(want < cap_blocks ? want : cap_blocks, pl.F, 1);
 
-        // staging block
+        // spline state (launch parameter of the pose kernel)
         std::memcpy(st->knots_t, sp->knots_t, sizeof(double) * 3 * sp->num_ctrl_knots);
         std::memcpy(st->knots_R, sp->knots_R, sizeof(double) * 4 * sp->num_ctrl_knots);
         std::memcpy(st->cap, ctx->cap, sizeof(double) * pl.F);
@@ -333,44 +328,17 @@ namespace
         return MBAVO_OK;
     }
 
-    // Enqueue H2D(stage) -> pose kernel -> tracking kernel [-> D2H(packed)] on ctx->stream (direct or under capture).
-    int enqueue_evaluation(mbavo_ctx *ctx, int level, const EvalPlan &pl, double *packed_dev_out, bool copy_back)
+    // pose kernel -> tracking kernel on ctx->stream.  blocking: the tracking kernel also publishes the result into the
+    // context's mapped pinned buffer under a fresh sequence number (wait_result picks it up).
+    int run_evaluation(mbavo_ctx *ctx, int level, const EvalPlan &pl, double *packed_dev_out, bool blocking, double inv_num_residuals,
+                       double huber_a)
     {
         LevelStore &L = ctx->levels[level];
         cudaStream_t s = ctx->stream;
-        CUDA_TRY(cudaMemcpyAsync(ctx->stage_dev, ctx->stage_host, sizeof(EvalStage), cudaMemcpyHostToDevice, s));
-        CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage_dev, pl.N * pl.F, pl.with_h ? 1 : 0, ctx->samples, ctx->mid, ctx->seg_end, s));
-        TrackParams prm{};
-        prm.lv = L.dev;
-        prm.samples = ctx->samples;
-        prm.mid = ctx->mid;
-        prm.seg_end = ctx->seg_end;
-        prm.stage = ctx->stage_dev;
-        prm.TP = pl.TP;
-        prm.PH = pl.PH;
-        prm.phase_fast = ctx->phase_fast;
-        prm.batches_per_frame = pl.batches_per_frame;
-        prm.block_partials = ctx->block_partials;
-        prm.counter = ctx->counter;
-        prm.packed_out = packed_dev_out;
-        if (ctx->timing)
-            CUDA_TRY(cudaEventRecord(ctx->ev0, s));
-        CUDA_TRY(launch_track_kernel(pl.K, pl.NK, pl.with_h, prm, pl.grid, pl.smem, s, nullptr));
-        if (ctx->timing)
-            CUDA_TRY(cudaEventRecord(ctx->ev1, s));
-        if (copy_back)
-            CUDA_TRY(cudaMemcpyAsync(ctx->packed_host, packed_dev_out, sizeof(double) * pl.E, cudaMemcpyDeviceToHost, s));
-        return MBAVO_OK;
-    }
-
-    int run_evaluation(mbavo_ctx *ctx, int level, const EvalPlan &pl, double *packed_dev_out, bool copy_back)
-    {
-        LevelStore &L = ctx->levels[level];
         size_t need = (size_t)pl.grid.x * pl.grid.y * pl.E;
         if (need > ctx->block_partials_cap)
         {
-            drop_graphs(ctx, -1);
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(s));
             cudaFree(ctx->block_partials);
             ctx->block_partials = nullptr;
             CUDA_TRY(cudaMalloc(&ctx->block_partials, need * sizeof(double)));
@@ -378,35 +346,59 @@ namespace
         }
         L.last_eval_frames = pl.F;
         ctx->launches += 2;
-        // graphs only for the blocking path with the context's own buffers (fixed addresses) and without event timing
-        const bool graphable = ctx->use_graphs && !ctx->timing && packed_dev_out == ctx->packed_dev && copy_back;
-        if (!graphable)
-            return enqueue_evaluation(ctx, level, pl, packed_dev_out, copy_back);
-
-        GraphKey key{level, pl.K, pl.NK, pl.with_h ? 1 : 0, pl.N, pl.F, pl.P, pl.S, ctx->level_gen[level]};
-        auto it = ctx->graphs.find(key);
-        if (it == ctx->graphs.end())
+        CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, pl.with_h ? 1 : 0, ctx->samples, ctx->mid, ctx->seg_end, s));
+        TrackParams prm{};
+        prm.lv = L.dev;
+        prm.samples = ctx->samples;
+        prm.mid = ctx->mid;
+        prm.seg_end = ctx->seg_end;
+        prm.inv_num_residuals = inv_num_residuals;
+        prm.huber_a = (float)huber_a;
+        prm.TP = pl.TP;
+        prm.PH = pl.PH;
+        prm.phase_fast = ctx->phase_fast;
+        prm.batches_per_frame = pl.batches_per_frame;
+        prm.block_partials = ctx->block_partials;
+        prm.counter = ctx->counter;
+        prm.packed_out = packed_dev_out;
+        if (blocking)
         {
-            cudaGraph_t graph = nullptr;
-            CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = enqueue_evaluation(ctx, level, pl, packed_dev_out, copy_back);
-            cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-            if (rc != MBAVO_OK)
-            {
-                if (graph)
-                    cudaGraphDestroy(graph);
-                return rc;
-            }
-            if (e != cudaSuccess)
-                return fail(MBAVO_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
-            cudaGraphExec_t exec = nullptr;
-            e = cudaGraphInstantiate(&exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e != cudaSuccess)
-                return fail(MBAVO_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
-            it = ctx->graphs.emplace(key, exec).first;
+            prm.host_out = ctx->result_map;
+            prm.host_seq = reinterpret_cast<volatile unsigned long long *>(ctx->result_map + packed_len(MBAVO_MAX_KNOT_WINDOW));
+            prm.seq = ++ctx->seq;
         }
-        CUDA_TRY(cudaGraphLaunch(it->second, ctx->stream));
+        if (ctx->timing)
+            CUDA_TRY(cudaEventRecord(ctx->ev0, s));
+        CUDA_TRY(launch_track_kernel(pl.K, pl.NK, pl.with_h, prm, pl.grid, pl.smem, s, nullptr));
+        if (ctx->timing)
+            CUDA_TRY(cudaEventRecord(ctx->ev1, s));
+        return MBAVO_OK;
+    }
+
+    // Spin until the tracking kernel has published sequence number ctx->seq (a few microseconds after its last block
+    // finishes); the stream is polled now and then so that a failed launch cannot hang the caller.
+    int wait_result(mbavo_ctx *ctx)
+    {
+        volatile unsigned long long *seq =
+            reinterpret_cast<volatile unsigned long long *>(ctx->result_host + packed_len(MBAVO_MAX_KNOT_WINDOW));
+        for (unsigned long long spins = 1;; ++spins)
+        {
+            if (*seq == ctx->seq)
+                break;
+            if ((spins & 0xfff) == 0)
+            {
+                cudaError_t e = cudaStreamQuery(ctx->stream);
+                if (e == cudaSuccess)
+                {
+                    if (*seq == ctx->seq)
+                        break;
+                    return fail(MBAVO_ECUDA, "tracking kernel finished without publishing its result");
+                }
+                if (e != cudaErrorNotReady)
+                    return fail(MBAVO_ECUDA, "evaluation failed: %s", cudaGetErrorString(e));
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
         return MBAVO_OK;
     }
 } // namespace
@@ -446,9 +438,6 @@ extern "C"
         ctx->num_sms = prop.multiProcessorCount;
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         ctx->stream = ctx->own_stream;
-        CUDA_TRY(cudaMallocHost(&ctx->stage_host, sizeof(EvalStage)));
-        std::memset(ctx->stage_host, 0, sizeof(EvalStage));
-        CUDA_TRY(cudaMalloc(&ctx->stage_dev, sizeof(EvalStage)));
         const size_t nsamp = (size_t)lim->max_num_frames * lim->max_num_virtual_poses_per_frame;
         CUDA_TRY(cudaMalloc(&ctx->samples, nsamp * sample_rec_floats(4) * sizeof(float)));
         CUDA_TRY(cudaMalloc(&ctx->mid, sizeof(double) * kMidDoubles * kMaxFrames));
@@ -457,16 +446,16 @@ extern "C"
         CUDA_TRY(cudaMemset(ctx->counter, 0, sizeof(unsigned int)));
         const int emax = packed_len(MBAVO_MAX_KNOT_WINDOW);
         CUDA_TRY(cudaMalloc(&ctx->packed_dev, sizeof(double) * emax));
-        CUDA_TRY(cudaMallocHost(&ctx->packed_host, sizeof(double) * emax));
+        CUDA_TRY(cudaHostAlloc(&ctx->result_host, sizeof(double) * (emax + 1), cudaHostAllocMapped));
+        std::memset(ctx->result_host, 0, sizeof(double) * (emax + 1));
+        CUDA_TRY(cudaHostGetDevicePointer(&ctx->result_map, ctx->result_host, 0));
         CUDA_TRY(cudaMalloc(&ctx->outlier_result_dev, sizeof(int) * 4));
         CUDA_TRY(cudaMallocHost(&ctx->outlier_result_host, sizeof(int) * 4));
         CUDA_TRY(cudaEventCreate(&ctx->ev0));
         CUDA_TRY(cudaEventCreate(&ctx->ev1));
         CUDA_TRY(cudaMalloc(&ctx->inexact_dev, sizeof(int)));
         CUDA_TRY(cudaMallocHost(&ctx->inexact_host, sizeof(int)));
-        const char *g = getenv("MBAVO_NO_GRAPHS");
-        ctx->use_graphs = !(g && g[0] == '1');
-        g = getenv("MBAVO_NO_TEXELS");
+        const char *g = getenv("MBAVO_NO_TEXELS");
         ctx->use_texels = !(g && g[0] == '1');
         g = getenv("MBAVO_PHASE_FAST");
         ctx->phase_fast = (g && g[0] == '1') ? 1 : 0;
@@ -487,7 +476,6 @@ extern "C"
             return MBAVO_OK;
         DeviceGuard guard(ctx->device);
         cudaStreamSynchronize(ctx->stream);
-        drop_graphs(ctx, -1);
         for (auto &L : ctx->levels)
         {
             free_level(L);
@@ -499,15 +487,13 @@ extern "C"
         }
         cudaFree(ctx->inexact_dev);
         cudaFreeHost(ctx->inexact_host);
-        cudaFreeHost(ctx->stage_host);
-        cudaFree(ctx->stage_dev);
         cudaFree(ctx->samples);
         cudaFree(ctx->mid);
         cudaFree(ctx->seg_end);
         cudaFree(ctx->block_partials);
         cudaFree(ctx->counter);
         cudaFree(ctx->packed_dev);
-        cudaFreeHost(ctx->packed_host);
+        cudaFreeHost(ctx->result_host);
         cudaFree(ctx->outlier_result_dev);
         cudaFreeHost(ctx->outlier_result_host);
         cudaEventDestroy(ctx->ev0);
@@ -523,7 +509,6 @@ extern "C"
             return fail(MBAVO_EINVAL, "null context");
         DeviceGuard guard(ctx->device);
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        drop_graphs(ctx, -1);
         ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
         return MBAVO_OK;
     }
@@ -575,8 +560,6 @@ extern "C"
             CUDA_TRY(cudaMalloc(&L.flags, ctx->lim.max_num_keypoints));
             CUDA_TRY(cudaMalloc(&L.patch_cost, sizeof(double) * (size_t)ctx->lim.max_num_keypoints * ctx->lim.max_num_frames));
         }
-        const LevelDev before = L.dev;
-        bool realloc = false;
         if (d->mem == MBAVO_MEM_HOST)
         {
             if (!L.owns || L.cap_pix < npix || L.cap_pts < (size_t)P || L.cap_frames < F)
@@ -589,7 +572,6 @@ extern "C"
                 CUDA_TRY(cudaMalloc(&L.xy, sizeof(double) * 2 * P));
                 CUDA_TRY(cudaMalloc(&L.z, sizeof(double) * P));
                 L.owns = true, L.cap_pix = npix, L.cap_pts = P, L.cap_frames = F;
-                realloc = true;
             }
             CUDA_TRY(cudaMemcpyAsync(L.ref_I, d->ref_I, npix, cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(L.ref_dIxy, d->ref_dIxy, npix * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -661,12 +643,6 @@ extern "C"
         else
             L.dev.patch_cost = L.patch_cost, L.dev.patch_cost_stride = 1;
         L.set = true;
-        // launch parameters are baked into captured graphs: a new generation whenever any of them changed
-        if (realloc || std::memcmp(&before, &L.dev, sizeof(LevelDev)) != 0)
-        {
-            ++ctx->level_gen[level];
-            drop_graphs(ctx, level);
-        }
         CUDA_TRY(cudaStreamSynchronize(s)); // host buffers are only borrowed for the call
         return MBAVO_OK;
     }
@@ -744,15 +720,18 @@ extern "C"
             return rc;
         LevelStore &L = ctx->levels[level];
         const long long nres = (long long)(pl.P - L.num_bad) * pl.F * pl.S; // spline_update_step.cpp:116
-        ctx->stage_host->inv_num_residuals = 1.0 / (double)nres;
-        ctx->stage_host->huber_a = (float)huber_a;
-        rc = run_evaluation(ctx, level, pl, ctx->packed_dev, true);
+        rc = run_evaluation(ctx, level, pl, ctx->packed_dev, true, 1.0 / (double)nres, huber_a);
         if (rc != MBAVO_OK)
             return rc;
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        rc = wait_result(ctx);
+        if (rc != MBAVO_OK)
+            return rc;
         if (ctx->timing)
+        {
+            CUDA_TRY(cudaEventSynchronize(ctx->ev1));
             cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
-        return mbavo_unpack(ctx->packed_host, pl.kmin, pl.NK, sp->num_ctrl_knots, total_cost, H, g);
+        }
+        return mbavo_unpack(ctx->result_host, pl.kmin, pl.NK, sp->num_ctrl_knots, total_cost, H, g);
     }
 
     int mbavo_evaluate_async(mbavo_ctx *ctx, int level, const mbavo_spline *sp, double huber_a, int with_hessian,
@@ -767,15 +746,11 @@ extern "C"
             return rc;
         LevelStore &L = ctx->levels[level];
         const long long nres = num_residuals_global > 0 ? num_residuals_global : (long long)(pl.P - L.num_bad) * pl.F * pl.S;
-        // the staging block is reused by the next call: wait for the previous H2D of it to be consumed
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        ctx->stage_host->inv_num_residuals = 1.0 / (double)nres;
-        ctx->stage_host->huber_a = (float)huber_a;
         if (kmin)
             *kmin = pl.kmin;
         if (knot_window)
             *knot_window = pl.NK;
-        return run_evaluation(ctx, level, pl, packed_dev, false);
+        return run_evaluation(ctx, level, pl, packed_dev, false, 1.0 / (double)nres, huber_a);
     }
 
     int mbavo_patch_costs(mbavo_ctx *ctx, int level, double *out)

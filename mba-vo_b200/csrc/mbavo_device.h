@@ -26,7 +26,8 @@ namespace mbavo
     // per-frame fp64 data for the patch centre (compute_local_patches_xy.cu:26-49): R_r2c (9) and t_r2c (3)
     constexpr int kMidDoubles = 12;
 
-    // Staging block copied host -> device once per evaluation (pinned source).
+    // Per-evaluation spline state, passed BY VALUE as the pose kernel's launch parameter (2.3 KB of the 4 KB parameter
+    // space): no host -> device copy precedes an evaluation.
     struct EvalStage
     {
         double knots_t[3 * 16];
@@ -35,10 +36,7 @@ namespace mbavo
         double exp_time[kMaxFrames];
         double t0, dt;
         int n_knots, K, N, F, kmin, NK;
-        double inv_num_residuals;     // 1 / ((P - num_bad) F S)            spline_update_step.cpp:116-117
-        float huber_a;
-        int pad_;
-        int seg_idx[kMaxFrames * 64]; // host-computed segment start knot of every sample (authoritative)
+        unsigned char seg_off[kMaxFrames * 64]; // host-computed segment start knot of every sample minus kmin (authoritative)
     };
 
     // Keyframe texels, built once per mbavo_set_level by pack_kernel (track_kernel.cu) from ref_I / ref_dIxy when every
@@ -74,14 +72,20 @@ namespace mbavo
         const float *samples;     // [F * N * rec] sample records
         const double *mid;        // [F * kMidDoubles]
         const int *seg_end;       // [F * kMaxSegments]: one past the last sample index of every segment offset
-        const EvalStage *stage;   // huber_a and inv_num_residuals live here so that launch parameters never change
+        double inv_num_residuals; // 1 / ((P - num_bad) F S)            spline_update_step.cpp:116-117
+        float huber_a;
         int TP;                   // points per warp batch
         int PH;                   // exposure-sample phases per pixel: the 32 lanes of a warp are PH phases x 32/PH pixels
         int phase_fast;           // lane = slot * PH + phase instead of phase * (32/PH) + slot
         int batches_per_frame;
         double *block_partials;   // [gridDim.x * gridDim.y * E]
         unsigned int *counter;    // last-block-done ticket
-        double *packed_out;       // [E]
+        double *packed_out;       // [E] device memory
+        // Blocking evaluations: the last block also stores the packed vector straight into mapped pinned host memory and
+        // then publishes `seq` there; the host spins on it instead of waiting for a D2H copy + stream synchronisation.
+        double *host_out;                     // [E] mapped pinned host memory, or nullptr
+        volatile unsigned long long *host_seq;
+        unsigned long long seq;
     };
 
     __host__ __device__ constexpr int packed_len(int NK) { return (6 * NK + 1) * (6 * NK + 2) / 2; }

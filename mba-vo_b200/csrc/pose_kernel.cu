@@ -254,9 +254,10 @@ namespace mbavo
 
         // one thread per (frame, sample)
         template <int K>
-        __global__ void pose_kernel(const EvalStage *__restrict__ st, int with_jacobian, float *__restrict__ samples,
+        __global__ void pose_kernel(const __grid_constant__ EvalStage stage, int with_jacobian, float *__restrict__ samples,
                                     double *__restrict__ mid, int *__restrict__ seg_end)
         {
+            const EvalStage *st = &stage;
             const int N = st->N, F = st->F;
             const int g = blockIdx.x * blockDim.x + threadIdx.x;
             if (g >= N * F)
@@ -266,7 +267,7 @@ namespace mbavo
             const double t_mu = st->exp_time[f];
             const double ts = __dadd_rn(__dadd_rn(st->cap[f], -__dmul_rn(t_mu, 0.5)),
                                         __ddiv_rn(__dmul_rn((double)i, t_mu), (double)(N - 1) + 1e-8));
-            const int idx = st->seg_idx[g]; // host-computed with the same expression (SplineFunctor.h:13-19)
+            const int idx = st->kmin + st->seg_off[g]; // host-computed with the same expression (SplineFunctor.h:13-19)
             const double u = __ddiv_rn(__dadd_rn(ts, -st->t0), st->dt) - (double)idx;
 
             double tt[3], wt[K], Theta[K * 9];
@@ -302,7 +303,7 @@ namespace mbavo
             }
             // seg_end[f][s] = number of samples of frame f whose segment offset is <= s  (samples are time-ordered)
             const int off = idx - st->kmin;
-            const int next_off = (i + 1 < N) ? st->seg_idx[g + 1] - st->kmin : kMaxSegments;
+            const int next_off = (i + 1 < N) ? (int)st->seg_off[g + 1] : kMaxSegments;
             for (int s = off; s < next_off && s < kMaxSegments; ++s)
                 seg_end[f * kMaxSegments + s] = i + 1;
             if (i == 0)
@@ -311,15 +312,15 @@ namespace mbavo
         }
     } // namespace
 
-    cudaError_t launch_pose_kernel(int K, const EvalStage *stage_dev, int total_samples, int with_jacobian, float *samples,
+    cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
                                    double *mid, int *seg_end, cudaStream_t stream)
     {
         const int threads = 64;
         const int blocks = (total_samples + threads - 1) / threads;
         if (K == 2)
-            pose_kernel<2><<<blocks, threads, 0, stream>>>(stage_dev, with_jacobian, samples, mid, seg_end);
+            pose_kernel<2><<<blocks, threads, 0, stream>>>(stage, with_jacobian, samples, mid, seg_end);
         else
-            pose_kernel<4><<<blocks, threads, 0, stream>>>(stage_dev, with_jacobian, samples, mid, seg_end);
+            pose_kernel<4><<<blocks, threads, 0, stream>>>(stage, with_jacobian, samples, mid, seg_end);
         return cudaGetLastError();
     }
 } // namespace mbavo

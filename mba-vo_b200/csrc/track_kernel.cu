@@ -320,8 +320,8 @@ namespace mbavo
             const double *mid = prm.mid + f * kMidDoubles;
             const float fxf = (float)lv.fx, fyf = (float)lv.fy;
             const float inv_N = 1.0f / (float)N;
-            const float huber_a = prm.stage->huber_a;
-            const double inv_num_residuals = prm.stage->inv_num_residuals;
+            const float huber_a = prm.huber_a;
+            const double inv_num_residuals = prm.inv_num_residuals;
             float *my_rows = rows_s + warp * 32 * D1P;
             float *my_rho = rho_s + warp * rho_per_warp;
             PixelRec *my_pix = pix_s + warp * 32;
@@ -507,10 +507,22 @@ namespace mbavo
                 double s = 0.0;
                 for (int b = 0; b < num_blocks; ++b)
                     s += __ldcg(prm.block_partials + (size_t)b * E + e);
-                prm.packed_out[e] = s * inv_num_residuals;
+                s *= inv_num_residuals;
+                prm.packed_out[e] = s;
+                if (prm.host_out)
+                    prm.host_out[e] = s;
+            }
+            if (prm.host_out)
+            {
+                __threadfence_system(); // the vector is visible to the host before the sequence number is
+                __syncthreads();
             }
             if (threadIdx.x == 0)
+            {
                 *prm.counter = 0u; // re-arm for the next launch
+                if (prm.host_out)
+                    *prm.host_seq = prm.seq;
+            }
         }
 
         // Keyframe texels (see LevelDev).  One thread per pixel; *inexact counts gradient values that fp16 cannot hold.

@@ -99,10 +99,12 @@ namespace
         }
     }
 
-    // x = A^-1 b by LDL^T (A symmetric, row-major)
-    bool solve_ldlt(const double *A, const double *b, int n, double *x)
+    // x = A^-1 b by LDL^T (A symmetric, row-major).  min_pivot_ratio > 0: give up (return false) when the smallest
+    // pivot falls below that fraction of the largest, or is not positive.
+    bool solve_ldlt(const double *A, const double *b, int n, double *x, double min_pivot_ratio = 0.0)
     {
         std::vector<double> L((size_t)n * n, 0.0), D(n, 0.0);
+        double dmax = 0.0;
         for (int j = 0; j < n; ++j)
         {
             double d = A[(size_t)j * n + j];
@@ -111,6 +113,12 @@ namespace
             D[j] = d;
             if (d == 0.0)
                 return false;
+            if (min_pivot_ratio > 0.0)
+            {
+                dmax = std::max(dmax, d);
+                if (!(d > min_pivot_ratio * dmax))
+                    return false;
+            }
             L[(size_t)j * n + j] = 1.0;
             for (int i = j + 1; i < n; ++i)
             {
@@ -234,7 +242,14 @@ extern "C"
         for (int i = 0; i < dim; ++i) // in place: the damping compounds over rejected steps (tracker.cpp:803)
             H[(size_t)i * dim + i] += H[(size_t)i * dim + i] * (1.0 / radius);
         if (solver_type == MBAVO_SOLVER_SVD_JACOBI)
-            solve_svd(H, g, dim, step);
+        {
+            // JacobiSVD::solve returns the pseudo-inverse solution, which IS the inverse solution whenever H has full
+            // numerical rank.  A positive-definite H whose LDL^T pivots stay within 1e-9 of the largest (cond < ~1e9,
+            // far from the SVD's rank threshold n eps) is solved by LDL^T (~1 us for 12 x 12 instead of ~40 us); anything
+            // else goes through the eigen-decomposition, which drops singular directions like the SVD does.
+            if (!solve_ldlt(H, g, dim, step, 1e-9))
+                solve_svd(H, g, dim, step);
+        }
         else if (solver_type == MBAVO_SOLVER_LDLT)
         {
             if (!solve_ldlt(H, g, dim, step))
