@@ -13,15 +13,22 @@ namespace mbavo
     constexpr int kWarpsPerBlock = 8;
     constexpr int kThreads = kWarpsPerBlock * 32;
 
-    // One exposure sample (virtual pose) as the tracking kernel consumes it, fp32, 16-byte aligned records:
-    //   [0..8]   R - I  rotation matrix of the pose quaternion minus identity, row-major, rounded after the
-    //                   subtraction                                              (compute_virtual_camera_poses.cu:102-109)
-    //   [9..11]  t      translation
-    //   [12..12+K)      wt[j]     translation blend weight of the segment's knot j        (SplineFunctor.h:30-40, 74-91)
-    //   [12+K .. 12+K+9K)  Theta[j] (3x3 row-major) = d theta / d w_j, theta the right perturbation of the pose
-    //                   rotation: dq/dw_j = L(q) [I/2; 0] Theta_j                           (SplineFunctor.h:178-213, 274-361)
-    //   then 1 int      segment offset inside the knot window (idx_i - kmin)
-    __host__ __device__ constexpr int sample_rec_floats(int K) { return ((12 + K + 9 * K + 1) + 3) / 4 * 4; }
+    // One exposure sample (virtual pose) as the tracking kernel consumes it: fp32, 16-byte aligned records laid out so
+    // that every operand PAIR of the kernel's packed FFMA2 arithmetic is an aligned pair of one 128-bit shared load.
+    // With Rm = R - I (rotation matrix of the pose quaternion minus identity, rounded after the subtraction,
+    // compute_virtual_camera_poses.cu:102-109) and t the translation:
+    //   [0..5]    (Rm00 Rm10) (Rm01 Rm11) (Rm02 Rm12)      column pairs:  (A0, A1) = rx c0 + ry c1 + c2
+    //   [6..9]    (Rm20 Rm21) Rm22 tz
+    //   [10..11]  (tx ty)
+    //   [12..15]  (Rm00 Rm01) (Rm10 Rm11)                  row pairs:     R^T g
+    //   then per knot j of the segment (10 floats each):
+    //     wt_j                      translation blend weight                               (SplineFunctor.h:30-40, 74-91)
+    //     Th00 Th10 Th20            first column of Theta_j
+    //     (Th01 Th02) (Th11 Th12) (Th21 Th22)   remaining columns as row pairs
+    //   Theta_j (3x3) = d theta / d w_j, theta the right perturbation of the pose rotation:
+    //   dq/dw_j = L(q) [I/2; 0] Theta_j                                                    (SplineFunctor.h:178-213, 274-361)
+    constexpr int kRecGeom = 16;
+    __host__ __device__ constexpr int sample_rec_floats(int K) { return (kRecGeom + 10 * K + 3) / 4 * 4; }
 
     // per-frame fp64 data for the patch centre (compute_local_patches_xy.cu:26-49): R_r2c (9) and t_r2c (3)
     constexpr int kMidDoubles = 12;
@@ -42,7 +49,7 @@ namespace mbavo
     // Keyframe texels, built once per mbavo_set_level by pack_kernel (track_kernel.cu) from ref_I / ref_dIxy when every
     // gradient value is exactly representable in fp16 (always true for Gradient.h's 0.5 * central differences of an
     // 8-bit image: multiples of 0.5 up to 127.5).  They carry bit-identical values in a gather-friendly layout:
-    //   pair texel (16 B per pixel): 8 halves  I(x,y) gx(x,y) gy(x,y) I(x+1,y) gx(x+1,y) gy(x+1,y) 0 0
+    //   pair texel (16 B per pixel): 8 halves  gx(x,y) gy(x,y) | gx(x+1,y) gy(x+1,y) | I(x,y) I(x+1,y) | 0 0
     //                                — one 128-bit load per image ROW of the bilinear footprint instead of 2 + 2 loads
     //   quad texel (4 B per pixel):  bytes     I(x,y) I(x+1,y) I(x,y+1) I(x+1,y+1)
     //                                — the whole footprint of a cost-only sample in one 32-bit load
@@ -64,6 +71,24 @@ namespace mbavo
         const unsigned char *flags; // 1 = outlier
         double *patch_cost;         // [F * P * patch_cost_stride]
         int patch_cost_stride;
+    };
+
+    // Sample records, mid-exposure poses and segment ranges of one evaluation as a LAUNCH PARAMETER of the tracking
+    // kernel (11 KB for k = 2, 16 KB for k = 4; parameters may be 32 KB): the host computes them (pose_kernel.cu,
+    // compute_sample_records_host), the kernel reads them through the constant bank with uniform loads (LDCU) straight
+    // into FFMA operands — no shared-memory traffic, no vector registers, no pose kernel launch.  Used whenever the
+    // evaluation has at most kTableSamples exposure samples in total (the reference tracker: 1 frame, N <= 64).
+    constexpr int kTableSamples = 64;
+    template <int K>
+    struct SampleTable
+    {
+        float rec[kTableSamples * sample_rec_floats(K)];
+        double mid[kMaxFrames * kMidDoubles];
+        int seg_end[kMaxFrames * kMaxSegments];
+    };
+    struct NoTable
+    {
+        int unused;
     };
 
     struct TrackParams

@@ -17,22 +17,22 @@ namespace mbavo
             double x, y, z, w;
         };
 
-        __device__ __forceinline__ Q qmul(const Q &a, const Q &b) // Quaternion.h:44-50
+        __host__ __device__ __forceinline__ Q qmul(const Q &a, const Q &b) // Quaternion.h:44-50
         {
             return Q{a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
                      a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
         }
-        __device__ __forceinline__ Q qconj(const Q &a) { return Q{-a.x, -a.y, -a.z, a.w}; }
+        __host__ __device__ __forceinline__ Q qconj(const Q &a) { return Q{-a.x, -a.y, -a.z, a.w}; }
 
         // q (x) p = L(q) p ; q (x) p = Rhat(p) q      (Quaternion.h:239-283), 4x4 row-major
-        __device__ __forceinline__ void left_matrix(const Q &q, double *M)
+        __host__ __device__ __forceinline__ void left_matrix(const Q &q, double *M)
         {
             M[0] = q.w, M[1] = -q.z, M[2] = q.y, M[3] = q.x;
             M[4] = q.z, M[5] = q.w, M[6] = -q.x, M[7] = q.y;
             M[8] = -q.y, M[9] = q.x, M[10] = q.w, M[11] = q.z;
             M[12] = -q.x, M[13] = -q.y, M[14] = -q.z, M[15] = q.w;
         }
-        __device__ __forceinline__ void right_matrix(const Q &q, double *M)
+        __host__ __device__ __forceinline__ void right_matrix(const Q &q, double *M)
         {
             M[0] = q.w, M[1] = q.z, M[2] = -q.y, M[3] = q.x;
             M[4] = -q.z, M[5] = q.w, M[6] = q.x, M[7] = q.y;
@@ -42,7 +42,7 @@ namespace mbavo
 
         // rotation vector of q and G = d phi / d q (3x4).  Branches and derivative expressions as in
         // Quaternion::log (Quaternion.h:61-152): the Jacobians of the pose inherit them.
-        __device__ void so3_log(const Q &q, double *phi, double *G)
+        __host__ __device__ inline void so3_log(const Q &q, double *phi, double *G)
         {
             const double v[3] = {q.x, q.y, q.z};
             const double n2 = q.x * q.x + q.y * q.y + q.z * q.z;
@@ -83,7 +83,7 @@ namespace mbavo
         }
 
         // unit quaternion of a rotation vector and E = d q / d phi (4x3)      (Quaternion::exp, Quaternion.h:154-233)
-        __device__ void so3_exp(const double *phi, Q &q, double *E)
+        __host__ __device__ inline void so3_exp(const double *phi, Q &q, double *E)
         {
             const double t2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
             double fi, fr;
@@ -112,7 +112,7 @@ namespace mbavo
         }
 
         template <int M, int P, int N>
-        __device__ __forceinline__ void mat_mul(const double *A, const double *B, double *C)
+        __host__ __device__ __forceinline__ void mat_mul(const double *A, const double *B, double *C)
         {
             for (int i = 0; i < M; ++i)
                 for (int j = 0; j < N; ++j)
@@ -126,7 +126,7 @@ namespace mbavo
 
         // blend weights of the K knots of a segment (SplineFunctor.h:24-28,176 / :47-54,232-234)
         template <int K>
-        __device__ __forceinline__ void spline_weights(double u, double *wt, double *wr)
+        __host__ __device__ __forceinline__ void spline_weights(double u, double *wt, double *wr)
         {
             if (K == 2)
             {
@@ -152,7 +152,7 @@ namespace mbavo
         // d_m = q_{m-1}* q_m, and through d_{m+1} = q_m* q_{m+1}.  With JR_m = dq/dw_m (the reference's 4x3 block),
         // Theta_m = 2 [L(q)^T JR_m]_{rows 0..2}.
         template <int K>
-        __device__ void spline_pose(const double *kt, const double *kR, double u, double *t_out, Q &q_out, double *wt,
+        __host__ __device__ inline void spline_pose(const double *kt, const double *kR, double u, double *t_out, Q &q_out, double *wt,
                                     double *Theta /* K x 9, nullable */)
         {
             double wr[K];
@@ -244,7 +244,7 @@ namespace mbavo
             }
         }
 
-        __device__ __forceinline__ void rotation_matrix(const Q &q, double *R)
+        __host__ __device__ __forceinline__ void rotation_matrix(const Q &q, double *R)
         {
             const double x = q.x, y = q.y, z = q.z, w = q.w;
             R[0] = w * w + x * x - y * y - z * z, R[1] = 2 * (x * y - w * z), R[2] = 2 * (x * z + w * y);
@@ -252,23 +252,47 @@ namespace mbavo
             R[6] = 2 * (x * z - w * y), R[7] = 2 * (y * z + w * x), R[8] = w * w - x * x - y * y + z * z;
         }
 
-        // one thread per (frame, sample)
-        template <int K>
-        __global__ void pose_kernel(const __grid_constant__ EvalStage stage, int with_jacobian, float *__restrict__ samples,
-                                    double *__restrict__ mid, int *__restrict__ seg_end)
+        // correctly rounded, never contracted: the host and the device evaluate the sample time identically
+        __host__ __device__ __forceinline__ double add_rn(double a, double b)
         {
-            const EvalStage *st = &stage;
-            const int N = st->N, F = st->F;
-            const int g = blockIdx.x * blockDim.x + threadIdx.x;
-            if (g >= N * F)
-                return;
+#ifdef __CUDA_ARCH__
+            return __dadd_rn(a, b);
+#else
+            volatile double r = a + b;
+            return r;
+#endif
+        }
+        __host__ __device__ __forceinline__ double mul_rn(double a, double b)
+        {
+#ifdef __CUDA_ARCH__
+            return __dmul_rn(a, b);
+#else
+            volatile double r = a * b;
+            return r;
+#endif
+        }
+        __host__ __device__ __forceinline__ double div_rn(double a, double b)
+        {
+#ifdef __CUDA_ARCH__
+            return __ddiv_rn(a, b);
+#else
+            volatile double r = a / b;
+            return r;
+#endif
+        }
+
+        // Sample g = f * N + i of the evaluation: record, mid-exposure pose of its frame, segment ranges.
+        template <int K>
+        __host__ __device__ inline void pose_one(const EvalStage *st, int g, int with_jacobian, float *samples, double *mid,
+                                                 int *seg_end)
+        {
+            const int N = st->N;
             const int f = g / N, i = g % N;
-            // compute_virtual_camera_poses.cu:33 — explicit _rn ops: no FMA contraction, bit-identical to the host
+            // compute_virtual_camera_poses.cu:33
             const double t_mu = st->exp_time[f];
-            const double ts = __dadd_rn(__dadd_rn(st->cap[f], -__dmul_rn(t_mu, 0.5)),
-                                        __ddiv_rn(__dmul_rn((double)i, t_mu), (double)(N - 1) + 1e-8));
+            const double ts = add_rn(add_rn(st->cap[f], -mul_rn(t_mu, 0.5)), div_rn(mul_rn((double)i, t_mu), (double)(N - 1) + 1e-8));
             const int idx = st->kmin + st->seg_off[g]; // host-computed with the same expression (SplineFunctor.h:13-19)
-            const double u = __ddiv_rn(__dadd_rn(ts, -st->t0), st->dt) - (double)idx;
+            const double u = div_rn(add_rn(ts, -st->t0), st->dt) - (double)idx;
 
             double tt[3], wt[K], Theta[K * 9];
             Q q;
@@ -279,16 +303,29 @@ namespace mbavo
             constexpr int REC = sample_rec_floats(K);
             float *rec = samples + (size_t)g * REC;
             // R - I, rounded AFTER the subtraction: the tracking kernel works with the small deviation of the warp from
-            // the identity so that its fp32 reference coordinates keep ~1e-6 px accuracy (track_kernel.cu, sample_step)
+            // the identity so that its fp32 reference coordinates keep ~1e-6 px accuracy (track_kernel.cu, sample_step).
+            // Record layout: mbavo_device.h.
+            float Rm[9];
             for (int e = 0; e < 9; ++e)
-                rec[e] = (float)(R[e] - ((e & 3) == 0 ? 1.0 : 0.0));
-            for (int e = 0; e < 3; ++e)
-                rec[9 + e] = (float)tt[e];
+                Rm[e] = (float)(R[e] - ((e & 3) == 0 ? 1.0 : 0.0));
+            rec[0] = Rm[0], rec[1] = Rm[3], rec[2] = Rm[1], rec[3] = Rm[4], rec[4] = Rm[2], rec[5] = Rm[5];
+            rec[6] = Rm[6], rec[7] = Rm[7], rec[8] = Rm[8], rec[9] = (float)tt[2];
+            rec[10] = (float)tt[0], rec[11] = (float)tt[1];
+            rec[12] = Rm[0], rec[13] = Rm[1], rec[14] = Rm[3], rec[15] = Rm[4];
             for (int j = 0; j < K; ++j)
-                rec[12 + j] = (float)wt[j];
-            for (int e = 0; e < 9 * K; ++e)
-                rec[12 + K + e] = with_jacobian ? (float)Theta[e] : 0.f;
-            reinterpret_cast<int *>(rec)[12 + K + 9 * K] = idx - st->kmin;
+            {
+                float *c = rec + kRecGeom + 10 * j;
+                const double *Th = Theta + 9 * j;
+                c[0] = (float)wt[j];
+                for (int r = 0; r < 3; ++r)
+                {
+                    c[1 + r] = with_jacobian ? (float)Th[3 * r] : 0.f;
+                    c[4 + 2 * r] = with_jacobian ? (float)Th[3 * r + 1] : 0.f;
+                    c[5 + 2 * r] = with_jacobian ? (float)Th[3 * r + 2] : 0.f;
+                }
+            }
+            for (int e = kRecGeom + 10 * K; e < REC; ++e)
+                rec[e] = 0.f;
 
             if (i == N / 2)
             {
@@ -310,7 +347,30 @@ namespace mbavo
                 for (int s = 0; s < off && s < kMaxSegments; ++s)
                     seg_end[f * kMaxSegments + s] = 0;
         }
+
+        // one thread per (frame, sample)
+        template <int K>
+        __global__ void pose_kernel(const __grid_constant__ EvalStage stage, int with_jacobian, float *__restrict__ samples,
+                                    double *__restrict__ mid, int *__restrict__ seg_end)
+        {
+            const int g = blockIdx.x * blockDim.x + threadIdx.x;
+            if (g < stage.N * stage.F)
+                pose_one<K>(&stage, g, with_jacobian, samples, mid, seg_end);
+        }
     } // namespace
+
+    // The same records on the host (they then travel to the tracking kernel as a launch parameter)
+    void compute_sample_records_host(int K, const EvalStage &stage, int with_jacobian, float *samples, double *mid, int *seg_end)
+    {
+        const int total = stage.N * stage.F;
+        for (int g = 0; g < total; ++g)
+        {
+            if (K == 2)
+                pose_one<2>(&stage, g, with_jacobian, samples, mid, seg_end);
+            else
+                pose_one<4>(&stage, g, with_jacobian, samples, mid, seg_end);
+        }
+    }
 
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
                                    double *mid, int *seg_end, cudaStream_t stream)

@@ -1,0 +1,85 @@
+// Tracking-kernel plumbing shared by the instantiation units: keyframe texel packing, shared-memory sizing, dispatch.
+#include "mbavo_device.h"
+
+#include <cuda_fp16.h>
+
+namespace mbavo
+{
+    cudaError_t track_dispatch_k2_lo(int NK, bool with_j, bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid,
+                                     size_t smem, cudaStream_t stream, int *query_occupancy);
+    cudaError_t track_dispatch_k2_hi(int NK, bool with_j, bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid,
+                                     size_t smem, cudaStream_t stream, int *query_occupancy);
+    cudaError_t track_dispatch_k4_lo(int NK, bool with_j, bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid,
+                                     size_t smem, cudaStream_t stream, int *query_occupancy);
+    cudaError_t track_dispatch_k4_hi(int NK, bool with_j, bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid,
+                                     size_t smem, cudaStream_t stream, int *query_occupancy);
+
+    namespace
+    {
+        // Keyframe texels (see LevelDev).  One thread per pixel; *inexact counts gradient values that fp16 cannot hold.
+        __global__ void pack_kernel(const unsigned char *__restrict__ I, const float2 *__restrict__ g, int H, int W,
+                                    uint4 *__restrict__ pair, unsigned int *__restrict__ quad, int *__restrict__ inexact)
+        {
+            const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+            if (x >= W)
+                return;
+            const int x1 = min(x + 1, W - 1), y1 = min(y + 1, H - 1);
+            const int i00 = y * W + x, i01 = y * W + x1, i10 = y1 * W + x, i11 = y1 * W + x1;
+            const unsigned int b00 = I[i00], b01 = I[i01], b10 = I[i10], b11 = I[i11];
+            quad[i00] = b00 | (b01 << 8) | (b10 << 16) | (b11 << 24);
+            const float2 g0 = g[i00], g1 = g[i01];
+            const __half hx0 = __float2half_rn(g0.x), hy0 = __float2half_rn(g0.y);
+            const __half hx1 = __float2half_rn(g1.x), hy1 = __float2half_rn(g1.y);
+            // bitwise round trip (also rejects NaN and values that overflow to inf)
+            if (__float_as_uint(__half2float(hx0)) != __float_as_uint(g0.x) ||
+                __float_as_uint(__half2float(hy0)) != __float_as_uint(g0.y))
+                atomicAdd(inexact, 1);
+            const unsigned int hI0 = __half_as_ushort(__float2half_rn((float)b00)), hI1 = __half_as_ushort(__float2half_rn((float)b01));
+            uint4 t; // (gx gy)(x,y) | (gx gy)(x+1,y) | I(x,y) I(x+1,y) | 0
+            t.x = (unsigned int)__half_as_ushort(hx0) | ((unsigned int)__half_as_ushort(hy0) << 16);
+            t.y = (unsigned int)__half_as_ushort(hx1) | ((unsigned int)__half_as_ushort(hy1) << 16);
+            t.z = hI0 | (hI1 << 16);
+            t.w = 0u;
+            pair[i00] = t;
+        }
+
+    } // namespace
+
+    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool crec, int N, int S, int TP)
+    {
+        const int REC = sample_rec_floats(K);
+        const int D1 = with_j ? 6 * NK + 1 : 1, D1E = (D1 + 1) & ~1;
+        const int PITCH = (D1E / 2) % 2 == 1 ? D1E : D1E + 2, T = D1E / 2, NT = T * (T + 1) / 2;
+        const int E = with_j ? packed_len(NK) : 1;
+        const int rho_per_warp = max(32, TP * S);
+        size_t main_bytes = (crec ? 0 : (size_t)N * REC * 4) + 8 * 4 + kMidDoubles * 8 + (size_t)kWarpsPerBlock * 32 * 32 /* PixelRec */ +
+                            (size_t)S * 8 +
+                            (size_t)kWarpsPerBlock * rho_per_warp * 4 + (size_t)((NT + 7) & ~7) * 2 +
+                            (size_t)kWarpsPerBlock * 32 * PITCH * 4;
+        size_t red_bytes = (size_t)kWarpsPerBlock * E * 8;
+        return (main_bytes > red_bytes ? main_bytes : red_bytes) + 16;
+    }
+
+    cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,
+                                   int *inexact, cudaStream_t stream)
+    {
+        const dim3 block(128, 1, 1), grid((W + 127) / 128, H, 1);
+        pack_kernel<<<grid, block, 0, stream>>>(I, reinterpret_cast<const float2 *>(dIxy), H, W, pair, quad, inexact);
+        return cudaGetLastError();
+    }
+
+    // with_j: Hessian pass (templated on the window) or cost-only pass (one instantiation per K).  table: host pointer to
+    // the SampleTable<K> to pass as launch parameter, or nullptr (records in prm.samples).
+    cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, const void *table, dim3 grid, size_t smem,
+                                    cudaStream_t stream, int *query_occupancy)
+    {
+        const bool packed = prm.lv.ref_pair != nullptr, crec = table != nullptr;
+        if (K == 2)
+            return (!with_j || NK <= 3) ? track_dispatch_k2_lo(NK, with_j, packed, crec, prm, table, grid, smem, stream, query_occupancy)
+                                        : track_dispatch_k2_hi(NK, with_j, packed, crec, prm, table, grid, smem, stream, query_occupancy);
+        if (K == 4)
+            return (!with_j || NK <= 5) ? track_dispatch_k4_lo(NK, with_j, packed, crec, prm, table, grid, smem, stream, query_occupancy)
+                                        : track_dispatch_k4_hi(NK, with_j, packed, crec, prm, table, grid, smem, stream, query_occupancy);
+        return cudaErrorInvalidValue;
+    }
+} // namespace mbavo

@@ -1,0 +1,19 @@
+// Instantiations of the tracking kernel: spline order k = 2, knot windows [4, 5, 6] (see track_kernel.cuh).
+#include "track_kernel.cuh"
+
+namespace mbavo
+{
+    cudaError_t track_dispatch_k2_hi(int NK, bool with_j, bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid,
+                                  size_t smem, cudaStream_t stream, int *query_occupancy)
+    {
+        if (!with_j)
+            return cudaErrorInvalidValue;
+        if (NK == 4)
+            return dispatch_variant<2, 4, true>(packed, crec, prm, table, grid, smem, stream, query_occupancy);
+        if (NK == 5)
+            return dispatch_variant<2, 5, true>(packed, crec, prm, table, grid, smem, stream, query_occupancy);
+        if (NK == 6)
+            return dispatch_variant<2, 6, true>(packed, crec, prm, table, grid, smem, stream, query_occupancy);
+        return cudaErrorInvalidValue;
+    }
+} // namespace mbavo

@@ -10,16 +10,14 @@
 // Mapping.  A warp owns a batch of TP whole host-map points of one frame and works through it in chunks of 32 residual
 // pixels:
 //   A  lane = pixel: patch centre (fp64), integer live pixel, ray -> 8-word pixel record in shared memory;
-//   B  lane = (pixel slot, exposure phase): the 32 lanes are PH phases x Q = 32/PH pixel slots.  Q is the patch size
-//      (8 for the reference pattern), so at any instruction the warp gathers around ONE host-map point: the taps of a
-//      load instruction fall into the handful of 128-byte lines the patch covers instead of the ~20 that 32 pixels of
-//      4 different points touch — the L1 data pipe (1 wavefront / clk / SM) was the limiter of the first version
-//      (profiles/r1a_*: l1tex data-pipe wavefronts 92 % of peak).  A lane walks the samples i = phase, phase + PH, ...
+//   B  lane = pixel (optionally lane = (pixel slot, exposure phase), MBAVO_PHASES): the lane walks the exposure samples
 //      sequentially in registers: plane-induced warp (fp32), 4-tap bilinear gather, dI/dt (1x3) and dI/dtheta (1x3,
 //      right perturbation of the pose rotation) chained to the control knots through the per-sample spline blocks of
-//      pose_kernel.  The PH partial sums of a pixel are combined by an xor-butterfly of warp shuffles;
-//   C  residual, Huber, row = sqrt(w) [r, J]: the 32 rows of the chunk are staged in shared memory and the packed
-//      upper triangle of rows^T rows is accumulated with one element set per lane (fp32 over 32 rows, fp64 across).
+//      pose_kernel.  The arithmetic is written in 2-vectors — (x, y) image components, matrix column / row pairs, pairs
+//      of Jacobian columns — and issued as packed FFMA2 / FMUL2 / FADD2 (sm_100 packed fp32, one operand may be a
+//      broadcast scalar): the kernel is issue-bound, and packing removes ~30 % of its instructions;
+//   C  residual, Huber, row = sqrt(w) [r, J]: the 32 rows of the chunk are staged in shared memory and rows^T rows is
+//      accumulated in 2x2 register tiles, one or more tiles per lane (fp32 over the 32 rows, fp64 across chunks).
 // Epilogue: deterministic block reduction -> per-block partials -> last block sums all partials in block order.
 //
 // Keyframe texels.  With LevelDev::ref_pair / ref_quad (built by pack_kernel below when the gradient image is exactly
@@ -29,9 +27,13 @@
 //
 // Precision: per-sample arithmetic fp32 (the reference's bilinear taps/weights are fp32 too, compute_pixel_intensity.h:43-68),
 // patch centre fp64 (its truncation picks the live pixel, …cost.cu:69-70), every sum across pixels fp64.
+#ifndef MBAVO_TRACK_KERNEL_CUH_
+#define MBAVO_TRACK_KERNEL_CUH_
 #include "mbavo_device.h"
 
 #include <cuda_fp16.h>
+
+#include <type_traits>
 
 #ifndef MBAVO_MINB_H
 #define MBAVO_MINB_H 2
@@ -53,6 +55,13 @@ namespace mbavo
         {
             return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540 | BYTE)) - 8388608.0f;
         }
+        // packed fp32 pairs (FFMA2 / FMUL2 / FADD2); bc() broadcasts a scalar, which the instruction takes as a .F32 operand
+        __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+        __device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
+        __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+        __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+        __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+
         __device__ __forceinline__ float2 halves(unsigned int v)
         {
             return __half22float2(*reinterpret_cast<const __half2 *>(&v));
@@ -118,18 +127,38 @@ namespace mbavo
             return ps;
         }
 
+        // Where a sample record is read from: shared memory (any F*N, phase split allowed) or the launch-parameter table
+        // (constant bank, uniform index).  q(k) = k-th group of four floats of the record.
+        struct SmemRec
+        {
+            const float *p;
+            __device__ __forceinline__ float4 q(int k) const { return *reinterpret_cast<const float4 *>(p + 4 * k); }
+        };
+        template <class Tab>
+        struct ConstRec
+        {
+            const Tab &t;
+            int base;
+            __device__ __forceinline__ float4 q(int k) const
+            {
+                return make_float4(t.rec[base + 4 * k], t.rec[base + 4 * k + 1], t.rec[base + 4 * k + 2], t.rec[base + 4 * k + 3]);
+            }
+        };
+
         // What a lane keeps in registers while it walks the samples of its pixel
         struct PixelRegs
         {
-            float rx, ry, D, iD;
+            float2 rxy;               // ray of the live pixel (z = 1)
+            float D, iD;              // plane depth, 1 / (D + 1e-8)
             float lox, hix, loy, hiy; // the reference coordinate (X + du, Y + dv) is inside [0, W-1] x [0, H-1] iff
                                       // lox <= du <= hix and loy <= dv <= hiy (all four are exact small integers)
-            float fxiD, fyiD;         // fx / (D + 1e-8), fy / (D + 1e-8)
+            float2 fxyiD;             // (fx, fy) / (D + 1e-8)
             int X, Y;
         };
 
         // One exposure sample of one pixel.  K knots per segment; OFF = segment offset inside the knot window.
-        // Accumulates sumI and, if WITH_J, the 1 x 6NK row (Jt: translation block, Jw: rotation block).
+        // Accumulates sumI and, if WITH_J, the 1 x 6NK row as three pairs per knot a:
+        //     J[a][0] = (dt_x, dt_y)   J[a][1] = (dt_z, dw_x)   J[a][2] = (dw_y, dw_z)
         //
         // Reference coordinate.  compute_pixel_intensity.h:108-144 evaluates u = fx P_x / (D + 1e-8) + c_x in fp64 and
         // rounds only the fractional part to fp32.  A plain fp32 evaluation of u loses ~W * 2^-24 px (4e-5 px at VGA),
@@ -137,28 +166,27 @@ namespace mbavo
         // PIXEL X:  with A = (R - I) ray (small), m = ray + A, tau = t_z / (D + 1e-8),
         //     u - X = fx [ (A_x - r_x A_z - tau m_x) / m_z + t_x / (D + 1e-8) ]
         // in which every term is of the size of the blur, so fp32 keeps ~1e-6 px; the integer tap is X + floor(u - X).
-        template <int K, int NK, bool WITH_J, bool PACKED, int OFF>
-        __device__ __forceinline__ void sample_step(const float *__restrict__ rec, const PixelRegs &ps, const LevelDev &lv,
-                                                    float fxf, float fyf, float &sumI,
-                                                    float (&Jt)[WITH_J ? NK : 1][3], float (&Jw)[WITH_J ? NK : 1][3])
+        template <int K, int NK, bool WITH_J, bool PACKED, int OFF, class Rec>
+        __device__ __forceinline__ void sample_step(const Rec rec, const PixelRegs &ps, const LevelDev &lv,
+                                                    float2 fxy, float &sumI, float2 (&J)[WITH_J ? NK : 1][3])
         {
-            const float4 a0 = *reinterpret_cast<const float4 *>(rec);      // Rm0 Rm1 Rm2 Rm3   (Rm = R - I)
-            const float4 a1 = *reinterpret_cast<const float4 *>(rec + 4);  // Rm4 Rm5 Rm6 Rm7
-            const float4 a2 = *reinterpret_cast<const float4 *>(rec + 8);  // Rm8 tx ty tz
-            const float A0 = fmaf(a0.x, ps.rx, fmaf(a0.y, ps.ry, a0.z));
-            const float A1 = fmaf(a0.w, ps.rx, fmaf(a1.x, ps.ry, a1.y));
-            const float A2 = fmaf(a1.z, ps.rx, fmaf(a1.w, ps.ry, a2.x));
-            const float m0 = ps.rx + A0, m1 = ps.ry + A1, m2 = 1.0f + A2;
+            const float4 g0 = rec.q(0); // (Rm00 Rm10) (Rm01 Rm11)      Rm = R - I
+            const float4 g1 = rec.q(1); // (Rm02 Rm12) (Rm20 Rm21)
+            const float4 g2 = rec.q(2); // Rm22 tz (tx ty)
+            const float2 A01 = fma2(bc(ps.rxy.x), f2(g0.x, g0.y), fma2(bc(ps.rxy.y), f2(g0.z, g0.w), f2(g1.x, g1.y)));
+            const float A2 = fmaf(g1.z, ps.rxy.x, fmaf(g1.w, ps.rxy.y, g2.x));
+            const float2 m01 = add2(ps.rxy, A01);
+            const float m2 = 1.0f + A2;
             const float il = rcp_approx(m2);                    // 1 / lambda (1 ulp: the terms it scales are blur-sized)
-            const float tau = a2.w * ps.iD;
-            const float du = fxf * fmaf(fmaf(-tau, m0, fmaf(-ps.rx, A2, A0)), il, a2.y * ps.iD);
-            const float dv = fyf * fmaf(fmaf(-tau, m1, fmaf(-ps.ry, A2, A1)), il, a2.z * ps.iD);
+            const float tau = g2.y * ps.iD;
+            const float2 num = fma2(bc(-tau), m01, fma2(bc(-A2), ps.rxy, A01));
+            const float2 duv = mul2(fxy, fma2(num, bc(il), mul2(f2(g2.z, g2.w), bc(ps.iD))));
             // inside [0, W-1] x [0, H-1] (compute_pixel_intensity.h:35); an invalid sample contributes nothing while the
             // divisor stays N (…cost.cu:107-110).  NaN / inf coordinates fail the comparisons.
-            if (!(du >= ps.lox && du <= ps.hix && dv >= ps.loy && dv <= ps.hiy))
+            if (!(duv.x >= ps.lox && duv.x <= ps.hix && duv.y >= ps.loy && duv.y <= ps.hiy))
                 return;
-            const float xf = floorf(du), yf = floorf(dv);
-            const float dx = du - xf, dy = dv - yf; // exact
+            const float xf = floorf(duv.x), yf = floorf(duv.y);
+            const float dx = duv.x - xf, dy = duv.y - yf; // exact
             const int xi = ps.X + (int)xf, yi = ps.Y + (int)yf;
 
             // bilinear_interpolation, compute_pixel_intensity.h:40-68
@@ -168,16 +196,15 @@ namespace mbavo
             const int idx = yi * lv.W + xi;
             const int rowoff = yi < lv.H - 1 ? lv.W : 0;
 
-            float gx, gy;
+            float2 gxy;
             if constexpr (PACKED && WITH_J)
             {
                 const uint4 ta = __ldg(lv.ref_pair + idx);
                 const uint4 tb = __ldg(lv.ref_pair + idx + rowoff);
-                const float2 p00 = halves(ta.x), q00 = halves(ta.y), r00 = halves(ta.z); // I00 gx00 | gy00 I01 | gx01 gy01
-                const float2 p10 = halves(tb.x), q10 = halves(tb.y), r10 = halves(tb.z); // I10 gx10 | gy10 I11 | gx11 gy11
-                sumI += w11 * q10.y + w10 * p10.x + w01 * q00.y + w00 * p00.x;
-                gx = w11 * r10.x + w10 * p10.y + w01 * r00.x + w00 * p00.y;
-                gy = w11 * r10.y + w10 * q10.x + w01 * r00.y + w00 * q00.x;
+                const float2 g00 = halves(ta.x), g01 = halves(ta.y), i0 = halves(ta.z); // (gx gy)(x,y) | (gx gy)(x+1,y) | I(x,y) I(x+1,y)
+                const float2 g10 = halves(tb.x), g11 = halves(tb.y), i1 = halves(tb.z);
+                sumI += w11 * i1.y + w10 * i1.x + w01 * i0.y + w00 * i0.x;
+                gxy = fma2(bc(w00), g00, fma2(bc(w01), g01, fma2(bc(w10), g10, mul2(bc(w11), g11))));
             }
             else if constexpr (PACKED)
             {
@@ -196,54 +223,72 @@ namespace mbavo
                 {
                     const float2 g00 = __ldg(lv.ref_dIxy + i00), g01 = __ldg(lv.ref_dIxy + i01);
                     const float2 g10 = __ldg(lv.ref_dIxy + i10), g11 = __ldg(lv.ref_dIxy + i11);
-                    gx = w11 * g11.x + w10 * g10.x + w01 * g01.x + w00 * g00.x;
-                    gy = w11 * g11.y + w10 * g10.y + w01 * g01.y + w00 * g00.y;
+                    gxy = fma2(bc(w00), g00, fma2(bc(w01), g01, fma2(bc(w10), g10, mul2(bc(w11), g11))));
                 }
             }
 
             if constexpr (WITH_J)
             {
-                const float s = (ps.D - a2.w) * il;                 // (D - t_z) / lambda       compute_pixel_intensity.h:128
+                const float4 g3 = rec.q(3); // (Rm00 Rm01) (Rm10 Rm11)
+                const float s = (ps.D - g2.y) * il;                 // (D - t_z) / lambda       compute_pixel_intensity.h:128
                 // dI/dt = dI/dP (I - m e_z^T / lambda)                                   compute_pixel_intensity.h:196-202
-                const float gtx = gx * ps.fxiD, gty = gy * ps.fyiD;
-                const float gtz = -(gtx * m0 + gty * m1) * il;
+                const float2 gt = mul2(gxy, ps.fxyiD);
+                const float gtz = -(gt.x * m01.x + gt.y * m01.y) * il;
                 // dI/dtheta = s (r x R^T dI/dt): right perturbation R <- R Exp(theta) of the pose rotation; equals
-                // dI/dq (compute_pixel_intensity.h:179-206) contracted with dq/dtheta = L(q)[I/2;0]
-                const float b0 = gtx + fmaf(a0.x, gtx, fmaf(a0.w, gty, a1.z * gtz));
-                const float b1 = gty + fmaf(a0.y, gtx, fmaf(a1.x, gty, a1.w * gtz));
-                const float b2 = gtz + fmaf(a0.z, gtx, fmaf(a1.y, gty, a2.x * gtz));
-                const float v0 = s * (ps.ry * b2 - b1);
-                const float v1 = s * (b0 - ps.rx * b2);
-                const float v2 = s * (ps.rx * b1 - ps.ry * b0);
+                // dI/dq (compute_pixel_intensity.h:179-206) contracted with dq/dtheta = L(q)[I/2;0].   b = s R^T dI/dt
+                const float2 b01 = mul2(bc(s), fma2(bc(gt.x), f2(g3.x, g3.y),
+                                                    fma2(bc(gt.y), f2(g3.z, g3.w), fma2(bc(gtz), f2(g1.z, g1.w), gt))));
+                const float b2 = s * fmaf(g1.x, gt.x, fmaf(g1.y, gt.y, fmaf(g2.x, gtz, gtz)));
+                const float v0 = fmaf(ps.rxy.y, b2, -b01.y);
+                const float v1 = fmaf(-ps.rxy.x, b2, b01.x);
+                const float v2 = fmaf(ps.rxy.x, b01.y, -ps.rxy.y * b01.x);
+                // per knot: wt | Th00 Th10 Th20 | (Th01 Th02) (Th11 Th12) (Th21 Th22)
+                constexpr int NC = (10 * K + 3) / 4 * 4;
+                float c[NC];
+#pragma unroll
+                for (int q = 0; q < NC / 4; ++q)
+                {
+                    const float4 v = rec.q(kRecGeom / 4 + q);
+                    c[4 * q] = v.x, c[4 * q + 1] = v.y, c[4 * q + 2] = v.z, c[4 * q + 3] = v.w;
+                }
 #pragma unroll
                 for (int j = 0; j < K; ++j)
                 {
-                    const float wt = rec[12 + j];
-                    const float *Th = rec + 12 + K + 9 * j;
-                    Jt[OFF + j][0] = fmaf(wt, gtx, Jt[OFF + j][0]);
-                    Jt[OFF + j][1] = fmaf(wt, gty, Jt[OFF + j][1]);
-                    Jt[OFF + j][2] = fmaf(wt, gtz, Jt[OFF + j][2]);
-                    Jw[OFF + j][0] = fmaf(v0, Th[0], fmaf(v1, Th[3], fmaf(v2, Th[6], Jw[OFF + j][0])));
-                    Jw[OFF + j][1] = fmaf(v0, Th[1], fmaf(v1, Th[4], fmaf(v2, Th[7], Jw[OFF + j][1])));
-                    Jw[OFF + j][2] = fmaf(v0, Th[2], fmaf(v1, Th[5], fmaf(v2, Th[8], Jw[OFF + j][2])));
+                    const float *k = c + 10 * j;
+                    J[OFF + j][0] = fma2(bc(k[0]), gt, J[OFF + j][0]);
+                    J[OFF + j][1].x = fmaf(k[0], gtz, J[OFF + j][1].x);
+                    J[OFF + j][1].y = fmaf(v0, k[1], fmaf(v1, k[2], fmaf(v2, k[3], J[OFF + j][1].y)));
+                    J[OFF + j][2] = fma2(bc(v0), f2(k[4], k[5]), fma2(bc(v1), f2(k[6], k[7]), fma2(bc(v2), f2(k[8], k[9]), J[OFF + j][2])));
                 }
             }
         }
 
-        template <int K, int NK, bool PACKED, int OFF>
+        // Samples of the segments OFF, OFF + 1, ... in time order.  CREC: records from the launch-parameter table (index i
+        // uniform, step 1); else from shared memory with PH exposure phases (lane-dependent start, step PH).
+        template <int K, int NK, bool PACKED, bool CREC, int OFF, class Tab>
         struct SegmentLoop
         {
-            __device__ __forceinline__ static void run(const float *__restrict__ samples_s, const int *__restrict__ seg_end_s,
-                                                       int &i, int PH, const PixelRegs &ps, const LevelDev &lv, float fxf,
-                                                       float fyf, float &sumI, float (&Jt)[NK][3], float (&Jw)[NK][3])
+            __device__ __forceinline__ static void run(const Tab &tab, int tab_base, const float *__restrict__ samples_s,
+                                                       const int *__restrict__ seg_end_s, int &i, int PH, const PixelRegs &ps,
+                                                       const LevelDev &lv, float2 fxy, float &sumI, float2 (&J)[NK][3])
             {
                 constexpr int REC = sample_rec_floats(K);
-                const int end = seg_end_s[OFF];
-                for (; i < end; i += PH)
-                    sample_step<K, NK, true, PACKED, OFF>(samples_s + i * REC, ps, lv, fxf, fyf, sumI, Jt, Jw);
+                if constexpr (CREC)
+                {
+                    const int end = tab.seg_end[tab_base + OFF];
+                    for (; i < end; ++i)
+                        sample_step<K, NK, true, PACKED, OFF>(ConstRec<Tab>{tab, (tab_base / kMaxSegments * lv.N + i) * REC}, ps, lv, fxy,
+                                                              sumI, J);
+                }
+                else
+                {
+                    const int end = seg_end_s[OFF];
+                    for (; i < end; i += PH)
+                        sample_step<K, NK, true, PACKED, OFF>(SmemRec{samples_s + i * REC}, ps, lv, fxy, sumI, J);
+                }
                 if constexpr (OFF + 1 <= NK - K)
-                    SegmentLoop<K, NK, PACKED, (OFF + 1 <= NK - K ? OFF + 1 : OFF)>::run(samples_s, seg_end_s, i, PH, ps, lv, fxf,
-                                                                                      fyf, sumI, Jt, Jw);
+                    SegmentLoop<K, NK, PACKED, CREC, (OFF + 1 <= NK - K ? OFF + 1 : OFF), Tab>::run(tab, tab_base, samples_s, seg_end_s, i, PH,
+                                                                                            ps, lv, fxy, sumI, J);
             }
         };
 
@@ -261,17 +306,33 @@ namespace mbavo
             return x;
         }
 
-        // K: knots per segment, NK: knots in the window (NK - K + 1 segments touched), WITH_J: Hessian pass or cost only,
-        // PACKED: keyframe texels available.
-        template <int K, int NK, bool WITH_J, bool PACKED>
-        __global__ void __launch_bounds__(kThreads, WITH_J ? (NK <= 3 ? MBAVO_MINB_H : 1) : 4) track_kernel(const TrackParams prm)
+        template <int K, bool CREC>
+        using TableOf = typename std::conditional<CREC, SampleTable<K>, NoTable>::type;
+
+        // Geometry of the staged rows and of the 2x2 tiling of rows^T rows
+        template <int NK, bool WITH_J>
+        struct RowGeom
         {
+            static constexpr int D1 = WITH_J ? 6 * NK + 1 : 1;          // row length: [r | J]
+            static constexpr int D1E = (D1 + 1) & ~1;                    // padded with one zero column to an even length
+            static constexpr int PITCH = (D1E / 2) % 2 == 1 ? D1E : D1E + 2; // even pitch with odd PITCH/2: row writes 2-way at worst
+            static constexpr int T = D1E / 2;                            // tiles per dimension
+            static constexpr int NT = T * (T + 1) / 2;                   // upper-triangular tiles
+            static constexpr int MT = WITH_J ? (NT + 31) / 32 : 1;       // tiles owned by one lane
+            static constexpr int E = WITH_J ? packed_len(NK) : 1;        // packed upper triangle
+        };
+
+        // K: knots per segment, NK: knots in the window (NK - K + 1 segments touched), WITH_J: Hessian pass or cost only,
+        // PACKED: keyframe texels available, CREC: sample records in the launch-parameter table `tab` (else in prm.samples).
+        template <int K, int NK, bool WITH_J, bool PACKED, bool CREC>
+        __global__ void __launch_bounds__(kThreads, WITH_J ? (NK <= 3 ? MBAVO_MINB_H : 1) : 4)
+            track_kernel(const __grid_constant__ TrackParams prm, const __grid_constant__ TableOf<K, CREC> tab)
+        {
+            using Tab = TableOf<K, CREC>;
+            using G = RowGeom<NK, WITH_J>;
             constexpr int REC = sample_rec_floats(K);
             constexpr int NJ = WITH_J ? NK : 1;
-            constexpr int D1 = WITH_J ? 6 * NK + 1 : 1;     // row length: [r | J]
-            constexpr int D1P = D1 | 1;                      // odd row pitch: conflict-free row writes
-            constexpr int E = WITH_J ? packed_len(NK) : 1;   // packed upper triangle
-            constexpr int ME = (E + 31) / 32;                // elements owned by one lane
+            constexpr int D1 = G::D1, PITCH = G::PITCH, NT = G::NT, MT = G::MT, E = G::E;
 
             const LevelDev &lv = prm.lv;
             const int f = blockIdx.y;
@@ -279,63 +340,88 @@ namespace mbavo
             const int S = lv.S, N = lv.N, TP = prm.TP, PH = prm.PH;
             const int Q = 32 / PH;                           // pixel slots per pass
             // lane -> (slot, phase): slot-fastest (a quarter-warp = 8 pixels of one phase) or phase-fastest (a quarter-warp
-            // = 8 consecutive exposure samples of one pixel, which mostly share a 128-byte line)
+            // = 8 consecutive exposure samples of one pixel)
             const bool pf = prm.phase_fast != 0;
             const int slot = pf ? lane / PH : lane & (Q - 1), phase = pf ? lane & (PH - 1) : lane / Q;
             const int bfly_lo = pf ? 1 : Q, bfly_hi = pf ? PH : 32;
 
             extern __shared__ __align__(16) unsigned char smem_raw[];
-            float *samples_s = reinterpret_cast<float *>(smem_raw);                  // N * REC
-            int *seg_end_s = reinterpret_cast<int *>(samples_s + N * REC);          // kMaxSegments (+1 pad)
-            PixelRec *pix_s = reinterpret_cast<PixelRec *>(seg_end_s + 8);          // warps * 32
+            float *samples_s = reinterpret_cast<float *>(smem_raw);                  // N * REC (nothing if CREC)
+            int *seg_end_s = reinterpret_cast<int *>(samples_s + (CREC ? 0 : N * REC)); // kMaxSegments (+1 pad)
+            double *mid_s = reinterpret_cast<double *>(seg_end_s + 8);              // kMidDoubles
+            PixelRec *pix_s = reinterpret_cast<PixelRec *>(mid_s + kMidDoubles);    // warps * 32
             int2 *pattern_s = reinterpret_cast<int2 *>(pix_s + kWarpsPerBlock * 32); // S
             float *rho_s = reinterpret_cast<float *>(pattern_s + S);                // warps * max(32, TP*S)
             const int rho_per_warp = max(32, TP * S);
-            unsigned short *pair_s = reinterpret_cast<unsigned short *>(rho_s + kWarpsPerBlock * rho_per_warp); // E (padded)
-            float *rows_s = reinterpret_cast<float *>(pair_s + ((E + 7) & ~7));    // warps * 32 * D1P
+            unsigned short *tile_s = reinterpret_cast<unsigned short *>(rho_s + kWarpsPerBlock * rho_per_warp); // NT (padded)
+            float *rows_s = reinterpret_cast<float *>(tile_s + ((NT + 7) & ~7));   // warps * 32 * PITCH
             double *red_s = reinterpret_cast<double *>(smem_raw);                   // epilogue: warps * E doubles (aliases all)
 
-            for (int e = threadIdx.x; e < N * REC; e += blockDim.x)
-                samples_s[e] = prm.samples[(size_t)f * N * REC + e];
-            if (threadIdx.x < kMaxSegments)
-                seg_end_s[threadIdx.x] = prm.seg_end[f * kMaxSegments + threadIdx.x];
+            if constexpr (CREC)
+            {
+                if (threadIdx.x == 0)
+                {
+#pragma unroll
+                    for (int e = 0; e < kMidDoubles; ++e)
+                        mid_s[e] = tab.mid[f * kMidDoubles + e];
+                }
+            }
+            else
+            {
+                for (int e = threadIdx.x; e < N * REC; e += blockDim.x)
+                    samples_s[e] = prm.samples[(size_t)f * N * REC + e];
+                if (threadIdx.x < kMaxSegments)
+                    seg_end_s[threadIdx.x] = prm.seg_end[f * kMaxSegments + threadIdx.x];
+                if (threadIdx.x < kMidDoubles)
+                    mid_s[threadIdx.x] = prm.mid[f * kMidDoubles + threadIdx.x];
+            }
             for (int e = threadIdx.x; e < S; e += blockDim.x)
                 pattern_s[e] = lv.pattern[e];
             if (WITH_J)
             {
-                // pair table: packed index e -> (a, b), a <= b, row-major upper triangle of the D1 x D1 matrix
-                for (int e = threadIdx.x; e < E; e += blockDim.x)
+                // tile table: tile id -> (ta, tb), ta <= tb, row-major upper triangle of the T x T tile grid
+                for (int e = threadIdx.x; e < NT; e += blockDim.x)
                 {
                     int a = 0, rem = e;
-                    while (rem >= D1 - a)
+                    while (rem >= G::T - a)
                     {
-                        rem -= D1 - a;
+                        rem -= G::T - a;
                         ++a;
                     }
-                    pair_s[e] = (unsigned short)((a << 8) | (a + rem));
+                    tile_s[e] = (unsigned short)((a << 8) | (a + rem));
                 }
             }
             __syncthreads();
 
-            const double *mid = prm.mid + f * kMidDoubles;
-            const float fxf = (float)lv.fx, fyf = (float)lv.fy;
+            const double *mid = mid_s;
+            const float2 fxy = f2((float)lv.fx, (float)lv.fy);
             const float inv_N = 1.0f / (float)N;
             const float huber_a = prm.huber_a;
             const double inv_num_residuals = prm.inv_num_residuals;
-            float *my_rows = rows_s + warp * 32 * D1P;
+            float *my_rows = rows_s + warp * 32 * PITCH;
             float *my_rho = rho_s + warp * rho_per_warp;
             PixelRec *my_pix = pix_s + warp * 32;
 
-            double acc[ME];
+            // this lane's tiles (offsets of the two operand pairs inside a row) and their fp64 accumulators
+            int tile_a[MT], tile_b[MT];
+            double acc[MT][4];
 #pragma unroll
-            for (int m = 0; m < ME; ++m)
-                acc[m] = 0.0;
+            for (int m = 0; m < MT; ++m)
+            {
+                const int id = lane + 32 * m;
+                const unsigned int t = (WITH_J && id < NT) ? tile_s[id] : 0u;
+                tile_a[m] = 2 * (int)(t >> 8), tile_b[m] = 2 * (int)(t & 0xff);
+                acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.0;
+            }
             double cost_acc = 0.0;
 
             const int items = TP * S;
-            for (int wb = blockIdx.x * kWarpsPerBlock + warp; wb < prm.batches_per_frame; wb += gridDim.x * kWarpsPerBlock)
+            // Block-uniform trip count (a warp past the last batch walks an all-invalid batch): loops whose bounds depend on
+            // threadIdx keep the compiler from using the uniform datapath for the sample index and the record loads.
+            for (int wb0 = blockIdx.x * kWarpsPerBlock; wb0 < prm.batches_per_frame; wb0 += gridDim.x * kWarpsPerBlock)
             {
-                const int p0 = wb * TP;
+                const int wb = wb0 + warp;
+                const int p0 = wb < prm.batches_per_frame ? wb * TP : lv.P;
                 for (int base = 0; base < items; base += 32)
                 {
                     // ---- A: pixel records -----------------------------------------------------------------------------
@@ -354,30 +440,38 @@ namespace mbavo
                         const int4 r1 = *(reinterpret_cast<const int4 *>(my_pix + q) + 1);
                         const bool valid = r1.w & 1;
                         PixelRegs ps;
-                        ps.rx = r0.x, ps.ry = r0.y, ps.D = r0.z, ps.iD = r0.w;
+                        ps.rxy = f2(r0.x, r0.y), ps.D = r0.z, ps.iD = r0.w;
                         ps.X = r1.y, ps.Y = r1.z;
                         ps.lox = -(float)ps.X, ps.hix = (float)(lv.W - 1 - ps.X);
                         ps.loy = -(float)ps.Y, ps.hiy = (float)(lv.H - 1 - ps.Y);
-                        ps.fxiD = fxf * ps.iD, ps.fyiD = fyf * ps.iD;
+                        ps.fxyiD = mul2(fxy, bc(ps.iD));
 
                         float sumI = 0.f;
-                        float Jt[NJ][3], Jw[NJ][3];
+                        float2 J[NJ][3];
 #pragma unroll
                         for (int a = 0; a < NJ; ++a)
-                            Jt[a][0] = Jt[a][1] = Jt[a][2] = Jw[a][0] = Jw[a][1] = Jw[a][2] = 0.f;
+                            J[a][0] = J[a][1] = J[a][2] = f2(0.f, 0.f);
 
-                        if (valid)
+                        // An invalid pixel walks the samples too, with an empty validity window: the sample loops stay
+                        // free of thread-dependent control flow around them, which lets the compiler keep the sample index
+                        // and the record loads on the uniform datapath.
+                        if (!valid)
+                            ps.lox = ps.loy = __int_as_float(0x7f800000), ps.hix = ps.hiy = __int_as_float(0xff800000);
+                        if constexpr (WITH_J)
                         {
-                            if constexpr (WITH_J)
-                            {
-                                int i = phase;
-                                SegmentLoop<K, NK, PACKED, 0>::run(samples_s, seg_end_s, i, PH, ps, lv, fxf, fyf, sumI, Jt, Jw);
-                            }
-                            else
-                            {
-                                for (int i = phase; i < N; i += PH) // cost only: the segment of a sample is irrelevant
-                                    sample_step<K, NK, false, PACKED, 0>(samples_s + i * REC, ps, lv, fxf, fyf, sumI, Jt, Jw);
-                            }
+                            int i = CREC ? 0 : phase;
+                            SegmentLoop<K, NK, PACKED, CREC, 0, Tab>::run(tab, f * kMaxSegments, samples_s, seg_end_s, i, PH, ps, lv, fxy,
+                                                                          sumI, J);
+                        }
+                        else if constexpr (CREC)
+                        {
+                            for (int i = 0; i < N; ++i) // cost only: the segment of a sample is irrelevant
+                                sample_step<K, NK, false, PACKED, 0>(ConstRec<Tab>{tab, (f * N + i) * REC}, ps, lv, fxy, sumI, J);
+                        }
+                        else
+                        {
+                            for (int i = phase; i < N; i += PH)
+                                sample_step<K, NK, false, PACKED, 0>(SmemRec{samples_s + i * REC}, ps, lv, fxy, sumI, J);
                         }
                         // combine the PH phases of every pixel (fixed butterfly order: deterministic)
                         for (int o = bfly_lo; o < bfly_hi; o <<= 1)
@@ -391,8 +485,8 @@ namespace mbavo
 #pragma unroll
                                     for (int c = 0; c < 3; ++c)
                                     {
-                                        Jt[a][c] += __shfl_xor_sync(0xffffffffu, Jt[a][c], o);
-                                        Jw[a][c] += __shfl_xor_sync(0xffffffffu, Jw[a][c], o);
+                                        J[a][c].x += __shfl_xor_sync(0xffffffffu, J[a][c].x, o);
+                                        J[a][c].y += __shfl_xor_sync(0xffffffffu, J[a][c].y, o);
                                     }
                                 }
                             }
@@ -408,19 +502,21 @@ namespace mbavo
                             if constexpr (WITH_J)
                             {
                                 const float scale = (r1.w == 1) ? sw : 0.f; // invalid pixels and outliers add nothing (…cost.cu:267)
-                                float *row = my_rows + q * D1P;
+                                float *row = my_rows + q * PITCH;
                                 row[0] = scale * r;
                                 const float sj = scale * inv_N;
+                                // row = [r | t-block of every knot | w-block of every knot] (merge_hessian_gradient_cost.cpp:52-62)
 #pragma unroll
                                 for (int a = 0; a < NK; ++a)
                                 {
-                                    row[1 + 3 * a + 0] = sj * Jt[a][0];
-                                    row[1 + 3 * a + 1] = sj * Jt[a][1];
-                                    row[1 + 3 * a + 2] = sj * Jt[a][2];
-                                    row[1 + 3 * NK + 3 * a + 0] = sj * Jw[a][0];
-                                    row[1 + 3 * NK + 3 * a + 1] = sj * Jw[a][1];
-                                    row[1 + 3 * NK + 3 * a + 2] = sj * Jw[a][2];
+                                    row[1 + 3 * a + 0] = sj * J[a][0].x;
+                                    row[1 + 3 * a + 1] = sj * J[a][0].y;
+                                    row[1 + 3 * a + 2] = sj * J[a][1].x;
+                                    row[1 + 3 * NK + 3 * a + 0] = sj * J[a][1].y;
+                                    row[1 + 3 * NK + 3 * a + 1] = sj * J[a][2].x;
+                                    row[1 + 3 * NK + 3 * a + 2] = sj * J[a][2].y;
                                 }
+                                row[D1] = 0.f; // padding column of the 2x2 tiling
                             }
                         }
                     }
@@ -429,25 +525,30 @@ namespace mbavo
                         // rows of a short last chunk: zero
                         if (lane >= chunk)
                         {
-                            float *row = my_rows + lane * D1P;
+                            float *row = my_rows + lane * PITCH;
 #pragma unroll
-                            for (int c = 0; c < D1; ++c)
+                            for (int c = 0; c <= D1; ++c)
                                 row[c] = 0.f;
                         }
                         __syncwarp();
-                        // ---- C: packed upper triangle of rows^T rows (…cost.cu:214-230): lane owns elements lane, lane+32, …
+                        // ---- C: rows^T rows (…cost.cu:214-230) in 2x2 tiles: (a0 a1)^T (b0 b1) summed over the 32 rows
 #pragma unroll
-                        for (int m = 0; m < ME; ++m)
+                        for (int m = 0; m < MT; ++m)
                         {
-                            const int e = lane + 32 * m;
-                            if (e < E)
+                            if (lane + 32 * m < NT)
                             {
-                                const int a = pair_s[e] >> 8, b = pair_s[e] & 0xff;
-                                float sacc = 0.f;
+                                const float *pa = my_rows + tile_a[m], *pb = my_rows + tile_b[m];
+                                float2 s0 = f2(0.f, 0.f), s1 = f2(0.f, 0.f);
 #pragma unroll 8
                                 for (int qq = 0; qq < 32; ++qq)
-                                    sacc = fmaf(my_rows[qq * D1P + a], my_rows[qq * D1P + b], sacc);
-                                acc[m] += (double)sacc;
+                                {
+                                    const float2 va = *reinterpret_cast<const float2 *>(pa + qq * PITCH);
+                                    const float2 vb = *reinterpret_cast<const float2 *>(pb + qq * PITCH);
+                                    s0 = fma2(bc(va.x), vb, s0);
+                                    s1 = fma2(bc(va.y), vb, s1);
+                                }
+                                acc[m][0] += (double)s0.x, acc[m][1] += (double)s0.y;
+                                acc[m][2] += (double)s1.x, acc[m][3] += (double)s1.y;
                             }
                         }
                     }
@@ -470,17 +571,29 @@ namespace mbavo
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
                 cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, o);
-            if (lane == 0)
-                acc[0] = cost_acc; // packed[0] is the cost, not r^2 (…cost.cu:232-238)
 
             __syncthreads(); // every warp is done with samples_s / rows_s before red_s (aliasing them) is written
-#pragma unroll
-            for (int m = 0; m < ME; ++m)
+            if constexpr (WITH_J)
             {
-                const int e = lane + 32 * m;
-                if (e < E)
-                    red_s[warp * E + e] = acc[m];
+                // tile element (i, j) is matrix element (r, c) = (tile_a + i, tile_b + j); packed index of the upper triangle
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                {
+                    if (lane + 32 * m < NT)
+                    {
+#pragma unroll
+                        for (int ij = 0; ij < 4; ++ij)
+                        {
+                            const int r = tile_a[m] + (ij >> 1), c = tile_b[m] + (ij & 1);
+                            if (r <= c && c < D1)
+                                red_s[warp * E + r * D1 - r * (r - 1) / 2 + (c - r)] = acc[m][ij];
+                        }
+                    }
+                }
+                __syncwarp();
             }
+            if (lane == 0)
+                red_s[warp * E] = cost_acc; // packed[0] is the cost, not sum r^2 (…cost.cu:232-238)
             __syncthreads();
             const int block_linear = blockIdx.y * gridDim.x + blockIdx.x;
             const int num_blocks = gridDim.x * gridDim.y;
@@ -525,122 +638,58 @@ namespace mbavo
             }
         }
 
-        // Keyframe texels (see LevelDev).  One thread per pixel; *inexact counts gradient values that fp16 cannot hold.
-        __global__ void pack_kernel(const unsigned char *__restrict__ I, const float2 *__restrict__ g, int H, int W,
-                                    uint4 *__restrict__ pair, unsigned int *__restrict__ quad, int *__restrict__ inexact)
-        {
-            const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-            if (x >= W)
-                return;
-            const int x1 = min(x + 1, W - 1), y1 = min(y + 1, H - 1);
-            const int i00 = y * W + x, i01 = y * W + x1, i10 = y1 * W + x, i11 = y1 * W + x1;
-            const unsigned int b00 = I[i00], b01 = I[i01], b10 = I[i10], b11 = I[i11];
-            quad[i00] = b00 | (b01 << 8) | (b10 << 16) | (b11 << 24);
-            const float2 g0 = g[i00], g1 = g[i01];
-            const __half hx0 = __float2half_rn(g0.x), hy0 = __float2half_rn(g0.y);
-            const __half hx1 = __float2half_rn(g1.x), hy1 = __float2half_rn(g1.y);
-            // bitwise round trip (also rejects NaN and values that overflow to inf)
-            if (__float_as_uint(__half2float(hx0)) != __float_as_uint(g0.x) ||
-                __float_as_uint(__half2float(hy0)) != __float_as_uint(g0.y))
-                atomicAdd(inexact, 1);
-            const unsigned int hI0 = __half_as_ushort(__float2half_rn((float)b00)), hI1 = __half_as_ushort(__float2half_rn((float)b01));
-            uint4 t;
-            t.x = hI0 | ((unsigned int)__half_as_ushort(hx0) << 16);
-            t.y = (unsigned int)__half_as_ushort(hy0) | (hI1 << 16);
-            t.z = (unsigned int)__half_as_ushort(hx1) | ((unsigned int)__half_as_ushort(hy1) << 16);
-            t.w = 0u;
-            pair[i00] = t;
-        }
-
-        template <int K, int NK, bool WITH_J, bool PACKED>
-        cudaError_t launch_one(const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream)
+        template <int K, int NK, bool WITH_J, bool PACKED, bool CREC>
+        cudaError_t launch_one(const TrackParams &prm, const void *table, dim3 grid, size_t smem, cudaStream_t stream)
         {
             static unsigned long long configured = 0; // per instantiation and per device (attribute of the device function)
             int dev = 0;
             cudaGetDevice(&dev);
             if (!(configured >> dev & 1ull))
             {
-                cudaError_t e = cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED>,
+                cudaError_t e = cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED, CREC>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
                 if (e != cudaSuccess)
                     return e;
                 configured |= 1ull << dev;
             }
-            track_kernel<K, NK, WITH_J, PACKED><<<grid, kThreads, smem, stream>>>(prm);
+            static const NoTable none{};
+            const auto *tab = reinterpret_cast<const TableOf<K, CREC> *>(CREC ? table : static_cast<const void *>(&none));
+            track_kernel<K, NK, WITH_J, PACKED, CREC><<<grid, kThreads, smem, stream>>>(prm, *tab);
             return cudaGetLastError();
         }
 
         // Occupancy-derived grid width for one instantiation
-        template <int K, int NK, bool WITH_J, bool PACKED>
+        template <int K, int NK, bool WITH_J, bool PACKED, bool CREC>
         int blocks_per_sm(size_t smem)
         {
             int n = 0;
-            cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, track_kernel<K, NK, WITH_J, PACKED>, kThreads, smem);
+            cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED, CREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, track_kernel<K, NK, WITH_J, PACKED, CREC>, kThreads, smem);
             return n > 0 ? n : 1;
         }
 
+        // One (K, NK, WITH_J): the four (texels, record source) variants
         template <int K, int NK, bool WITH_J>
-        cudaError_t dispatch_packed(bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
-                                    int *query_occupancy)
+        cudaError_t dispatch_variant(bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid, size_t smem,
+                                     cudaStream_t stream, int *query_occupancy)
         {
-            if (query_occupancy)
-            {
-                *query_occupancy = packed ? blocks_per_sm<K, NK, WITH_J, true>(smem) : blocks_per_sm<K, NK, WITH_J, false>(smem);
-                return cudaSuccess;
-            }
-            return packed ? launch_one<K, NK, WITH_J, true>(prm, grid, smem, stream)
-                          : launch_one<K, NK, WITH_J, false>(prm, grid, smem, stream);
-        }
-    } // namespace
-
-    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, int N, int S, int TP)
-    {
-        const int REC = sample_rec_floats(K);
-        const int D1 = with_j ? 6 * NK + 1 : 1, D1P = D1 | 1;
-        const int E = with_j ? packed_len(NK) : 1;
-        const int rho_per_warp = max(32, TP * S);
-        size_t main_bytes = (size_t)N * REC * 4 + 8 * 4 + (size_t)kWarpsPerBlock * 32 * sizeof(PixelRec) + (size_t)S * 8 +
-                            (size_t)kWarpsPerBlock * rho_per_warp * 4 + (size_t)((E + 7) & ~7) * 2 +
-                            (size_t)kWarpsPerBlock * 32 * D1P * 4;
-        size_t red_bytes = (size_t)kWarpsPerBlock * E * 8;
-        return (main_bytes > red_bytes ? main_bytes : red_bytes) + 16;
+#define MBAVO_VARIANT(P_, C_)                                                             \
+    if (packed == P_ && crec == C_)                                                       \
+    {                                                                                     \
+        if (query_occupancy)                                                              \
+        {                                                                                 \
+            *query_occupancy = blocks_per_sm<K, NK, WITH_J, P_, C_>(smem);                \
+            return cudaSuccess;                                                           \
+        }                                                                                 \
+        return launch_one<K, NK, WITH_J, P_, C_>(prm, table, grid, smem, stream);         \
     }
-
-    cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,
-                                   int *inexact, cudaStream_t stream)
-    {
-        const dim3 block(128, 1, 1), grid((W + 127) / 128, H, 1);
-        pack_kernel<<<grid, block, 0, stream>>>(I, reinterpret_cast<const float2 *>(dIxy), H, W, pair, quad, inexact);
-        return cudaGetLastError();
-    }
-
-#define MBAVO_DISPATCH(K_, NK_)   \
-    if (K == K_ && NK == NK_)     \
-        return dispatch_packed<K_, NK_, true>(packed, prm, grid, smem, stream, query_occupancy);
-
-    // with_j: Hessian pass (templated on the window) or cost-only pass (one instantiation per K)
-    cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, dim3 grid, size_t smem,
-                                    cudaStream_t stream, int *query_occupancy)
-    {
-        const bool packed = prm.lv.ref_pair != nullptr || (query_occupancy && prm.PH < 0);
-        if (!with_j)
-        {
-            if (K == 2)
-                return dispatch_packed<2, 2, false>(packed, prm, grid, smem, stream, query_occupancy);
-            if (K == 4)
-                return dispatch_packed<4, 4, false>(packed, prm, grid, smem, stream, query_occupancy);
+            MBAVO_VARIANT(true, true)
+            MBAVO_VARIANT(true, false)
+            MBAVO_VARIANT(false, true)
+            MBAVO_VARIANT(false, false)
+#undef MBAVO_VARIANT
             return cudaErrorInvalidValue;
         }
-        MBAVO_DISPATCH(2, 2)
-        MBAVO_DISPATCH(2, 3)
-        MBAVO_DISPATCH(2, 4)
-        MBAVO_DISPATCH(2, 5)
-        MBAVO_DISPATCH(2, 6)
-        MBAVO_DISPATCH(4, 4)
-        MBAVO_DISPATCH(4, 5)
-        MBAVO_DISPATCH(4, 6)
-        MBAVO_DISPATCH(4, 7)
-        return cudaErrorInvalidValue;
-    }
+    } // namespace
 } // namespace mbavo
+#endif
