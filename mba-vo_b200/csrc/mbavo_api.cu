@@ -19,10 +19,9 @@ namespace mbavo
 {
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
                                    double *mid, int *seg_end, cudaStream_t stream);
-    void compute_sample_records_host(int K, const EvalStage &stage, int with_jacobian, float *samples, double *mid, int *seg_end);
-    cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, const void *table, dim3 grid, size_t smem,
-                                    cudaStream_t stream, int *query_occupancy);
-    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool crec, int N, int S, int TP);
+    cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
+                                    int *query_occupancy, bool dependent);
+    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, int N, int S, int TP);
     cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,
                                    int *inexact, cudaStream_t stream);
 } // namespace mbavo
@@ -89,9 +88,7 @@ struct mbavo_ctx
     LevelStore levels[MBAVO_MAX_LEVELS];
 
     EvalStage stage{};       // spline state of the evaluation being issued (launch parameter of the pose kernel)
-    SampleTable<2> tab2{};   // host-computed sample records of the evaluation being issued (launch parameter of the
-    SampleTable<4> tab4{};   // tracking kernel), k = 2 / k = 4
-    bool use_table = true;   // MBAVO_NO_TABLE=1: always pose kernel -> global -> shared memory
+    bool use_pdl = true;     // MBAVO_NO_PDL=1: tracking kernel fully serialised behind the pose kernel
     float *samples = nullptr;
     double *mid = nullptr;
     int *seg_end = nullptr;
@@ -241,7 +238,6 @@ namespace
     {
         int K, NK, kmin, N, F, P, S, TP, PH, batches_per_frame;
         bool with_h;
-        bool crec; // sample records travel as launch parameter (host-computed) instead of pose kernel -> global -> shared
         dim3 grid;
         size_t smem;
         int E;
@@ -299,26 +295,23 @@ namespace
             while (pl.PH > pl.N)
                 pl.PH >>= 1;
         }
-        pl.crec = ctx->use_table && pl.PH == 1 && pl.F * pl.N <= kTableSamples;
-        pl.smem = track_kernel_smem_bytes(pl.K, pl.NK, with_h, pl.crec, pl.N, pl.S, pl.TP);
+        pl.smem = track_kernel_smem_bytes(pl.K, pl.NK, with_h, pl.N, pl.S, pl.TP);
         if (pl.smem > 200 * 1024)
             return fail(MBAVO_ECAPACITY, "shared memory need %zu B exceeds 200 KiB (N=%d, S=%d, window=%d)", pl.smem, pl.N, pl.S,
                         pl.NK);
         int occ = 0;
         const int packed = L.dev.ref_pair != nullptr ? 1 : 0;
         for (const auto &c : ctx->occ_cache)
-            if (c.K == pl.K && c.NK == pl.NK && c.with_h == (with_h ? 1 : 0) && c.packed == packed + 2 * (pl.crec ? 1 : 0) &&
-                c.smem == pl.smem)
+            if (c.K == pl.K && c.NK == pl.NK && c.with_h == (with_h ? 1 : 0) && c.packed == packed && c.smem == pl.smem)
                 occ = c.occ;
         if (occ == 0)
         {
             TrackParams query{};
             query.lv = L.dev; // selects the texel / direct-gather instantiation
-            cudaError_t e = launch_track_kernel(pl.K, pl.NK, with_h, query, pl.crec ? (const void *)&ctx->tab2 : nullptr, dim3(), pl.smem,
-                                                nullptr, &occ);
+            cudaError_t e = launch_track_kernel(pl.K, pl.NK, with_h, query, dim3(), pl.smem, nullptr, &occ, false);
             if (e != cudaSuccess)
                 return fail(MBAVO_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e));
-            ctx->occ_cache.push_back({pl.K, pl.NK, with_h ? 1 : 0, packed + 2 * (pl.crec ? 1 : 0), pl.smem, occ});
+            ctx->occ_cache.push_back({pl.K, pl.NK, with_h ? 1 : 0, packed, pl.smem, occ});
         }
         int want = (pl.batches_per_frame + kWarpsPerBlock - 1) / kWarpsPerBlock;
         int cap_blocks = ctx->num_sms * occ / pl.F;
@@ -353,21 +346,8 @@ namespace
             ctx->block_partials_cap = need;
         }
         L.last_eval_frames = pl.F;
-        const void *table = nullptr;
-        if (pl.crec)
-        {
-            // sample records on the host, straight into the launch-parameter table
-            if (pl.K == 2)
-                compute_sample_records_host(2, ctx->stage, pl.with_h ? 1 : 0, ctx->tab2.rec, ctx->tab2.mid, ctx->tab2.seg_end), table = &ctx->tab2;
-            else
-                compute_sample_records_host(4, ctx->stage, pl.with_h ? 1 : 0, ctx->tab4.rec, ctx->tab4.mid, ctx->tab4.seg_end), table = &ctx->tab4;
-            ctx->launches += 1;
-        }
-        else
-        {
-            CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, pl.with_h ? 1 : 0, ctx->samples, ctx->mid, ctx->seg_end, s));
-            ctx->launches += 2;
-        }
+        ctx->launches += 2;
+        CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, pl.with_h ? 1 : 0, ctx->samples, ctx->mid, ctx->seg_end, s));
         TrackParams prm{};
         prm.lv = L.dev;
         prm.samples = ctx->samples;
@@ -390,7 +370,8 @@ namespace
         }
         if (ctx->timing)
             CUDA_TRY(cudaEventRecord(ctx->ev0, s));
-        CUDA_TRY(launch_track_kernel(pl.K, pl.NK, pl.with_h, prm, table, pl.grid, pl.smem, s, nullptr));
+        // event timing brackets the tracking kernel alone, so it is then launched fully serialised
+        CUDA_TRY(launch_track_kernel(pl.K, pl.NK, pl.with_h, prm, pl.grid, pl.smem, s, nullptr, ctx->use_pdl && !ctx->timing));
         if (ctx->timing)
             CUDA_TRY(cudaEventRecord(ctx->ev1, s));
         return MBAVO_OK;
@@ -476,8 +457,8 @@ extern "C"
         CUDA_TRY(cudaEventCreate(&ctx->ev1));
         CUDA_TRY(cudaMalloc(&ctx->inexact_dev, sizeof(int)));
         CUDA_TRY(cudaMallocHost(&ctx->inexact_host, sizeof(int)));
-        const char *g = getenv("MBAVO_NO_TABLE");
-        ctx->use_table = !(g && g[0] == '1');
+        const char *g = getenv("MBAVO_NO_PDL");
+        ctx->use_pdl = !(g && g[0] == '1');
         g = getenv("MBAVO_NO_TEXELS");
         ctx->use_texels = !(g && g[0] == '1');
         g = getenv("MBAVO_PHASE_FAST");
@@ -654,6 +635,7 @@ extern "C"
         }
         L.dev.H = d->H, L.dev.W = d->W;
         L.dev.fx = d->fx, L.dev.fy = d->fy, L.dev.cx = d->cx, L.dev.cy = d->cy;
+        L.dev.inv_fx = 1.0 / d->fx, L.dev.inv_fy = 1.0 / d->fy;
         L.dev.P = P, L.dev.S = d->patch_size, L.dev.N = d->num_virtual_poses, L.dev.F = F;
         L.dev.pattern = L.pattern;
         L.dev.flags = d->ext_outlier_flags ? d->ext_outlier_flags : L.flags;

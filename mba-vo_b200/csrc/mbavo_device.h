@@ -17,17 +17,16 @@ namespace mbavo
     // that every operand PAIR of the kernel's packed FFMA2 arithmetic is an aligned pair of one 128-bit shared load.
     // With Rm = R - I (rotation matrix of the pose quaternion minus identity, rounded after the subtraction,
     // compute_virtual_camera_poses.cu:102-109) and t the translation:
-    //   [0..5]    (Rm00 Rm10) (Rm01 Rm11) (Rm02 Rm12)      column pairs:  (A0, A1) = rx c0 + ry c1 + c2
-    //   [6..9]    (Rm20 Rm21) Rm22 tz
-    //   [10..11]  (tx ty)
-    //   [12..15]  (Rm00 Rm01) (Rm10 Rm11)                  row pairs:     R^T g
+    //   [0..3]    (Rm00 Rm01) (Rm10 Rm11)                  row pairs of the upper-left block:  R^T g
+    //   [4..7]    (Rm20 Rm21) Rm02 Rm12
+    //   [8..11]   Rm22 tz (tx ty)
     //   then per knot j of the segment (10 floats each):
     //     wt_j                      translation blend weight                               (SplineFunctor.h:30-40, 74-91)
     //     Th00 Th10 Th20            first column of Theta_j
     //     (Th01 Th02) (Th11 Th12) (Th21 Th22)   remaining columns as row pairs
     //   Theta_j (3x3) = d theta / d w_j, theta the right perturbation of the pose rotation:
     //   dq/dw_j = L(q) [I/2; 0] Theta_j                                                    (SplineFunctor.h:178-213, 274-361)
-    constexpr int kRecGeom = 16;
+    constexpr int kRecGeom = 12;
     __host__ __device__ constexpr int sample_rec_floats(int K) { return (kRecGeom + 10 * K + 3) / 4 * 4; }
 
     // per-frame fp64 data for the patch centre (compute_local_patches_xy.cu:26-49): R_r2c (9) and t_r2c (3)
@@ -63,6 +62,7 @@ namespace mbavo
         const unsigned char *cur_I[kMaxFrames];
         int H, W;
         double fx, fy, cx, cy;
+        double inv_fx, inv_fy;
         const char *xy;     // records with two doubles at byte offset xy_offset, stride xy_stride
         int xy_stride, xy_offset;
         const double *z;
@@ -71,24 +71,6 @@ namespace mbavo
         const unsigned char *flags; // 1 = outlier
         double *patch_cost;         // [F * P * patch_cost_stride]
         int patch_cost_stride;
-    };
-
-    // Sample records, mid-exposure poses and segment ranges of one evaluation as a LAUNCH PARAMETER of the tracking
-    // kernel (11 KB for k = 2, 16 KB for k = 4; parameters may be 32 KB): the host computes them (pose_kernel.cu,
-    // compute_sample_records_host), the kernel reads them through the constant bank with uniform loads (LDCU) straight
-    // into FFMA operands — no shared-memory traffic, no vector registers, no pose kernel launch.  Used whenever the
-    // evaluation has at most kTableSamples exposure samples in total (the reference tracker: 1 frame, N <= 64).
-    constexpr int kTableSamples = 64;
-    template <int K>
-    struct SampleTable
-    {
-        float rec[kTableSamples * sample_rec_floats(K)];
-        double mid[kMaxFrames * kMidDoubles];
-        int seg_end[kMaxFrames * kMaxSegments];
-    };
-    struct NoTable
-    {
-        int unused;
     };
 
     struct TrackParams

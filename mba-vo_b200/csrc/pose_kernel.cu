@@ -308,10 +308,9 @@ namespace mbavo
             float Rm[9];
             for (int e = 0; e < 9; ++e)
                 Rm[e] = (float)(R[e] - ((e & 3) == 0 ? 1.0 : 0.0));
-            rec[0] = Rm[0], rec[1] = Rm[3], rec[2] = Rm[1], rec[3] = Rm[4], rec[4] = Rm[2], rec[5] = Rm[5];
-            rec[6] = Rm[6], rec[7] = Rm[7], rec[8] = Rm[8], rec[9] = (float)tt[2];
-            rec[10] = (float)tt[0], rec[11] = (float)tt[1];
-            rec[12] = Rm[0], rec[13] = Rm[1], rec[14] = Rm[3], rec[15] = Rm[4];
+            rec[0] = Rm[0], rec[1] = Rm[1], rec[2] = Rm[3], rec[3] = Rm[4];
+            rec[4] = Rm[6], rec[5] = Rm[7], rec[6] = Rm[2], rec[7] = Rm[5];
+            rec[8] = Rm[8], rec[9] = (float)tt[2], rec[10] = (float)tt[0], rec[11] = (float)tt[1];
             for (int j = 0; j < K; ++j)
             {
                 float *c = rec + kRecGeom + 10 * j;
@@ -353,24 +352,12 @@ namespace mbavo
         __global__ void pose_kernel(const __grid_constant__ EvalStage stage, int with_jacobian, float *__restrict__ samples,
                                     double *__restrict__ mid, int *__restrict__ seg_end)
         {
+            cudaTriggerProgrammaticLaunchCompletion(); // the tracking kernel may start its prologue now
             const int g = blockIdx.x * blockDim.x + threadIdx.x;
             if (g < stage.N * stage.F)
                 pose_one<K>(&stage, g, with_jacobian, samples, mid, seg_end);
         }
     } // namespace
-
-    // The same records on the host (they then travel to the tracking kernel as a launch parameter)
-    void compute_sample_records_host(int K, const EvalStage &stage, int with_jacobian, float *samples, double *mid, int *seg_end)
-    {
-        const int total = stage.N * stage.F;
-        for (int g = 0; g < total; ++g)
-        {
-            if (K == 2)
-                pose_one<2>(&stage, g, with_jacobian, samples, mid, seg_end);
-            else
-                pose_one<4>(&stage, g, with_jacobian, samples, mid, seg_end);
-        }
-    }
 
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
                                    double *mid, int *seg_end, cudaStream_t stream)

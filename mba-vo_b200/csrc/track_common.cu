@@ -5,14 +5,14 @@
 
 namespace mbavo
 {
-    cudaError_t track_dispatch_k2_lo(int NK, bool with_j, bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid,
-                                     size_t smem, cudaStream_t stream, int *query_occupancy);
-    cudaError_t track_dispatch_k2_hi(int NK, bool with_j, bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid,
-                                     size_t smem, cudaStream_t stream, int *query_occupancy);
-    cudaError_t track_dispatch_k4_lo(int NK, bool with_j, bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid,
-                                     size_t smem, cudaStream_t stream, int *query_occupancy);
-    cudaError_t track_dispatch_k4_hi(int NK, bool with_j, bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid,
-                                     size_t smem, cudaStream_t stream, int *query_occupancy);
+    cudaError_t track_dispatch_k2_lo(int NK, bool with_j, bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
+                                     int *query_occupancy, bool dependent);
+    cudaError_t track_dispatch_k2_hi(int NK, bool with_j, bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
+                                     int *query_occupancy, bool dependent);
+    cudaError_t track_dispatch_k4_lo(int NK, bool with_j, bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
+                                     int *query_occupancy, bool dependent);
+    cudaError_t track_dispatch_k4_hi(int NK, bool with_j, bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
+                                     int *query_occupancy, bool dependent);
 
     namespace
     {
@@ -45,18 +45,20 @@ namespace mbavo
 
     } // namespace
 
-    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool crec, int N, int S, int TP)
+    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, int N, int S, int TP)
     {
         const int REC = sample_rec_floats(K);
         const int D1 = with_j ? 6 * NK + 1 : 1, D1E = (D1 + 1) & ~1;
         const int PITCH = (D1E / 2) % 2 == 1 ? D1E : D1E + 2, T = D1E / 2, NT = T * (T + 1) / 2;
         const int E = with_j ? packed_len(NK) : 1;
         const int rho_per_warp = max(32, TP * S);
-        size_t main_bytes = (crec ? 0 : (size_t)N * REC * 4) + 8 * 4 + kMidDoubles * 8 + (size_t)kWarpsPerBlock * 32 * 32 /* PixelRec */ +
+        size_t main_bytes = (size_t)N * REC * 4 + 8 * 4 + kMidDoubles * 8 + (size_t)kWarpsPerBlock * 32 * 32 /* PixelRec */ +
                             (size_t)S * 8 +
                             (size_t)kWarpsPerBlock * rho_per_warp * 4 + (size_t)((NT + 7) & ~7) * 2 +
                             (size_t)kWarpsPerBlock * 32 * PITCH * 4;
-        size_t red_bytes = (size_t)kWarpsPerBlock * E * 8;
+        const int MT = with_j ? (NT + 31) / 32 : 1;
+        main_bytes += 8 + (with_j ? (size_t)kWarpsPerBlock * MT * 4 * 32 * 8 : 0); // fp64 tile accumulators
+        size_t red_bytes = (size_t)(kWarpsPerBlock > (kThreads / E + 1) ? kWarpsPerBlock : kThreads / E + 1) * E * 8;
         return (main_bytes > red_bytes ? main_bytes : red_bytes) + 16;
     }
 
@@ -68,18 +70,18 @@ namespace mbavo
         return cudaGetLastError();
     }
 
-    // with_j: Hessian pass (templated on the window) or cost-only pass (one instantiation per K).  table: host pointer to
-    // the SampleTable<K> to pass as launch parameter, or nullptr (records in prm.samples).
-    cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, const void *table, dim3 grid, size_t smem,
-                                    cudaStream_t stream, int *query_occupancy)
+    // with_j: Hessian pass (templated on the window) or cost-only pass (one instantiation per K).  dependent: launch with
+    // programmatic stream serialisation (the previous kernel in the stream is the pose kernel).
+    cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
+                                    int *query_occupancy, bool dependent)
     {
-        const bool packed = prm.lv.ref_pair != nullptr, crec = table != nullptr;
+        const bool packed = prm.lv.ref_pair != nullptr;
         if (K == 2)
-            return (!with_j || NK <= 3) ? track_dispatch_k2_lo(NK, with_j, packed, crec, prm, table, grid, smem, stream, query_occupancy)
-                                        : track_dispatch_k2_hi(NK, with_j, packed, crec, prm, table, grid, smem, stream, query_occupancy);
+            return (!with_j || NK <= 3) ? track_dispatch_k2_lo(NK, with_j, packed, prm, grid, smem, stream, query_occupancy, dependent)
+                                        : track_dispatch_k2_hi(NK, with_j, packed, prm, grid, smem, stream, query_occupancy, dependent);
         if (K == 4)
-            return (!with_j || NK <= 5) ? track_dispatch_k4_lo(NK, with_j, packed, crec, prm, table, grid, smem, stream, query_occupancy)
-                                        : track_dispatch_k4_hi(NK, with_j, packed, crec, prm, table, grid, smem, stream, query_occupancy);
+            return (!with_j || NK <= 5) ? track_dispatch_k4_lo(NK, with_j, packed, prm, grid, smem, stream, query_occupancy, dependent)
+                                        : track_dispatch_k4_hi(NK, with_j, packed, prm, grid, smem, stream, query_occupancy, dependent);
         return cudaErrorInvalidValue;
     }
 } // namespace mbavo

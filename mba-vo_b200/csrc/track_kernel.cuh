@@ -33,8 +33,6 @@
 
 #include <cuda_fp16.h>
 
-#include <type_traits>
-
 #ifndef MBAVO_MINB_H
 #define MBAVO_MINB_H 2
 #endif
@@ -119,30 +117,20 @@ namespace mbavo
                 return ps;
             ps.state |= 1;
             ps.X = X, ps.Y = Y;
-            ps.rx = (float)(((double)X - lv.cx) / lv.fx);
-            ps.ry = (float)(((double)Y - lv.cy) / lv.fy);
+            // (no discrete decision depends on these: reciprocal multiplies instead of fp64 divisions)
+            ps.rx = (float)(((double)X - lv.cx) * lv.inv_fx);
+            ps.ry = (float)(((double)Y - lv.cy) * lv.inv_fy);
             ps.D = (float)z;
-            ps.iD = (float)(1.0 / (z + 1e-8));
+            ps.iD = __frcp_rn((float)(z + 1e-8));
             ps.icur = u8_to_float(__ldg(lv.cur_I[f] + (size_t)Y * lv.W + X));
             return ps;
         }
 
-        // Where a sample record is read from: shared memory (any F*N, phase split allowed) or the launch-parameter table
-        // (constant bank, uniform index).  q(k) = k-th group of four floats of the record.
+        // A sample record in shared memory; q(k) = k-th group of four floats
         struct SmemRec
         {
             const float *p;
             __device__ __forceinline__ float4 q(int k) const { return *reinterpret_cast<const float4 *>(p + 4 * k); }
-        };
-        template <class Tab>
-        struct ConstRec
-        {
-            const Tab &t;
-            int base;
-            __device__ __forceinline__ float4 q(int k) const
-            {
-                return make_float4(t.rec[base + 4 * k], t.rec[base + 4 * k + 1], t.rec[base + 4 * k + 2], t.rec[base + 4 * k + 3]);
-            }
         };
 
         // What a lane keeps in registers while it walks the samples of its pixel
@@ -170,11 +158,11 @@ namespace mbavo
         __device__ __forceinline__ void sample_step(const Rec rec, const PixelRegs &ps, const LevelDev &lv,
                                                     float2 fxy, float &sumI, float2 (&J)[WITH_J ? NK : 1][3])
         {
-            const float4 g0 = rec.q(0); // (Rm00 Rm10) (Rm01 Rm11)      Rm = R - I
-            const float4 g1 = rec.q(1); // (Rm02 Rm12) (Rm20 Rm21)
+            const float4 g0 = rec.q(0); // (Rm00 Rm01) (Rm10 Rm11)      Rm = R - I
+            const float4 g1 = rec.q(1); // (Rm20 Rm21) Rm02 Rm12
             const float4 g2 = rec.q(2); // Rm22 tz (tx ty)
-            const float2 A01 = fma2(bc(ps.rxy.x), f2(g0.x, g0.y), fma2(bc(ps.rxy.y), f2(g0.z, g0.w), f2(g1.x, g1.y)));
-            const float A2 = fmaf(g1.z, ps.rxy.x, fmaf(g1.w, ps.rxy.y, g2.x));
+            const float2 A01 = f2(fmaf(g0.x, ps.rxy.x, fmaf(g0.y, ps.rxy.y, g1.z)), fmaf(g0.z, ps.rxy.x, fmaf(g0.w, ps.rxy.y, g1.w)));
+            const float A2 = fmaf(g1.x, ps.rxy.x, fmaf(g1.y, ps.rxy.y, g2.x));
             const float2 m01 = add2(ps.rxy, A01);
             const float m2 = 1.0f + A2;
             const float il = rcp_approx(m2);                    // 1 / lambda (1 ulp: the terms it scales are blur-sized)
@@ -229,16 +217,15 @@ namespace mbavo
 
             if constexpr (WITH_J)
             {
-                const float4 g3 = rec.q(3); // (Rm00 Rm01) (Rm10 Rm11)
                 const float s = (ps.D - g2.y) * il;                 // (D - t_z) / lambda       compute_pixel_intensity.h:128
                 // dI/dt = dI/dP (I - m e_z^T / lambda)                                   compute_pixel_intensity.h:196-202
                 const float2 gt = mul2(gxy, ps.fxyiD);
                 const float gtz = -(gt.x * m01.x + gt.y * m01.y) * il;
                 // dI/dtheta = s (r x R^T dI/dt): right perturbation R <- R Exp(theta) of the pose rotation; equals
                 // dI/dq (compute_pixel_intensity.h:179-206) contracted with dq/dtheta = L(q)[I/2;0].   b = s R^T dI/dt
-                const float2 b01 = mul2(bc(s), fma2(bc(gt.x), f2(g3.x, g3.y),
-                                                    fma2(bc(gt.y), f2(g3.z, g3.w), fma2(bc(gtz), f2(g1.z, g1.w), gt))));
-                const float b2 = s * fmaf(g1.x, gt.x, fmaf(g1.y, gt.y, fmaf(g2.x, gtz, gtz)));
+                const float2 b01 = mul2(bc(s), fma2(bc(gt.x), f2(g0.x, g0.y),
+                                                    fma2(bc(gt.y), f2(g0.z, g0.w), fma2(bc(gtz), f2(g1.x, g1.y), gt))));
+                const float b2 = s * fmaf(g1.z, gt.x, fmaf(g1.w, gt.y, fmaf(g2.x, gtz, gtz)));
                 const float v0 = fmaf(ps.rxy.y, b2, -b01.y);
                 const float v1 = fmaf(-ps.rxy.x, b2, b01.x);
                 const float v2 = fmaf(ps.rxy.x, b01.y, -ps.rxy.y * b01.x);
@@ -263,32 +250,21 @@ namespace mbavo
             }
         }
 
-        // Samples of the segments OFF, OFF + 1, ... in time order.  CREC: records from the launch-parameter table (index i
-        // uniform, step 1); else from shared memory with PH exposure phases (lane-dependent start, step PH).
-        template <int K, int NK, bool PACKED, bool CREC, int OFF, class Tab>
+        // Samples of the segments OFF, OFF + 1, ... in time order, PH exposure phases (lane-dependent start, step PH)
+        template <int K, int NK, bool PACKED, int OFF>
         struct SegmentLoop
         {
-            __device__ __forceinline__ static void run(const Tab &tab, int tab_base, const float *__restrict__ samples_s,
-                                                       const int *__restrict__ seg_end_s, int &i, int PH, const PixelRegs &ps,
-                                                       const LevelDev &lv, float2 fxy, float &sumI, float2 (&J)[NK][3])
+            __device__ __forceinline__ static void run(const float *__restrict__ samples_s, const int *__restrict__ seg_end_s,
+                                                       int &i, int PH, const PixelRegs &ps, const LevelDev &lv, float2 fxy,
+                                                       float &sumI, float2 (&J)[NK][3])
             {
                 constexpr int REC = sample_rec_floats(K);
-                if constexpr (CREC)
-                {
-                    const int end = tab.seg_end[tab_base + OFF];
-                    for (; i < end; ++i)
-                        sample_step<K, NK, true, PACKED, OFF>(ConstRec<Tab>{tab, (tab_base / kMaxSegments * lv.N + i) * REC}, ps, lv, fxy,
-                                                              sumI, J);
-                }
-                else
-                {
-                    const int end = seg_end_s[OFF];
-                    for (; i < end; i += PH)
-                        sample_step<K, NK, true, PACKED, OFF>(SmemRec{samples_s + i * REC}, ps, lv, fxy, sumI, J);
-                }
+                const int end = seg_end_s[OFF];
+                for (; i < end; i += PH)
+                    sample_step<K, NK, true, PACKED, OFF>(SmemRec{samples_s + i * REC}, ps, lv, fxy, sumI, J);
                 if constexpr (OFF + 1 <= NK - K)
-                    SegmentLoop<K, NK, PACKED, CREC, (OFF + 1 <= NK - K ? OFF + 1 : OFF), Tab>::run(tab, tab_base, samples_s, seg_end_s, i, PH,
-                                                                                            ps, lv, fxy, sumI, J);
+                    SegmentLoop<K, NK, PACKED, (OFF + 1 <= NK - K ? OFF + 1 : OFF)>::run(samples_s, seg_end_s, i, PH, ps, lv, fxy,
+                                                                                      sumI, J);
             }
         };
 
@@ -306,8 +282,17 @@ namespace mbavo
             return x;
         }
 
-        template <int K, bool CREC>
-        using TableOf = typename std::conditional<CREC, SampleTable<K>, NoTable>::type;
+        // tile id -> (ta << 8) | tb, row-major upper triangle of the T x T tile grid
+        __device__ __forceinline__ unsigned int tile_s_copy(int id, int T)
+        {
+            int a = 0, rem = id;
+            while (rem >= T - a)
+            {
+                rem -= T - a;
+                ++a;
+            }
+            return (unsigned int)((a << 8) | (a + rem));
+        }
 
         // Geometry of the staged rows and of the 2x2 tiling of rows^T rows
         template <int NK, bool WITH_J>
@@ -323,12 +308,11 @@ namespace mbavo
         };
 
         // K: knots per segment, NK: knots in the window (NK - K + 1 segments touched), WITH_J: Hessian pass or cost only,
-        // PACKED: keyframe texels available, CREC: sample records in the launch-parameter table `tab` (else in prm.samples).
-        template <int K, int NK, bool WITH_J, bool PACKED, bool CREC>
+        // PACKED: keyframe texels available.
+        template <int K, int NK, bool WITH_J, bool PACKED>
         __global__ void __launch_bounds__(kThreads, WITH_J ? (NK <= 3 ? MBAVO_MINB_H : 1) : 4)
-            track_kernel(const __grid_constant__ TrackParams prm, const __grid_constant__ TableOf<K, CREC> tab)
+            track_kernel(const __grid_constant__ TrackParams prm)
         {
-            using Tab = TableOf<K, CREC>;
             using G = RowGeom<NK, WITH_J>;
             constexpr int REC = sample_rec_floats(K);
             constexpr int NJ = WITH_J ? NK : 1;
@@ -346,8 +330,8 @@ namespace mbavo
             const int bfly_lo = pf ? 1 : Q, bfly_hi = pf ? PH : 32;
 
             extern __shared__ __align__(16) unsigned char smem_raw[];
-            float *samples_s = reinterpret_cast<float *>(smem_raw);                  // N * REC (nothing if CREC)
-            int *seg_end_s = reinterpret_cast<int *>(samples_s + (CREC ? 0 : N * REC)); // kMaxSegments (+1 pad)
+            float *samples_s = reinterpret_cast<float *>(smem_raw);                  // N * REC
+            int *seg_end_s = reinterpret_cast<int *>(samples_s + N * REC);          // kMaxSegments (+1 pad)
             double *mid_s = reinterpret_cast<double *>(seg_end_s + 8);              // kMidDoubles
             PixelRec *pix_s = reinterpret_cast<PixelRec *>(mid_s + kMidDoubles);    // warps * 32
             int2 *pattern_s = reinterpret_cast<int2 *>(pix_s + kWarpsPerBlock * 32); // S
@@ -355,42 +339,28 @@ namespace mbavo
             const int rho_per_warp = max(32, TP * S);
             unsigned short *tile_s = reinterpret_cast<unsigned short *>(rho_s + kWarpsPerBlock * rho_per_warp); // NT (padded)
             float *rows_s = reinterpret_cast<float *>(tile_s + ((NT + 7) & ~7));   // warps * 32 * PITCH
+            // fp64 tile accumulators of every warp, [warp][m][ij][lane]: kept out of the register file (they are touched
+            // once per 32-pixel chunk) so that the sample loop has the registers
+            double *acc_s = reinterpret_cast<double *>(rows_s + kWarpsPerBlock * 32 * PITCH + ((kWarpsPerBlock * 32 * PITCH) & 1));
             double *red_s = reinterpret_cast<double *>(smem_raw);                   // epilogue: warps * E doubles (aliases all)
 
-            if constexpr (CREC)
-            {
-                if (threadIdx.x == 0)
-                {
-#pragma unroll
-                    for (int e = 0; e < kMidDoubles; ++e)
-                        mid_s[e] = tab.mid[f * kMidDoubles + e];
-                }
-            }
-            else
-            {
-                for (int e = threadIdx.x; e < N * REC; e += blockDim.x)
-                    samples_s[e] = prm.samples[(size_t)f * N * REC + e];
-                if (threadIdx.x < kMaxSegments)
-                    seg_end_s[threadIdx.x] = prm.seg_end[f * kMaxSegments + threadIdx.x];
-                if (threadIdx.x < kMidDoubles)
-                    mid_s[threadIdx.x] = prm.mid[f * kMidDoubles + threadIdx.x];
-            }
             for (int e = threadIdx.x; e < S; e += blockDim.x)
                 pattern_s[e] = lv.pattern[e];
             if (WITH_J)
             {
                 // tile table: tile id -> (ta, tb), ta <= tb, row-major upper triangle of the T x T tile grid
                 for (int e = threadIdx.x; e < NT; e += blockDim.x)
-                {
-                    int a = 0, rem = e;
-                    while (rem >= G::T - a)
-                    {
-                        rem -= G::T - a;
-                        ++a;
-                    }
-                    tile_s[e] = (unsigned short)((a << 8) | (a + rem));
-                }
+                    tile_s[e] = (unsigned short)tile_s_copy(e, G::T);
             }
+            // everything above is independent of the pose kernel; what follows reads its output (programmatic dependent
+            // launch: this grid may have started before the pose kernel finished)
+            cudaGridDependencySynchronize();
+            for (int e = threadIdx.x; e < N * REC; e += blockDim.x)
+                samples_s[e] = prm.samples[(size_t)f * N * REC + e];
+            if (threadIdx.x < kMaxSegments)
+                seg_end_s[threadIdx.x] = prm.seg_end[f * kMaxSegments + threadIdx.x];
+            if (threadIdx.x < kMidDoubles)
+                mid_s[threadIdx.x] = prm.mid[f * kMidDoubles + threadIdx.x];
             __syncthreads();
 
             const double *mid = mid_s;
@@ -402,26 +372,19 @@ namespace mbavo
             float *my_rho = rho_s + warp * rho_per_warp;
             PixelRec *my_pix = pix_s + warp * 32;
 
-            // this lane's tiles (offsets of the two operand pairs inside a row) and their fp64 accumulators
-            int tile_a[MT], tile_b[MT];
-            double acc[MT][4];
-#pragma unroll
-            for (int m = 0; m < MT; ++m)
+            double *my_acc = acc_s + warp * (MT * 4 * 32) + lane;
+            if constexpr (WITH_J)
             {
-                const int id = lane + 32 * m;
-                const unsigned int t = (WITH_J && id < NT) ? tile_s[id] : 0u;
-                tile_a[m] = 2 * (int)(t >> 8), tile_b[m] = 2 * (int)(t & 0xff);
-                acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.0;
+#pragma unroll
+                for (int e = 0; e < MT * 4; ++e)
+                    my_acc[e * 32] = 0.0;
             }
             double cost_acc = 0.0;
 
             const int items = TP * S;
-            // Block-uniform trip count (a warp past the last batch walks an all-invalid batch): loops whose bounds depend on
-            // threadIdx keep the compiler from using the uniform datapath for the sample index and the record loads.
-            for (int wb0 = blockIdx.x * kWarpsPerBlock; wb0 < prm.batches_per_frame; wb0 += gridDim.x * kWarpsPerBlock)
+            for (int wb = blockIdx.x * kWarpsPerBlock + warp; wb < prm.batches_per_frame; wb += gridDim.x * kWarpsPerBlock)
             {
-                const int wb = wb0 + warp;
-                const int p0 = wb < prm.batches_per_frame ? wb * TP : lv.P;
+                const int p0 = wb * TP;
                 for (int base = 0; base < items; base += 32)
                 {
                     // ---- A: pixel records -----------------------------------------------------------------------------
@@ -452,26 +415,18 @@ namespace mbavo
                         for (int a = 0; a < NJ; ++a)
                             J[a][0] = J[a][1] = J[a][2] = f2(0.f, 0.f);
 
-                        // An invalid pixel walks the samples too, with an empty validity window: the sample loops stay
-                        // free of thread-dependent control flow around them, which lets the compiler keep the sample index
-                        // and the record loads on the uniform datapath.
-                        if (!valid)
-                            ps.lox = ps.loy = __int_as_float(0x7f800000), ps.hix = ps.hiy = __int_as_float(0xff800000);
-                        if constexpr (WITH_J)
+                        if (valid)
                         {
-                            int i = CREC ? 0 : phase;
-                            SegmentLoop<K, NK, PACKED, CREC, 0, Tab>::run(tab, f * kMaxSegments, samples_s, seg_end_s, i, PH, ps, lv, fxy,
-                                                                          sumI, J);
-                        }
-                        else if constexpr (CREC)
-                        {
-                            for (int i = 0; i < N; ++i) // cost only: the segment of a sample is irrelevant
-                                sample_step<K, NK, false, PACKED, 0>(ConstRec<Tab>{tab, (f * N + i) * REC}, ps, lv, fxy, sumI, J);
-                        }
-                        else
-                        {
-                            for (int i = phase; i < N; i += PH)
-                                sample_step<K, NK, false, PACKED, 0>(SmemRec{samples_s + i * REC}, ps, lv, fxy, sumI, J);
+                            if constexpr (WITH_J)
+                            {
+                                int i = phase;
+                                SegmentLoop<K, NK, PACKED, 0>::run(samples_s, seg_end_s, i, PH, ps, lv, fxy, sumI, J);
+                            }
+                            else
+                            {
+                                for (int i = phase; i < N; i += PH) // cost only: the segment of a sample is irrelevant
+                                    sample_step<K, NK, false, PACKED, 0>(SmemRec{samples_s + i * REC}, ps, lv, fxy, sumI, J);
+                            }
                         }
                         // combine the PH phases of every pixel (fixed butterfly order: deterministic)
                         for (int o = bfly_lo; o < bfly_hi; o <<= 1)
@@ -535,9 +490,11 @@ namespace mbavo
 #pragma unroll
                         for (int m = 0; m < MT; ++m)
                         {
-                            if (lane + 32 * m < NT)
+                            const int id = lane + 32 * m;
+                            if (id < NT)
                             {
-                                const float *pa = my_rows + tile_a[m], *pb = my_rows + tile_b[m];
+                                const unsigned int t = tile_s[id];
+                                const float *pa = my_rows + 2 * (t >> 8), *pb = my_rows + 2 * (t & 0xff);
                                 float2 s0 = f2(0.f, 0.f), s1 = f2(0.f, 0.f);
 #pragma unroll 8
                                 for (int qq = 0; qq < 32; ++qq)
@@ -547,8 +504,8 @@ namespace mbavo
                                     s0 = fma2(bc(va.x), vb, s0);
                                     s1 = fma2(bc(va.y), vb, s1);
                                 }
-                                acc[m][0] += (double)s0.x, acc[m][1] += (double)s0.y;
-                                acc[m][2] += (double)s1.x, acc[m][3] += (double)s1.y;
+                                double *a = my_acc + m * 4 * 32;
+                                a[0] += (double)s0.x, a[32] += (double)s0.y, a[64] += (double)s1.x, a[96] += (double)s1.y;
                             }
                         }
                     }
@@ -572,19 +529,31 @@ namespace mbavo
             for (int o = 16; o > 0; o >>= 1)
                 cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, o);
 
-            __syncthreads(); // every warp is done with samples_s / rows_s before red_s (aliasing them) is written
+            // the accumulators leave shared memory before red_s (which aliases everything) is written
+            double acc[MT][4];
             if constexpr (WITH_J)
             {
-                // tile element (i, j) is matrix element (r, c) = (tile_a + i, tile_b + j); packed index of the upper triangle
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+#pragma unroll
+                    for (int ij = 0; ij < 4; ++ij)
+                        acc[m][ij] = my_acc[(m * 4 + ij) * 32];
+            }
+            __syncthreads();
+            if constexpr (WITH_J)
+            {
+                // tile element (i, j) is matrix element (r, c) = (2 ta + i, 2 tb + j); packed index of the upper triangle
 #pragma unroll
                 for (int m = 0; m < MT; ++m)
                 {
-                    if (lane + 32 * m < NT)
+                    const int id = lane + 32 * m;
+                    if (id < NT)
                     {
+                        const unsigned int t = tile_s_copy(id, G::T);
 #pragma unroll
                         for (int ij = 0; ij < 4; ++ij)
                         {
-                            const int r = tile_a[m] + (ij >> 1), c = tile_b[m] + (ij & 1);
+                            const int r = 2 * (int)(t >> 8) + (ij >> 1), c = 2 * (int)(t & 0xff) + (ij & 1);
                             if (r <= c && c < D1)
                                 red_s[warp * E + r * D1 - r * (r - 1) / 2 + (c - r)] = acc[m][ij];
                         }
@@ -613,13 +582,38 @@ namespace mbavo
             __syncthreads();
             if (ticket_s != (unsigned int)(num_blocks - 1))
                 return;
-            // last block: sum the partials of all blocks in block order
+            // last block: sum the partials of all blocks in a fixed order — PARTS contiguous block ranges per element summed
+            // by different threads (8 loads in flight each), then combined in range order
             __threadfence();
+            constexpr int PARTS = E >= kThreads ? 1 : kThreads / E;
+            for (int idx = threadIdx.x; idx < E * PARTS; idx += blockDim.x)
+            {
+                const int e = idx % E, part = idx / E;
+                const int b0 = (int)((long long)num_blocks * part / PARTS), b1 = (int)((long long)num_blocks * (part + 1) / PARTS);
+                const double *src = prm.block_partials + e;
+                double s = 0.0;
+                int b = b0;
+                for (; b + 8 <= b1; b += 8)
+                {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        v[u] = __ldcg(src + (size_t)(b + u) * E);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        s += v[u];
+                }
+                for (; b < b1; ++b)
+                    s += __ldcg(src + (size_t)b * E);
+                red_s[idx] = s;
+            }
+            __syncthreads();
             for (int e = threadIdx.x; e < E; e += blockDim.x)
             {
                 double s = 0.0;
-                for (int b = 0; b < num_blocks; ++b)
-                    s += __ldcg(prm.block_partials + (size_t)b * E + e);
+#pragma unroll
+                for (int part = 0; part < PARTS; ++part)
+                    s += red_s[part * E + e];
                 s *= inv_num_residuals;
                 prm.packed_out[e] = s;
                 if (prm.host_out)
@@ -638,57 +632,53 @@ namespace mbavo
             }
         }
 
-        template <int K, int NK, bool WITH_J, bool PACKED, bool CREC>
-        cudaError_t launch_one(const TrackParams &prm, const void *table, dim3 grid, size_t smem, cudaStream_t stream)
+        template <int K, int NK, bool WITH_J, bool PACKED>
+        cudaError_t launch_one(const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream, bool dependent)
         {
             static unsigned long long configured = 0; // per instantiation and per device (attribute of the device function)
             int dev = 0;
             cudaGetDevice(&dev);
             if (!(configured >> dev & 1ull))
             {
-                cudaError_t e = cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED, CREC>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                cudaError_t e = cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     200 * 1024);
                 if (e != cudaSuccess)
                     return e;
                 configured |= 1ull << dev;
             }
-            static const NoTable none{};
-            const auto *tab = reinterpret_cast<const TableOf<K, CREC> *>(CREC ? table : static_cast<const void *>(&none));
-            track_kernel<K, NK, WITH_J, PACKED, CREC><<<grid, kThreads, smem, stream>>>(prm, *tab);
-            return cudaGetLastError();
+            // Programmatic dependent launch: the kernel may start while the pose kernel before it in the stream is still
+            // running; it waits (griddepcontrol.wait) right before it reads what the pose kernel wrote.
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = grid, cfg.blockDim = dim3(kThreads, 1, 1), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr, cfg.numAttrs = dependent ? 1 : 0;
+            return cudaLaunchKernelEx(&cfg, track_kernel<K, NK, WITH_J, PACKED>, prm);
         }
 
         // Occupancy-derived grid width for one instantiation
-        template <int K, int NK, bool WITH_J, bool PACKED, bool CREC>
+        template <int K, int NK, bool WITH_J, bool PACKED>
         int blocks_per_sm(size_t smem)
         {
             int n = 0;
-            cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED, CREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, track_kernel<K, NK, WITH_J, PACKED, CREC>, kThreads, smem);
+            cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, track_kernel<K, NK, WITH_J, PACKED>, kThreads, smem);
             return n > 0 ? n : 1;
         }
 
-        // One (K, NK, WITH_J): the four (texels, record source) variants
+        // One (K, NK, WITH_J): texel / direct-gather variant
         template <int K, int NK, bool WITH_J>
-        cudaError_t dispatch_variant(bool packed, bool crec, const TrackParams &prm, const void *table, dim3 grid, size_t smem,
-                                     cudaStream_t stream, int *query_occupancy)
+        cudaError_t dispatch_variant(bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
+                                     int *query_occupancy, bool dependent)
         {
-#define MBAVO_VARIANT(P_, C_)                                                             \
-    if (packed == P_ && crec == C_)                                                       \
-    {                                                                                     \
-        if (query_occupancy)                                                              \
-        {                                                                                 \
-            *query_occupancy = blocks_per_sm<K, NK, WITH_J, P_, C_>(smem);                \
-            return cudaSuccess;                                                           \
-        }                                                                                 \
-        return launch_one<K, NK, WITH_J, P_, C_>(prm, table, grid, smem, stream);         \
-    }
-            MBAVO_VARIANT(true, true)
-            MBAVO_VARIANT(true, false)
-            MBAVO_VARIANT(false, true)
-            MBAVO_VARIANT(false, false)
-#undef MBAVO_VARIANT
-            return cudaErrorInvalidValue;
+            if (query_occupancy)
+            {
+                *query_occupancy = packed ? blocks_per_sm<K, NK, WITH_J, true>(smem) : blocks_per_sm<K, NK, WITH_J, false>(smem);
+                return cudaSuccess;
+            }
+            return packed ? launch_one<K, NK, WITH_J, true>(prm, grid, smem, stream, dependent)
+                          : launch_one<K, NK, WITH_J, false>(prm, grid, smem, stream, dependent);
         }
     } // namespace
 } // namespace mbavo
