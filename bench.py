@@ -17,7 +17,9 @@ Legs (own arm):
 
 `--impl reference` times that CPU implementation alone (rank 0 only).
 For N > 1 (torchrun, one rank per GPU): every rank holds its own 20k-point shard of an N-times larger point set
-(weak scaling), the packed [cost, g, H] vector is all-reduced over NCCL once per evaluation.
+(weak scaling).  The packed [cost, g, H] vector of every evaluation is all-reduced INSIDE the tracking kernel through
+peer-mapped mailboxes over NVLink (mbavo_shard_*; `--collective fused`, default), or by NCCL after the kernel
+(`--collective nccl`, the baseline form).  torch.distributed carries the IPC handles, the barriers and the max-over-ranks.
 """
 import argparse
 import json
@@ -219,8 +221,24 @@ def run_own(args, pkg):
             ctx.set_level(l, lv)
 
     upload_all()
-    if world > 1:
-        # same dataflow as mbavo_b200.parallel.ShardedEvaluator: the fused kernel leaves this rank's packed vector in
+    fused = world > 1 and args.collective == "fused"
+    if fused:
+        # one-shot all-reduce inside the kernel: exchange the mailbox IPC handles once, then every C-ABI call is collective
+        handle, _ = ctx.shard_export()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handle)
+        ctx.shard_connect(world, rank, handles=gathered)
+        for l, lv in enumerate(prob.levels):
+            ctx.shard_set_global_points(l, lv.P * world)
+
+        def upload_all():  # noqa: F811  (set_level keeps the connection; the global point counts stay valid)
+            for l, lv in enumerate(pinned):
+                ctx.set_level(l, lv)
+
+        def evaluate(level, kt, kR, with_h):
+            return ctx.evaluate(level, prob.k, prob.t0, prob.dt, kt, kR, prob.huber_a, with_h)
+    elif world > 1:
+        # NCCL form, same dataflow as mbavo_b200.parallel.ShardedEvaluator: the fused kernel leaves this rank's packed vector in
         # `packed`, NCCL sums it in place on the same stream, one D2H brings the global result back
         packed = torch.zeros(ctx.packed_len(8), dtype=torch.float64, device=dev)
         prob_global_P = [lv.P * world for lv in prob.levels]  # global normaliser: world * P points per level
@@ -259,7 +277,7 @@ def run_own(args, pkg):
             e0.record(stream)
             if with_upload:
                 upload_all()
-            gpu_step(ctx, prob, evaluate if world > 1 else None, solve, plus)
+            gpu_step(ctx, prob, evaluate if (world > 1 and not fused) else None, solve, plus)
             e1.record(stream)
             torch.cuda.synchronize(dev)
             total += e0.elapsed_time(e1)
@@ -317,7 +335,9 @@ def run_own(args, pkg):
             "config": {"workload": WORKLOAD, "step": "1 GN iteration per pyramid level (H pass + solve + cost pass)",
                        "point_samples_per_step": ps_step, "points_per_gpu_level0": prob.levels[0].P,
                        "l2": "flushed between steps with a 256 MiB memset (not timed); working set (4 MB) is L2-resident within a step",
-                       "parallelism": f"point-sharded x{world}, 1 NCCL all-reduce of the packed H/g/cost per evaluation" if world > 1 else "single GPU",
+                       "parallelism": (f"point-sharded x{world}, packed H/g/cost all-reduced " +
+                                       ("inside the tracking kernel through peer-mapped mailboxes over NVLink" if fused else
+                                        "by NCCL after the kernel")) if world > 1 else "single GPU",
                        "accumulation": "fp32 per sample, fp64 across pixels"},
             "gn_iters_per_s": len(prob.levels) * args.steps / (ms_value * 1e-3),
             "e2e": {"value": e2e_value, "unit": "point-samples/s", "h2d_bytes_per_step": int(h2d_step),
@@ -360,6 +380,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"])
     args = ap.parse_args()
     import __graft_entry__ as ge
 

@@ -31,7 +31,7 @@ extern "C" {
 #define MBAVO_ERANGE (-3)      /* an exposure sample needs a control knot outside [0, n_knots) */
 #define MBAVO_ECAPACITY (-4)   /* exceeds the limits the context was created with */
 #define MBAVO_ENOTREADY (-5)   /* level / frame times not set */
-#define MBAVO_ENCCL (-6)       /* NCCL unavailable or failed */
+#define MBAVO_ENCCL (-6)       /* sharded call: a peer rank did not arrive (collective failed) */
 
 #define MBAVO_MAX_LEVELS 8     /* BlurAwareDirectTrackerOptions per-level arrays, blur_aware_direct_tracker.h:17-31 */
 #define MBAVO_MAX_FRAMES 16
@@ -155,6 +155,32 @@ int mbavo_evaluate_async(mbavo_ctx *ctx, int level, const mbavo_spline *spline, 
  * into the dense H (6n x 6n), g (6n) and cost.  hessian/gradient NULL => cost only. */
 int mbavo_unpack(const double *packed_host, int kmin, int knot_window, int num_ctrl_knots, double *total_cost,
                  double *hessian, double *gradient);
+
+/* ---- point sharding over the GPUs of one node ------------------------------------------------------
+ * One process (or thread) and one context per GPU, each holding a contiguous block of the host-map points of every
+ * level; images, spline and pattern are replicated.  After mbavo_shard_connect, mbavo_evaluate / mbavo_detect_outliers
+ * (and everything built on them: mbavo_gn_iteration, mbavo_optimize_level) are COLLECTIVE calls that every rank makes
+ * with the same arguments and that return the same global result on every rank: the last block of the tracking kernel
+ * writes this rank's packed [cost, g, triu(H)] into every rank's mailbox over NVLink (peer-mapped memory), publishes a
+ * sequence number, waits for the other ranks' vectors in its own mailbox and sums them in rank order — a one-shot
+ * all-reduce fused into the kernel, no NCCL call, no extra launch.  The reference has no multi-GPU path; this replaces
+ * what a ported version would do with ncclAllReduce after kernel_compute_frame_cost_gradient_hessian.
+ *
+ *   mbavo_shard_export   creates this context's mailbox; handle_out (MBAVO_IPC_HANDLE_BYTES, may be NULL) receives its CUDA
+ *                        IPC handle for ranks in OTHER processes, mailbox_ptr_out (may be NULL) its device pointer for
+ *                        ranks in the SAME process.
+ *   mbavo_shard_connect  handles: world x MBAVO_IPC_HANDLE_BYTES in rank order (other processes), or mailbox_ptrs: world
+ *                        device pointers in rank order (same process); the entry of `rank` itself is ignored.
+ *   mbavo_shard_set_global_points   total number of host-map points of `level` over all ranks (the normaliser
+ *                        1 / ((P - num_bad) F S) of spline_update_step.cpp:116-117 is global; num_bad_keypoints given to
+ *                        mbavo_set_outliers / mbavo_set_num_bad is the global count too).
+ * A rank that waits more than 4 s for a peer gives up: the call returns MBAVO_ENCCL. */
+#define MBAVO_IPC_HANDLE_BYTES 64
+#define MBAVO_MAX_SHARDS 8
+int mbavo_shard_export(mbavo_ctx *ctx, void *handle_out, void **mailbox_ptr_out);
+int mbavo_shard_connect(mbavo_ctx *ctx, int world, int rank, const void *handles, void *const *mailbox_ptrs);
+int mbavo_shard_disconnect(mbavo_ctx *ctx);
+int mbavo_shard_set_global_points(mbavo_ctx *ctx, int level, int num_keypoints_global);
 
 /* ---- host-side solver, mirrors of the tracker's LM loop ------------------ */
 

@@ -21,8 +21,10 @@ EXPORTED_SYMBOLS = [
     "mbavo_set_level", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
-    "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels",
+    "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
+    "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points",
 ]
+IPC_HANDLE_BYTES = 64
 
 
 class MbavoError(RuntimeError):
@@ -279,6 +281,29 @@ class Context:
         s["first_step"] = np.array(summ.first_step[: 6 * n])
         s["decisions"] = summ.decisions.decode()
         return kt, kR, s
+
+    # -- point sharding ----------------------------------------------------------------------------------------
+    def shard_export(self):
+        """mbavo_shard_export -> (ipc_handle bytes, mailbox device pointer)."""
+        h = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        ptr = C.c_void_p()
+        self._check(self.lib.mbavo_shard_export(self._h, h, C.byref(ptr)))
+        return bytes(h), int(ptr.value)
+
+    def shard_connect(self, world: int, rank: int, handles: Optional[Sequence[bytes]] = None,
+                      mailbox_ptrs: Optional[Sequence[int]] = None):
+        """mbavo_shard_connect: `handles` (other processes) or `mailbox_ptrs` (same process), both in rank order."""
+        hb = None
+        if handles is not None:
+            hb = (C.c_ubyte * (IPC_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
+        pp = (C.c_void_p * world)(*mailbox_ptrs) if mailbox_ptrs is not None else None
+        self._check(self.lib.mbavo_shard_connect(self._h, C.c_int(world), C.c_int(rank), hb, pp))
+
+    def shard_disconnect(self):
+        self._check(self.lib.mbavo_shard_disconnect(self._h))
+
+    def shard_set_global_points(self, level: int, num_keypoints_global: int):
+        self._check(self.lib.mbavo_shard_set_global_points(self._h, C.c_int(level), C.c_int(num_keypoints_global)))
 
     # -- introspection ----------------------------------------------------------------------------------------
     def kernel_launches(self) -> int:

@@ -89,6 +89,13 @@ struct mbavo_ctx
 
     EvalStage stage{};       // spline state of the evaluation being issued (launch parameter of the pose kernel)
     bool use_pdl = true;     // MBAVO_NO_PDL=1: tracking kernel fully serialised behind the pose kernel
+
+    // point sharding (mbavo_shard_*): this rank's mailbox, the mapped mailboxes of all ranks, exchange counters
+    Mailbox *mailbox = nullptr;
+    ShardParams shard{};                    // world <= 1: not sharded
+    bool peer_is_ipc[kMaxShards] = {};      // opened with cudaIpcOpenMemHandle (to be closed)
+    unsigned long long shard_seq = 0, aux_seq = 0;
+    int points_global[MBAVO_MAX_LEVELS] = {};
     float *samples = nullptr;
     double *mid = nullptr;
     int *seg_end = nullptr;
@@ -159,13 +166,16 @@ namespace
     }
 
     // detectOutliersAndUploadToGpu (blur_aware_direct_tracker.cpp:650-698) on the device: one block, fixed-order tree sums.
-    // result[0] = number flagged by this call.
+    // result[0] = number flagged by this call (over all ranks when sharded), result[1] = 1 if a peer timed out.
+    // Sharded: mean, variance and the flag count are all-reduced through the mailboxes (3 small exchanges, seq0 + 0..2).
     __global__ void outlier_kernel(const double *__restrict__ cost, int P, int stride, double k_sigma,
-                                   unsigned char *__restrict__ flags, int *__restrict__ result)
+                                   unsigned char *__restrict__ flags, int *__restrict__ result, const ShardParams sh)
     {
         __shared__ double s_a[1024];
         __shared__ double s_b[1024];
+        __shared__ double s_x[8];
         const int tid = threadIdx.x;
+        bool ok = true;
         double sum = 0, cnt = 0;
         for (int i = tid; i < P; i += blockDim.x)
         {
@@ -181,7 +191,12 @@ namespace
                 s_a[tid] += s_a[tid + o], s_b[tid] += s_b[tid + o];
             __syncthreads();
         }
-        const double n = s_b[0], mu = s_a[0] / n;
+        if (tid == 0)
+            s_x[0] = s_a[0], s_x[1] = s_b[0];
+        __syncthreads();
+        if (sh.world > 1)
+            ok = shard_allreduce_small(sh, sh.seq, s_x, 2) && ok;
+        const double n = s_x[1], mu = s_x[0] / n;
         __syncthreads();
         double var = 0;
         for (int i = tid; i < P; i += blockDim.x)
@@ -198,7 +213,12 @@ namespace
                 s_a[tid] += s_a[tid + o];
             __syncthreads();
         }
-        const double thr = k_sigma * (double)sqrtf((float)(s_a[0] / n)); // `max_chi_square_error * sqrtf(var)`, :687
+        if (tid == 0)
+            s_x[0] = s_a[0];
+        __syncthreads();
+        if (sh.world > 1)
+            ok = shard_allreduce_small(sh, sh.seq + 1, s_x, 1) && ok;
+        const double thr = k_sigma * (double)sqrtf((float)(s_x[0] / n)); // `max_chi_square_error * sqrtf(var)`, :687
         __syncthreads();
         double bad = 0;
         for (int i = tid; i < P; i += blockDim.x)
@@ -219,7 +239,15 @@ namespace
             __syncthreads();
         }
         if (tid == 0)
-            result[0] = (int)s_a[0];
+            s_x[0] = s_a[0];
+        __syncthreads();
+        if (sh.world > 1)
+            ok = shard_allreduce_small(sh, sh.seq + 2, s_x, 1) && ok;
+        if (tid == 0)
+        {
+            result[0] = (int)s_x[0];
+            result[1] = ok ? 0 : 1;
+        }
     }
 
     // Sample time and segment of (frame, sample): compute_virtual_camera_poses.cu:33 + SplineFunctor.h:13-19.  The device
@@ -362,6 +390,11 @@ namespace
         prm.block_partials = ctx->block_partials;
         prm.counter = ctx->counter;
         prm.packed_out = packed_dev_out;
+        if (ctx->shard.world > 1)
+        {
+            prm.shard = ctx->shard;
+            prm.shard.seq = ++ctx->shard_seq;
+        }
         if (blocking)
         {
             prm.host_out = ctx->result_map;
@@ -491,6 +524,8 @@ extern "C"
         }
         cudaFree(ctx->inexact_dev);
         cudaFreeHost(ctx->inexact_host);
+        mbavo_shard_disconnect(ctx);
+        cudaFree(ctx->mailbox);
         cudaFree(ctx->samples);
         cudaFree(ctx->mid);
         cudaFree(ctx->seg_end);
@@ -658,8 +693,9 @@ extern "C"
             return fail(MBAVO_ENOTREADY, "level not set");
         DeviceGuard guard(ctx->device);
         LevelStore &L = ctx->levels[level];
-        if (num_bad < 0 || num_bad >= L.dev.P)
-            return fail(MBAVO_EINVAL, "num_bad_keypoints %d outside [0, %d)", num_bad, L.dev.P);
+        const int pts_all = ctx->shard.world > 1 && ctx->points_global[level] > 0 ? ctx->points_global[level] : L.dev.P;
+        if (num_bad < 0 || num_bad >= pts_all)
+            return fail(MBAVO_EINVAL, "num_bad_keypoints %d outside [0, %d)", num_bad, pts_all);
         unsigned char *dst = const_cast<unsigned char *>(L.dev.flags);
         if (flags)
             CUDA_TRY(cudaMemcpyAsync(dst, flags, L.dev.P, cudaMemcpyHostToDevice, ctx->stream));
@@ -674,8 +710,9 @@ extern "C"
     {
         if (!ctx || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
             return fail(MBAVO_ENOTREADY, "level not set");
-        if (num_bad < 0 || num_bad >= ctx->levels[level].dev.P)
-            return fail(MBAVO_EINVAL, "num_bad_keypoints %d outside [0, %d)", num_bad, ctx->levels[level].dev.P);
+        const int pts_all2 = ctx->shard.world > 1 && ctx->points_global[level] > 0 ? ctx->points_global[level] : ctx->levels[level].dev.P;
+        if (num_bad < 0 || num_bad >= pts_all2)
+            return fail(MBAVO_EINVAL, "num_bad_keypoints %d outside [0, %d)", num_bad, pts_all2);
         ctx->levels[level].num_bad = num_bad;
         return MBAVO_OK;
     }
@@ -724,13 +761,19 @@ extern "C"
         if (rc != MBAVO_OK)
             return rc;
         LevelStore &L = ctx->levels[level];
-        const long long nres = (long long)(pl.P - L.num_bad) * pl.F * pl.S; // spline_update_step.cpp:116
+        // spline_update_step.cpp:116; sharded: the point count and the outlier count are the global ones
+        const long long pts = ctx->shard.world > 1 ? ctx->points_global[level] : pl.P;
+        if (ctx->shard.world > 1 && pts < pl.P)
+            return fail(MBAVO_ENOTREADY, "mbavo_shard_set_global_points has not been called for level %d", level);
+        const long long nres = (pts - L.num_bad) * pl.F * pl.S;
         rc = run_evaluation(ctx, level, pl, ctx->packed_dev, true, 1.0 / (double)nres, huber_a);
         if (rc != MBAVO_OK)
             return rc;
         rc = wait_result(ctx);
         if (rc != MBAVO_OK)
             return rc;
+        if (ctx->shard.world > 1 && ctx->result_host[0] != ctx->result_host[0])
+            return fail(MBAVO_ENCCL, "sharded evaluation: a peer rank did not arrive within 4 s");
         if (ctx->timing)
         {
             CUDA_TRY(cudaEventSynchronize(ctx->ev1));
@@ -755,7 +798,12 @@ extern "C"
             *kmin = pl.kmin;
         if (knot_window)
             *knot_window = pl.NK;
-        return run_evaluation(ctx, level, pl, packed_dev, false, 1.0 / (double)nres, huber_a);
+        // the caller reduces the vectors itself (e.g. ncclAllReduce): no mailbox exchange for this launch
+        const ShardParams keep = ctx->shard;
+        ctx->shard.world = 0;
+        rc = run_evaluation(ctx, level, pl, packed_dev, false, 1.0 / (double)nres, huber_a);
+        ctx->shard = keep;
+        return rc;
     }
 
     int mbavo_patch_costs(mbavo_ctx *ctx, int level, double *out)
@@ -781,14 +829,125 @@ extern "C"
         if (L.last_eval_frames == 0)
             return fail(MBAVO_ENOTREADY, "no evaluation has run on level %d", level);
         // "only works for tracking one frame" (blur_aware_direct_tracker.cpp:641): statistics over frame 0's patches
+        ShardParams sh = ctx->shard;
+        if (sh.world > 1)
+        {
+            sh.seq = ctx->aux_seq + 1;
+            ctx->aux_seq += 3;
+        }
         outlier_kernel<<<1, 1024, 0, ctx->stream>>>(L.dev.patch_cost, L.dev.P, L.dev.patch_cost_stride, k_sigma,
-                                                    const_cast<unsigned char *>(L.dev.flags), ctx->outlier_result_dev);
+                                                    const_cast<unsigned char *>(L.dev.flags), ctx->outlier_result_dev, sh);
         CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
-        CUDA_TRY(cudaMemcpyAsync(ctx->outlier_result_host, ctx->outlier_result_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->outlier_result_host, ctx->outlier_result_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->outlier_result_host[1] != 0)
+            return fail(MBAVO_ENCCL, "sharded outlier detection: a peer rank did not arrive within 4 s");
         L.num_bad = ctx->outlier_result_host[0];
         *num_bad = L.num_bad;
+        return MBAVO_OK;
+    }
+
+    // ---- point sharding over the GPUs of one node ------------------------------------------------------------------
+    static int ensure_mailbox(mbavo_ctx *ctx)
+    {
+        if (ctx->mailbox)
+            return MBAVO_OK;
+        CUDA_TRY(cudaMalloc(&ctx->mailbox, sizeof(Mailbox)));
+        CUDA_TRY(cudaMemset(ctx->mailbox, 0, sizeof(Mailbox)));
+        CUDA_TRY(cudaDeviceSynchronize());
+        return MBAVO_OK;
+    }
+
+    int mbavo_shard_export(mbavo_ctx *ctx, void *handle_out, void **mailbox_ptr_out)
+    {
+        if (!ctx)
+            return fail(MBAVO_EINVAL, "null context");
+        DeviceGuard guard(ctx->device);
+        int rc = ensure_mailbox(ctx);
+        if (rc != MBAVO_OK)
+            return rc;
+        if (handle_out)
+        {
+            static_assert(sizeof(cudaIpcMemHandle_t) == MBAVO_IPC_HANDLE_BYTES, "IPC handle size");
+            cudaIpcMemHandle_t h;
+            CUDA_TRY(cudaIpcGetMemHandle(&h, ctx->mailbox));
+            std::memcpy(handle_out, &h, sizeof h);
+        }
+        if (mailbox_ptr_out)
+            *mailbox_ptr_out = ctx->mailbox;
+        return MBAVO_OK;
+    }
+
+    int mbavo_shard_connect(mbavo_ctx *ctx, int world, int rank, const void *handles, void *const *mailbox_ptrs)
+    {
+        if (!ctx || world < 1 || world > kMaxShards || rank < 0 || rank >= world || (world > 1 && !handles && !mailbox_ptrs))
+            return fail(MBAVO_EINVAL, "bad sharding arguments (world %d, rank %d, at most %d ranks)", world, rank, kMaxShards);
+        DeviceGuard guard(ctx->device);
+        int rc = ensure_mailbox(ctx);
+        if (rc != MBAVO_OK)
+            return rc;
+        mbavo_shard_disconnect(ctx);
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ShardParams sh{};
+        sh.world = world, sh.rank = rank;
+        for (int r = 0; r < world; ++r)
+        {
+            if (r == rank)
+                sh.peer[r] = ctx->mailbox;
+            else if (mailbox_ptrs)
+            {
+                // same process: plain peer access (a no-op on the same device)
+                cudaPointerAttributes at{};
+                CUDA_TRY(cudaPointerGetAttributes(&at, mailbox_ptrs[r]));
+                if (at.device != ctx->device)
+                {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                        return fail(MBAVO_ECUDA, "peer access %d -> %d: %s", ctx->device, at.device, cudaGetErrorString(e));
+                    cudaGetLastError();
+                }
+                sh.peer[r] = static_cast<Mailbox *>(mailbox_ptrs[r]);
+            }
+            else
+            {
+                cudaIpcMemHandle_t h;
+                std::memcpy(&h, static_cast<const char *>(handles) + (size_t)r * MBAVO_IPC_HANDLE_BYTES, sizeof h);
+                void *p = nullptr;
+                CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                sh.peer[r] = static_cast<Mailbox *>(p);
+                ctx->peer_is_ipc[r] = true;
+            }
+        }
+        ctx->shard = sh;
+        ctx->shard_seq = ctx->aux_seq = 0;
+        // the mailbox sequence numbers restart with the connection
+        CUDA_TRY(cudaMemsetAsync(ctx->mailbox, 0, sizeof(Mailbox), ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return MBAVO_OK;
+    }
+
+    int mbavo_shard_disconnect(mbavo_ctx *ctx)
+    {
+        if (!ctx)
+            return MBAVO_OK;
+        DeviceGuard guard(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        for (int r = 0; r < kMaxShards; ++r)
+        {
+            if (ctx->peer_is_ipc[r] && ctx->shard.peer[r])
+                cudaIpcCloseMemHandle(ctx->shard.peer[r]);
+            ctx->peer_is_ipc[r] = false;
+        }
+        ctx->shard = ShardParams{};
+        return MBAVO_OK;
+    }
+
+    int mbavo_shard_set_global_points(mbavo_ctx *ctx, int level, int num_keypoints_global)
+    {
+        if (!ctx || level < 0 || level >= MBAVO_MAX_LEVELS || num_keypoints_global < 1)
+            return fail(MBAVO_EINVAL, "bad level / point count");
+        ctx->points_global[level] = num_keypoints_global;
         return MBAVO_OK;
     }
 
@@ -810,5 +969,18 @@ extern "C"
         return MBAVO_OK;
     }
 
-    float mbavo_last_kernel_ms(mbavo_ctx *ctx) { return ctx ? ctx->last_ms : -1.f; }
+    float mbavo_last_kernel_ms(mbavo_ctx *ctx)
+    {
+        if (!ctx || !ctx->timing)
+            return -1.f;
+        // (also valid after mbavo_evaluate_async: waits for the tracking kernel of the last launch)
+        DeviceGuard guard(ctx->device);
+        float ms = -1.f;
+        if (cudaEventSynchronize(ctx->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return ctx->last_ms;
+        }
+        return ms;
+    }
 }

@@ -73,6 +73,98 @@ namespace mbavo
         int patch_cost_stride;
     };
 
+    // ---- point sharding over the GPUs of one node: one-shot all-reduce through peer-mapped mailboxes ---------------
+    // Every rank owns one Mailbox in its device memory; all ranks map all mailboxes (CUDA IPC across processes, plain peer
+    // access inside a process) and WRITE their contribution into every rank's mailbox over NVLink: the last block of the
+    // tracking kernel stores its packed vector into slot[parity][my_rank] of every peer, publishes the sequence number
+    // with a system-scope release, spins on the W flags of its OWN mailbox and sums the W slots in rank order (identical,
+    // deterministic result on every rank).  Two parities suffice: a rank can only be one evaluation ahead of a peer.
+    constexpr int kMaxShards = 8;
+    constexpr int kMailVec = (6 * kMaxKnotWindow + 1) * (6 * kMaxKnotWindow + 2) / 2; // packed_len(kMaxKnotWindow)
+    struct Mailbox
+    {
+        unsigned long long flag[2][kMaxShards];     // sequence number of the vector in slot[parity][source rank]
+        unsigned long long aux_flag[2][kMaxShards]; // same for the small-vector exchange of the outlier statistics
+        double aux[2][kMaxShards][8];
+        double slot[2][kMaxShards][kMailVec];
+    };
+    struct ShardParams
+    {
+        int world, rank;                // world <= 1: not sharded
+        Mailbox *peer[kMaxShards];      // peer[rank] is this rank's own mailbox
+        unsigned long long seq;         // sequence number of this exchange (same on every rank)
+    };
+
+#ifdef __CUDACC__
+    // ---- system-scope accesses of the sharding mailboxes (peer memory over NVLink) ------------------------------
+    __device__ __forceinline__ void st_sys(double *p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+    __device__ __forceinline__ double ld_sys(const double *p)
+    {
+        double v;
+        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+    {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+    {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ unsigned long long global_timer_ns()
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        return t;
+    }
+    // spin until *flag == seq; gives up after ~4 s (a peer that never arrives must not hang the GPU)
+    __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long seq)
+    {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(flag) != seq)
+        {
+            __nanosleep(64);
+            if (global_timer_ns() - t0 > 4000000000ull)
+                return false;
+        }
+        return true;
+    }
+
+
+    // All-reduce (sum) of n <= 8 doubles in shared memory `vals` over the ranks, executed by ALL threads of a one-block
+    // kernel (blockDim >= world * n); on return vals holds the global sums on every rank.  false: a peer timed out.
+    __device__ __forceinline__ bool shard_allreduce_small(const ShardParams &sh, unsigned long long seq, double *vals, int n)
+    {
+        __shared__ int ok_s;
+        const int par = (int)(seq & 1ull), tid = threadIdx.x;
+        if (tid == 0)
+            ok_s = 1;
+        if (tid < sh.world * n)
+            st_sys(&sh.peer[tid / n]->aux[par][sh.rank][tid % n], vals[tid % n]);
+        __threadfence_system();
+        __syncthreads();
+        if (tid < sh.world)
+        {
+            st_release_sys(&sh.peer[tid]->aux_flag[par][sh.rank], seq);
+            if (!wait_flag(&sh.peer[sh.rank]->aux_flag[par][tid], seq))
+                ok_s = 0;
+        }
+        __syncthreads();
+        if (tid < n)
+        {
+            double s = 0.0;
+            for (int r = 0; r < sh.world; ++r)
+                s += ld_sys(&sh.peer[sh.rank]->aux[par][r][tid]);
+            vals[tid] = s;
+        }
+        __syncthreads();
+        return ok_s != 0;
+    }
+#endif
+
     struct TrackParams
     {
         LevelDev lv;
@@ -93,6 +185,7 @@ namespace mbavo
         double *host_out;                     // [E] mapped pinned host memory, or nullptr
         volatile unsigned long long *host_seq;
         unsigned long long seq;
+        ShardParams shard;                    // point sharding: the vector published is the sum over all ranks
     };
 
     __host__ __device__ constexpr int packed_len(int NK) { return (6 * NK + 1) * (6 * NK + 2) / 2; }

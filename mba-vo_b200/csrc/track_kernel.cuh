@@ -36,11 +36,20 @@
 #ifndef MBAVO_MINB_H
 #define MBAVO_MINB_H 2
 #endif
+// Hessian pass: branch-free sample step, sample loop unrolled by 2 (measured best: profiles/r1_history.md); the cost-only
+// pass keeps the early exit of an invalid sample.
+#ifndef MBAVO_BRANCHLESS
+#define MBAVO_BRANCHLESS 1
+#endif
+#ifndef MBAVO_UNROLL
+#define MBAVO_UNROLL 2
+#endif
 
 namespace mbavo
 {
     namespace
     {
+        constexpr int kSampleUnroll = MBAVO_UNROLL;
         __device__ __forceinline__ float u8_to_float(unsigned int b)
         {
             // exact for 0..255: place the byte in the mantissa of 2^23 and subtract 2^23 (full-rate LOP3 + FADD
@@ -165,24 +174,46 @@ namespace mbavo
             const float A2 = fmaf(g1.x, ps.rxy.x, fmaf(g1.y, ps.rxy.y, g2.x));
             const float2 m01 = add2(ps.rxy, A01);
             const float m2 = 1.0f + A2;
-            const float il = rcp_approx(m2);                    // 1 / lambda (1 ulp: the terms it scales are blur-sized)
+            const float il_raw = rcp_approx(m2);                // 1 / lambda (1 ulp: the terms it scales are blur-sized)
             const float tau = g2.y * ps.iD;
             const float2 num = fma2(bc(-tau), m01, fma2(bc(-A2), ps.rxy, A01));
-            const float2 duv = mul2(fxy, fma2(num, bc(il), mul2(f2(g2.z, g2.w), bc(ps.iD))));
+            const float2 duv = mul2(fxy, fma2(num, bc(il_raw), mul2(f2(g2.z, g2.w), bc(ps.iD))));
             // inside [0, W-1] x [0, H-1] (compute_pixel_intensity.h:35); an invalid sample contributes nothing while the
             // divisor stays N (…cost.cu:107-110).  NaN / inf coordinates fail the comparisons.
-            if (!(duv.x >= ps.lox && duv.x <= ps.hix && duv.y >= ps.loy && duv.y <= ps.hiy))
-                return;
-            const float xf = floorf(duv.x), yf = floorf(duv.y);
-            const float dx = duv.x - xf, dy = duv.y - yf; // exact
-            const int xi = ps.X + (int)xf, yi = ps.Y + (int)yf;
-
-            // bilinear_interpolation, compute_pixel_intensity.h:40-68
-            const float dxdy = dx * dy;
-            const float w00 = 1.0f - dx - dy + dxdy, w01 = dx - dxdy, w10 = dy - dxdy, w11 = dxdy;
-            // the +1 taps carry weight 0 on the last column / row; they are clamped instead of read out of bounds
-            const int idx = yi * lv.W + xi;
-            const int rowoff = yi < lv.H - 1 ? lv.W : 0;
+            float il, w00, w01, w10, w11;
+            int idx, rowoff, xi;
+            if constexpr (WITH_J && MBAVO_BRANCHLESS)
+            {
+            // Branch-free form: an invalid sample keeps going with zero weights, a safe tap address and il = 0 (so that
+            // nothing non-finite reaches the sums).  Straight-line code lets the compiler overlap the loads of one sample
+            // with the arithmetic of the previous one when the sample loop is unrolled.
+                const bool ok = duv.x >= ps.lox && duv.x <= ps.hix && duv.y >= ps.loy && duv.y <= ps.hiy;
+                il = ok ? il_raw : 0.f;
+                const float xf = floorf(duv.x), yf = floorf(duv.y);
+                const float dx = duv.x - xf, dy = duv.y - yf; // exact
+                const int yi = ps.Y + (int)yf;
+                xi = ok ? ps.X + (int)xf : 0;
+                const float dxdy = dx * dy;
+                w00 = ok ? 1.0f - dx - dy + dxdy : 0.f, w01 = ok ? dx - dxdy : 0.f, w10 = ok ? dy - dxdy : 0.f, w11 = ok ? dxdy : 0.f;
+                idx = ok ? yi * lv.W + xi : 0;
+                rowoff = (ok && yi < lv.H - 1) ? lv.W : 0;
+            }
+            else
+            {
+                if (!(duv.x >= ps.lox && duv.x <= ps.hix && duv.y >= ps.loy && duv.y <= ps.hiy))
+                    return;
+                il = il_raw;
+                const float xf = floorf(duv.x), yf = floorf(duv.y);
+                const float dx = duv.x - xf, dy = duv.y - yf; // exact
+                const int yi = ps.Y + (int)yf;
+                xi = ps.X + (int)xf;
+                // bilinear_interpolation, compute_pixel_intensity.h:40-68
+                const float dxdy = dx * dy;
+                w00 = 1.0f - dx - dy + dxdy, w01 = dx - dxdy, w10 = dy - dxdy, w11 = dxdy;
+                // the +1 taps carry weight 0 on the last column / row; they are clamped instead of read out of bounds
+                idx = yi * lv.W + xi;
+                rowoff = yi < lv.H - 1 ? lv.W : 0;
+            }
 
             float2 gxy;
             if constexpr (PACKED && WITH_J)
@@ -260,6 +291,7 @@ namespace mbavo
             {
                 constexpr int REC = sample_rec_floats(K);
                 const int end = seg_end_s[OFF];
+#pragma unroll kSampleUnroll
                 for (; i < end; i += PH)
                     sample_step<K, NK, true, PACKED, OFF>(SmemRec{samples_s + i * REC}, ps, lv, fxy, sumI, J);
                 if constexpr (OFF + 1 <= NK - K)
@@ -608,13 +640,53 @@ namespace mbavo
                 red_s[idx] = s;
             }
             __syncthreads();
+            double *fin_s = red_s + E * PARTS; // this rank's vector, scaled by 1 / num_residuals (global when sharded)
             for (int e = threadIdx.x; e < E; e += blockDim.x)
             {
                 double s = 0.0;
 #pragma unroll
                 for (int part = 0; part < PARTS; ++part)
                     s += red_s[part * E + e];
-                s *= inv_num_residuals;
+                fin_s[e] = s * inv_num_residuals;
+            }
+            __syncthreads();
+            __shared__ int shard_ok_s;
+            const ShardParams &sh = prm.shard;
+            if (sh.world > 1)
+            {
+                // one-shot all-reduce over NVLink: push this rank's vector into every rank's mailbox, publish, wait for the
+                // W vectors in the own mailbox, sum them in rank order
+                const int par = (int)(sh.seq & 1ull);
+                for (int r = 0; r < sh.world; ++r)
+                {
+                    double *dst = sh.peer[r]->slot[par][sh.rank];
+                    for (int e = threadIdx.x; e < E; e += blockDim.x)
+                        st_sys(dst + e, fin_s[e]);
+                }
+                if (threadIdx.x == 0)
+                    shard_ok_s = 1;
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x < sh.world)
+                {
+                    st_release_sys(&sh.peer[threadIdx.x]->flag[par][sh.rank], sh.seq);
+                    if (!wait_flag(&sh.peer[sh.rank]->flag[par][threadIdx.x], sh.seq))
+                        shard_ok_s = 0;
+                }
+                __syncthreads();
+                const Mailbox *mine = sh.peer[sh.rank];
+                for (int e = threadIdx.x; e < E; e += blockDim.x)
+                {
+                    double s = 0.0;
+                    for (int r = 0; r < sh.world; ++r)
+                        s += ld_sys(&mine->slot[par][r][e]);
+                    fin_s[e] = shard_ok_s ? s : __longlong_as_double(0x7ff8000000000000ll); // NaN: a peer timed out
+                }
+                __syncthreads();
+            }
+            for (int e = threadIdx.x; e < E; e += blockDim.x)
+            {
+                const double s = fin_s[e];
                 prm.packed_out[e] = s;
                 if (prm.host_out)
                     prm.host_out[e] = s;

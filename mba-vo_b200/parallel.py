@@ -1,10 +1,15 @@
 """Point-sharded evaluation over the GPUs of one node.
 
 Host-map points are independent units; the only coupling between shards is the sum into the packed vector
-[cost, g, triu(H)].  Every rank owns a contiguous block of the points of every pyramid level, images / spline /
-pattern are replicated, and ONE all-reduce of the packed vector (752 B for 2 knots) per evaluation makes the result
-global.  torch.distributed (NCCL over NVLink) is plumbing only: the packed vector is produced by the fused kernel
-directly into the tensor that is all-reduced, on the same stream.
+[cost, g, triu(H)] (and three scalars of the outlier statistics).  Every rank owns a contiguous block of the points of
+every pyramid level; images / spline / pattern are replicated.
+
+Two ways to make the result global:
+  * fused (default, `connect_shards`): the tracking kernel's last block exchanges the packed vector with all ranks
+    through peer-mapped mailboxes over NVLink and sums them in rank order — one-shot all-reduce inside the kernel.
+    torch.distributed only carries the 64-byte CUDA IPC handles once, at set-up.
+  * NCCL (`ShardedEvaluator`, baseline): kernel -> ncclAllReduce of the packed vector (728 B for 2 knots) on the same
+    stream -> D2H.
 """
 from __future__ import annotations
 
@@ -24,6 +29,21 @@ def reduce_packed(local: np.ndarray, all_reduce_sum: Callable[[np.ndarray], np.n
     """Sum of the per-shard packed vectors.  Each shard is already scaled by 1 / num_residuals_GLOBAL, so the plain
     sum is the global [cost, g, triu(H)]."""
     return all_reduce_sum(np.ascontiguousarray(local, dtype=np.float64))
+
+
+def connect_shards(ctx, prob, rank: int, world: int, all_gather_bytes: Callable[[bytes], list]):
+    """Upload this rank's shard of every level of `prob` into `ctx` and connect the fused all-reduce.
+    all_gather_bytes(b) -> [b_0, ..., b_{world-1}] exchanges one bytes object per rank (any transport).
+    Afterwards ctx.evaluate / gn_iteration / optimize_level / detect_outliers are collective calls."""
+    ctx.set_frame_times(prob.cap, prob.exp)
+    for l, lv in enumerate(prob.levels):
+        lo, hi = shard_bounds(lv.P, rank, world)
+        ctx.set_level(l, lv, slice(lo, hi))
+    handle, _ = ctx.shard_export()
+    handles = all_gather_bytes(handle)
+    ctx.shard_connect(world, rank, handles=handles)
+    for l, lv in enumerate(prob.levels):
+        ctx.shard_set_global_points(l, lv.P)
 
 
 class ShardedEvaluator:

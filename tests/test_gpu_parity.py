@@ -303,3 +303,106 @@ def test_sharded_evaluator_single_rank(pkg, api, synth):
         c2, _, _ = ev.evaluate(0, prob.knots_t, prob.knots_R, False)
     assert c == want[0] and np.array_equal(H, want[1]) and np.array_equal(g, want[2])
     assert abs(c2 - c) <= 1e-6 * c  # the cost-only pass blends byte taps, the Hessian pass fp16 texels: same values, other FMA order
+
+
+def _run_ranks(fns):
+    """Run one callable per rank concurrently (ctypes releases the GIL while a rank spins inside a collective call)."""
+    import threading
+
+    out, err = [None] * len(fns), [None] * len(fns)
+
+    def body(i):
+        try:
+            out[i] = fns[i]()
+        except BaseException as e:  # noqa: BLE001
+            err[i] = e
+
+    th = [threading.Thread(target=body, args=(i,)) for i in range(len(fns))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_shard_allreduce(pkg, api, O, orc, synth, world):
+    """mbavo_shard_*: `world` ranks (contexts on this GPU, one thread each, mailboxes connected by pointer) evaluate their
+    point shards; the kernels exchange the packed vectors through the mailboxes and every rank returns the global result.
+    Checked against the unsharded context and the oracle; then the collective outlier detection and a collective LM loop."""
+    from mbavo_b200.parallel import shard_bounds
+
+    prob = synth.make_config("tiny")
+    lv = prob.levels[0]
+    ctxs = [pkg.Context(api.limits_for(prob)) for _ in range(world)]
+    try:
+        ptrs = []
+        for r, ctx in enumerate(ctxs):
+            ctx.set_frame_times(prob.cap, prob.exp)
+            for l, lvl in enumerate(prob.levels):
+                lo, hi = shard_bounds(lvl.P, r, world)
+                ctx.set_level(l, lvl, slice(lo, hi))
+            ptrs.append(ctx.shard_export()[1])
+        for r, ctx in enumerate(ctxs):
+            ctx.shard_connect(world, r, mailbox_ptrs=ptrs)
+            for l, lvl in enumerate(prob.levels):
+                ctx.shard_set_global_points(l, lvl.P)
+        args = (0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a)
+        res = _run_ranks([lambda c=c: c.evaluate(*args, True) for c in ctxs])
+        res_c = _run_ranks([lambda c=c: c.evaluate(*args, False) for c in ctxs])
+        want = orc.evaluate(prob, 0)
+        for (c, H, g), (c2, _, _) in zip(res, res_c):
+            assert c == res[0][0] and np.array_equal(H, res[0][1]) and np.array_equal(g, res[0][2])  # identical on all ranks
+            assert abs(c - want[0]) <= COST_TOL * want[0] and abs(c2 - want[0]) <= COST_TOL * want[0]
+            assert max_rel(H, want[1]) <= 1e-5 and max_rel(g, want[2]) <= 1e-5
+            assert rel(first_step(O, H, g), first_step(O, want[1], want[2])) <= DELTA_TOL
+        # collective outlier statistics == the restatement applied to ALL patch costs
+        kt = prob.knots_t + 0.05
+        _run_ranks([lambda c=c: c.evaluate(0, prob.k, prob.t0, prob.dt, kt, prob.knots_R, prob.huber_a, False) for c in ctxs])
+        pcs = [ctx.patch_costs(0, prob.F, shard_bounds(lv.P, r, world)[1] - shard_bounds(lv.P, r, world)[0])[0]
+               for r, ctx in enumerate(ctxs)]
+        want_flags = np.zeros(lv.P, dtype=np.uint8)
+        want_n = O.detect_outliers(np.concatenate(pcs)[None, :], want_flags, 3.0)
+        got_n = _run_ranks([lambda c=c: c.detect_outliers(0, 3.0) for c in ctxs])
+        assert want_n > 0 and all(n == want_n for n in got_n)
+        got = _run_ranks([lambda c=c: c.evaluate(0, prob.k, prob.t0, prob.dt, kt, prob.knots_R, prob.huber_a, True) for c in ctxs])
+        want2 = orc.evaluate(prob, 0, kt, prob.knots_R, flags=want_flags, num_bad=want_n)
+        assert abs(got[0][0] - want2[0]) <= COST_TOL * want2[0] and max_rel(got[0][1], want2[1]) <= 1e-4
+        # a whole collective LM loop: every rank commits the same knots, equal to the single-context run
+        for c in ctxs:
+            c.set_outliers(0, None)
+        lm = _run_ranks([lambda c=c: pkg.optimize_trajectory(c, prob) for c in ctxs])
+        with pkg.Context(api.limits_for(prob)) as solo:
+            api.upload_problem(solo, prob)
+            kt1, kR1, s1 = pkg.optimize_trajectory(solo, prob)
+        for kt_r, kR_r, s_r in lm:
+            assert np.array_equal(kt_r, lm[0][0]) and np.array_equal(kR_r, lm[0][1])
+            # (the sharded sums add the same terms in another order; the LM iterations amplify that rounding)
+            assert np.abs(kt_r - kt1).max() <= 1e-4 and np.abs(kR_r - kR1).max() <= 1e-5
+            assert [x["decisions"] for x in s_r] == [x["decisions"] for x in s1]
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_shard_peer_timeout_is_an_error(pkg, api, synth):
+    """A rank whose peer never calls gets MBAVO_ENCCL after the in-kernel time-out instead of hanging the GPU."""
+    prob = synth.make_config("tiny")
+    a, b = pkg.Context(api.limits_for(prob)), pkg.Context(api.limits_for(prob))
+    try:
+        ptrs = []
+        for ctx in (a, b):
+            api.upload_problem(ctx, prob)
+            ptrs.append(ctx.shard_export()[1])
+        a.shard_connect(2, 0, mailbox_ptrs=ptrs)
+        a.shard_set_global_points(0, 2 * prob.levels[0].P)
+        with pytest.raises(pkg.MbavoError, match="-6"):
+            a.evaluate(0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, False)
+        a.shard_disconnect()
+        assert a.evaluate(0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, False)[0] > 0
+    finally:
+        a.close()
+        b.close()
