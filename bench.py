@@ -10,8 +10,10 @@ sum_l 2 * P_l * N of them.
 
 Legs (own arm):
   value     inputs resident in HBM, K steps through the C-ABI (mbavo_evaluate), device-timed
-  e2e       the same K steps, but every step first re-uploads every level (images, gradients, points) from PINNED host
-            buffers through mbavo_set_level, and reads H, g, cost back: host<->device copies inside the timed region
+  e2e       the same K steps, but every step first re-uploads the frame from PINNED host buffers through the C-ABI — the
+            level-0 keyframe and live image (mbavo_set_keyframe_pyramid / mbavo_set_live_pyramid build the coarser levels,
+            gradients and texels on the GPU) and the host-map points of every level (mbavo_set_level_points) — and reads
+            H, g, cost back: host<->device copies inside the timed region
   roofline  per-kernel durations of the same steps (CUDA events around the tracking kernel, on its stream)
   cpu_baseline  the reference's arithmetic on the host cores (oracle/_ref, else the oracle port), bounded sample
 
@@ -212,13 +214,18 @@ def run_own(args, pkg):
         pinned.append(pkg.synth.Level(H=lv.H, W=lv.W, fx=lv.fx, fy=lv.fy, cx=lv.cx, cy=lv.cy, ref_I=pin(lv.ref_I),
                                       ref_dIxy=pin(lv.ref_dIxy), cur_I=[pin(c) for c in lv.cur_I], xy=pin(lv.xy), z=pin(lv.z),
                                       pattern=pin(lv.pattern), N=lv.N))
-    h2d_step = sum(lv.ref_I.nbytes + lv.ref_dIxy.nbytes + sum(c.nbytes for c in lv.cur_I) + lv.xy.nbytes + lv.z.nbytes +
-                   lv.pattern.nbytes for lv in prob.levels) + 2 * len(prob.levels) * (7 * prob.n_knots * 8 + 2048)
-    d2h_step = len(prob.levels) * (91 * 8 + 8)
+    n_levels = len(prob.levels)
+    # per step: level-0 keyframe + live image, points / pattern of every level, and per evaluation the spline state
+    # (launch parameter of the pose kernel, ~2.3 KB); back: the packed vector + sequence word per evaluation
+    h2d_step = pinned[0].ref_I.nbytes + sum(c.nbytes for c in pinned[0].cur_I) + \
+        sum(lv.xy.nbytes + lv.z.nbytes + lv.pattern.nbytes for lv in prob.levels) + 2 * n_levels * 2304
+    d2h_step = 2 * n_levels * 8 + n_levels * 91 * 8 + n_levels * 8
 
     def upload_all():
+        ctx.set_keyframe_pyramid(n_levels, pinned[0].ref_I)
+        ctx.set_live_pyramid(n_levels, pinned[0].cur_I)
         for l, lv in enumerate(pinned):
-            ctx.set_level(l, lv)
+            ctx.set_level_points(l, lv)
 
     upload_all()
     fused = world > 1 and args.collective == "fused"
@@ -230,10 +237,6 @@ def run_own(args, pkg):
         ctx.shard_connect(world, rank, handles=gathered)
         for l, lv in enumerate(prob.levels):
             ctx.shard_set_global_points(l, lv.P * world)
-
-        def upload_all():  # noqa: F811  (set_level keeps the connection; the global point counts stay valid)
-            for l, lv in enumerate(pinned):
-                ctx.set_level(l, lv)
 
         def evaluate(level, kt, kR, with_h):
             return ctx.evaluate(level, prob.k, prob.t0, prob.dt, kt, kR, prob.huber_a, with_h)

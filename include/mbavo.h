@@ -112,6 +112,37 @@ int mbavo_set_frame_times(mbavo_ctx *ctx, int n_frames, const double *cap_time, 
  * level's outlier flags (optimizePyramidLevel, :600-601). */
 int mbavo_set_level(mbavo_ctx *ctx, int level, const mbavo_level *data);
 
+/* ---- pyramids built on the device ----------------------------------------------------------
+ * The step before the path: ImagePyramid<T>::computePyramid (src/core/measurements/ImagePyramid.h:59-99, 2x2 box, float
+ * average, truncating cast), compute_image_gradients (src/core/image_proc/Gradient.h:17-75, 0.5 * central differences,
+ * zero 1-pixel border) and the per-level cudaMalloc + H2D of Image::uploadToGpu (Image.h:125-136) that the tracker runs
+ * on the CPU per keyframe (blur_aware_direct_tracker.cpp:346-353) and per frame (:112-116).  Only the level-0 images
+ * cross PCIe; coarser levels, gradients and texels are produced on the GPU, bit-identical to the CPU loops.
+ * Level l has H0 / 2^l x W0 / 2^l pixels.  A level is ready for mbavo_evaluate once its keyframe, live frame and points
+ * are set; mbavo_set_level on the same level index replaces it. */
+typedef struct mbavo_level_points
+{
+    int mem;                       /* MBAVO_MEM_HOST or MBAVO_MEM_DEVICE, applies to keypoint_xy / keypoint_z */
+    double fx, fy, cx, cy;         /* intrinsics of this level (tracker.cpp:766-776) */
+    const void *keypoint_xy;       /* as in mbavo_level */
+    int keypoint_xy_stride, keypoint_xy_offset;
+    const double *keypoint_z;
+    int num_keypoints;
+    const int *pattern_xy;
+    int patch_size;
+    int num_virtual_poses;
+} mbavo_level_points;
+
+int mbavo_set_keyframe_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0);
+int mbavo_set_live_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *const *cur_I0, int n_frames);
+int mbavo_set_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *points);
+
+/* A new live (blurred) frame for an already set level — what BlurAwareDirectTracker::trackFrame uploads per frame
+ * (blur_aware_direct_tracker.cpp:112-116) while keyframe image, gradient, texels and host-map points stay resident.
+ * cur_I: n_frames images of the level's H*W (host or device, as the level was set; the array itself is in host memory).
+ * Clears the level's outlier flags like mbavo_set_level. */
+int mbavo_set_live_images(mbavo_ctx *ctx, int level, int mem, const unsigned char *const *cur_I, int n_frames);
+
 /* Outlier flags of a level: cuda_keypoints_outlier_flags + num_bad_keypoints (spline_update_step.h:25-26).
  * flags == NULL clears them.  flags is a host array of num_keypoints bytes (1 = outlier). */
 int mbavo_set_outliers(mbavo_ctx *ctx, int level, const unsigned char *flags, int num_bad_keypoints);

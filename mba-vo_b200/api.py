@@ -18,7 +18,8 @@ SOLVER_SVD_JACOBI, SOLVER_LDLT = 0, 1
 # every symbol include/mbavo.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "mbavo_last_error", "mbavo_version", "mbavo_create", "mbavo_destroy", "mbavo_set_stream", "mbavo_set_frame_times",
-    "mbavo_set_level", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
+    "mbavo_set_level", "mbavo_set_keyframe_pyramid", "mbavo_set_live_pyramid", "mbavo_set_level_points",
+    "mbavo_set_live_images", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
     "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
@@ -44,6 +45,13 @@ class _Level(C.Structure):
                 ("num_keypoints", C.c_int), ("pattern_xy", C.c_void_p), ("patch_size", C.c_int),
                 ("num_virtual_poses", C.c_int), ("ext_outlier_flags", C.c_void_p), ("ext_patch_cost", C.c_void_p),
                 ("ext_patch_cost_stride", C.c_int)]
+
+
+class _LevelPoints(C.Structure):
+    _fields_ = [("mem", C.c_int), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("keypoint_xy", C.c_void_p), ("keypoint_xy_stride", C.c_int), ("keypoint_xy_offset", C.c_int),
+                ("keypoint_z", C.c_void_p), ("num_keypoints", C.c_int), ("pattern_xy", C.c_void_p), ("patch_size", C.c_int),
+                ("num_virtual_poses", C.c_int)]
 
 
 class _Spline(C.Structure):
@@ -165,6 +173,31 @@ class Context:
         d = _Level(MEM_DEVICE, H, W, fx, fy, cx, cy, ref_I_ptr, ref_dIxy_ptr, cur, F, xy_ptr, xy_stride, xy_offset, z_ptr, P,
                    pattern_ptr, S, N, ext_flags_ptr, ext_patch_cost_ptr, ext_patch_cost_stride)
         self._check(self.lib.mbavo_set_level(self._h, C.c_int(level), C.byref(d)))
+
+    def set_keyframe_pyramid(self, n_levels: int, ref_I0: np.ndarray):
+        """mbavo_set_keyframe_pyramid: level-0 keyframe (host uint8); coarser levels, gradients, texels built on the GPU."""
+        H0, W0 = ref_I0.shape
+        self._check(self.lib.mbavo_set_keyframe_pyramid(self._h, C.c_int(n_levels), C.c_int(MEM_HOST), C.c_void_p(ref_I0.ctypes.data),
+                                                        C.c_int(H0), C.c_int(W0)))
+
+    def set_live_pyramid(self, n_levels: int, cur_I0: Sequence[np.ndarray]):
+        F = len(cur_I0)
+        cur = (C.c_void_p * F)(*[c.ctypes.data for c in cur_I0])
+        self._check(self.lib.mbavo_set_live_pyramid(self._h, C.c_int(n_levels), C.c_int(MEM_HOST), cur, C.c_int(F)))
+
+    def set_level_points(self, level: int, lv, point_slice: Optional[slice] = None):
+        """mbavo_set_level_points from a synth.Level: intrinsics, host-map points, pattern, exposure samples."""
+        xy = lv.xy if point_slice is None else np.ascontiguousarray(lv.xy[point_slice])
+        z = lv.z if point_slice is None else np.ascontiguousarray(lv.z[point_slice])
+        d = _LevelPoints(MEM_HOST, lv.fx, lv.fy, lv.cx, lv.cy, xy.ctypes.data, 16, 0, z.ctypes.data, xy.shape[0],
+                         lv.pattern.ctypes.data, lv.S, lv.N)
+        self._check(self.lib.mbavo_set_level_points(self._h, C.c_int(level), C.byref(d)))
+
+    def set_live_images(self, level: int, cur_I: Sequence[np.ndarray]):
+        """mbavo_set_live_images with host images: a new blurred frame for a level whose keyframe stays resident."""
+        F = len(cur_I)
+        cur = (C.c_void_p * F)(*[c.ctypes.data for c in cur_I])
+        self._check(self.lib.mbavo_set_live_images(self._h, C.c_int(level), C.c_int(MEM_HOST), cur, C.c_int(F)))
 
     def set_outliers(self, level: int, flags: Optional[np.ndarray], num_bad: int = 0):
         if flags is None:
@@ -331,6 +364,16 @@ def upload_problem(ctx: Context, prob) -> None:
     ctx.set_frame_times(prob.cap, prob.exp)
     for l, lv in enumerate(prob.levels):
         ctx.set_level(l, lv)
+
+
+def upload_problem_pyramid(ctx: Context, prob) -> None:
+    """The same problem through the device-built pyramid path: only the level-0 images travel."""
+    ctx.set_frame_times(prob.cap, prob.exp)
+    n = len(prob.levels)
+    ctx.set_keyframe_pyramid(n, prob.levels[0].ref_I)
+    ctx.set_live_pyramid(n, prob.levels[0].cur_I)
+    for l, lv in enumerate(prob.levels):
+        ctx.set_level_points(l, lv)
 
 
 def optimize_trajectory(ctx: Context, prob, **kw):

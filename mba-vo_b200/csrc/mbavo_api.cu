@@ -24,6 +24,9 @@ namespace mbavo
     size_t track_kernel_smem_bytes(int K, int NK, bool with_j, int N, int S, int TP);
     cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,
                                    int *inexact, cudaStream_t stream);
+    cudaError_t launch_pyr_down_kernel(const unsigned char *src, int Ws, unsigned char *dst, int Hd, int Wd, cudaStream_t stream);
+    cudaError_t launch_pack_image_kernel(const unsigned char *I, int H, int W, uint4 *pair, unsigned int *quad, float *grad,
+                                         cudaStream_t stream);
 } // namespace mbavo
 
 using namespace mbavo;
@@ -65,6 +68,13 @@ namespace
         uint4 *tex_pair = nullptr;
         unsigned int *tex_quad = nullptr;
         size_t cap_tex = 0;
+        // device-built pyramid path (mbavo_set_keyframe_pyramid / mbavo_set_live_pyramid / mbavo_set_level_points)
+        unsigned char *pyr_ref = nullptr, *pyr_cur[kMaxFrames] = {};
+        float *pyr_grad = nullptr;
+        double *pts_xy = nullptr, *pts_z = nullptr;
+        size_t pyr_cap_ref = 0, pyr_cap_cur = 0, pyr_cap_grad = 0, pts_cap = 0;
+        int pyr_cap_frames = 0;
+        bool has_key = false, has_live = false, has_pts = false;
         // always owned
         int2 *pattern = nullptr;
         unsigned char *flags = nullptr;
@@ -521,6 +531,12 @@ extern "C"
             cudaFree(L.patch_cost);
             cudaFree(L.tex_pair);
             cudaFree(L.tex_quad);
+            cudaFree(L.pyr_ref);
+            cudaFree(L.pyr_grad);
+            for (auto &c : L.pyr_cur)
+                cudaFree(c);
+            cudaFree(L.pts_xy);
+            cudaFree(L.pts_z);
         }
         cudaFree(ctx->inexact_dev);
         cudaFreeHost(ctx->inexact_host);
@@ -589,7 +605,10 @@ extern "C"
         DeviceGuard guard(ctx->device);
         LevelStore &L = ctx->levels[level];
         cudaStream_t s = ctx->stream;
-        CUDA_TRY(cudaStreamSynchronize(s)); // nothing in flight may still read the buffers we are about to replace
+        // nothing in flight may still read the buffers we are about to replace (only mbavo_evaluate_async leaves work in
+        // flight; every other entry point returns with the stream idle)
+        if (cudaStreamQuery(s) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(s));
         const size_t npix = (size_t)d->H * d->W;
         const int P = d->num_keypoints, F = d->n_frames;
 
@@ -642,6 +661,7 @@ extern "C"
         // keyframe texels: built from the device copies on every call (the caller may have changed the image content
         // behind an unchanged pointer); kept only if every gradient value survives the fp16 round trip
         L.dev.ref_pair = nullptr, L.dev.ref_quad = nullptr;
+        bool texels_pending = false;
         if (ctx->use_texels && npix < (size_t)1 << 27)
         {
             if (L.cap_tex < npix)
@@ -658,9 +678,7 @@ extern "C"
                                         L.tex_quad, ctx->inexact_dev, s));
             ctx->launches += 1;
             CUDA_TRY(cudaMemcpyAsync(ctx->inexact_host, ctx->inexact_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
-            if (*ctx->inexact_host == 0)
-                L.dev.ref_pair = L.tex_pair, L.dev.ref_quad = L.tex_quad;
+            texels_pending = true; // the verdict is read after the one synchronisation at the end
         }
         CUDA_TRY(cudaMemcpyAsync(L.pattern, d->pattern_xy, sizeof(int2) * d->patch_size, cudaMemcpyDefault, s));
         if (!d->ext_outlier_flags)
@@ -683,7 +701,246 @@ extern "C"
         else
             L.dev.patch_cost = L.patch_cost, L.dev.patch_cost_stride = 1;
         L.set = true;
+        L.has_key = L.has_live = L.has_pts = false; // the level no longer comes from the device-built pyramid path
         CUDA_TRY(cudaStreamSynchronize(s)); // host buffers are only borrowed for the call
+        if (texels_pending && *ctx->inexact_host == 0)
+            L.dev.ref_pair = L.tex_pair, L.dev.ref_quad = L.tex_quad;
+        return MBAVO_OK;
+    }
+
+    // ---- device-built pyramids ----------------------------------------------------------------
+    static int ensure_level_scratch(mbavo_ctx *ctx, LevelStore &L)
+    {
+        if (!L.pattern)
+        {
+            CUDA_TRY(cudaMalloc(&L.pattern, sizeof(int2) * ctx->lim.max_patch_size));
+            CUDA_TRY(cudaMalloc(&L.flags, ctx->lim.max_num_keypoints));
+            CUDA_TRY(cudaMalloc(&L.patch_cost, sizeof(double) * (size_t)ctx->lim.max_num_keypoints * ctx->lim.max_num_frames));
+        }
+        return MBAVO_OK;
+    }
+
+    static void pyramid_level_ready(LevelStore &L)
+    {
+        L.set = L.has_key && L.has_live && L.has_pts;
+    }
+
+    int mbavo_set_keyframe_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0)
+    {
+        if (!ctx || !ref_I0 || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS || (mem != MBAVO_MEM_HOST && mem != MBAVO_MEM_DEVICE))
+            return fail(MBAVO_EINVAL, "bad arguments");
+        if ((H0 >> (n_levels - 1)) < 2 || (W0 >> (n_levels - 1)) < 2)
+            return fail(MBAVO_EINVAL, "%d levels of a %d x %d image leave less than 2 x 2 pixels", n_levels, H0, W0);
+        DeviceGuard guard(ctx->device);
+        cudaStream_t s = ctx->stream;
+        if (cudaStreamQuery(s) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(s));
+        for (int l = 0; l < n_levels; ++l)
+        {
+            LevelStore &L = ctx->levels[l];
+            const int H = H0 / (1 << l), W = W0 / (1 << l); // ImagePyramid.h:71-72
+            const size_t npix = (size_t)H * W;
+            int rc = ensure_level_scratch(ctx, L);
+            if (rc != MBAVO_OK)
+                return rc;
+            if (L.has_key && (L.dev.H != H || L.dev.W != W))
+                L.has_live = false; // live images of another size are void
+            if (L.pyr_cap_ref < npix)
+            {
+                cudaFree(L.pyr_ref);
+                L.pyr_ref = nullptr, L.pyr_cap_ref = 0;
+                CUDA_TRY(cudaMalloc(&L.pyr_ref, npix));
+                L.pyr_cap_ref = npix;
+            }
+            if (ctx->use_texels && L.cap_tex < npix)
+            {
+                cudaFree(L.tex_pair);
+                cudaFree(L.tex_quad);
+                L.tex_pair = nullptr, L.tex_quad = nullptr, L.cap_tex = 0;
+                CUDA_TRY(cudaMalloc(&L.tex_pair, npix * sizeof(uint4)));
+                CUDA_TRY(cudaMalloc(&L.tex_quad, npix * sizeof(unsigned int)));
+                L.cap_tex = npix;
+            }
+            if (!ctx->use_texels && L.pyr_cap_grad < npix)
+            {
+                cudaFree(L.pyr_grad);
+                L.pyr_grad = nullptr, L.pyr_cap_grad = 0;
+                CUDA_TRY(cudaMalloc(&L.pyr_grad, npix * 2 * sizeof(float)));
+                L.pyr_cap_grad = npix;
+            }
+            if (l == 0)
+                CUDA_TRY(cudaMemcpyAsync(L.pyr_ref, ref_I0, npix, mem == MBAVO_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+            else
+                CUDA_TRY(launch_pyr_down_kernel(ctx->levels[l - 1].pyr_ref, W0 / (1 << (l - 1)), L.pyr_ref, H, W, s));
+            CUDA_TRY(launch_pack_image_kernel(L.pyr_ref, H, W, ctx->use_texels ? L.tex_pair : nullptr, ctx->use_texels ? L.tex_quad : nullptr,
+                                              ctx->use_texels ? nullptr : L.pyr_grad, s));
+            ctx->launches += l == 0 ? 1 : 2;
+            if (L.owns)
+                free_level(L); // buffers of an earlier mbavo_set_level
+            L.dev.H = H, L.dev.W = W;
+            L.dev.ref_I = L.pyr_ref;
+            L.dev.ref_dIxy = reinterpret_cast<const float2 *>(ctx->use_texels ? nullptr : L.pyr_grad);
+            L.dev.ref_pair = ctx->use_texels ? L.tex_pair : nullptr;
+            L.dev.ref_quad = ctx->use_texels ? L.tex_quad : nullptr;
+            L.has_key = true;
+            pyramid_level_ready(L);
+        }
+        CUDA_TRY(cudaStreamSynchronize(s)); // the host image is only borrowed for the call
+        return MBAVO_OK;
+    }
+
+    int mbavo_set_live_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *const *cur_I0, int n_frames)
+    {
+        if (!ctx || !cur_I0 || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS || (mem != MBAVO_MEM_HOST && mem != MBAVO_MEM_DEVICE))
+            return fail(MBAVO_EINVAL, "bad arguments");
+        if (n_frames < 1 || n_frames > ctx->lim.max_num_frames)
+            return fail(MBAVO_ECAPACITY, "n_frames %d outside [1, %d]", n_frames, ctx->lim.max_num_frames);
+        for (int l = 0; l < n_levels; ++l)
+            if (!ctx->levels[l].has_key)
+                return fail(MBAVO_ENOTREADY, "mbavo_set_keyframe_pyramid has not set level %d", l);
+        DeviceGuard guard(ctx->device);
+        cudaStream_t s = ctx->stream;
+        if (cudaStreamQuery(s) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(s));
+        for (int l = 0; l < n_levels; ++l)
+        {
+            LevelStore &L = ctx->levels[l];
+            const size_t npix = (size_t)L.dev.H * L.dev.W;
+            if (L.pyr_cap_cur < npix || L.pyr_cap_frames < n_frames)
+            {
+                for (auto &c : L.pyr_cur)
+                {
+                    cudaFree(c);
+                    c = nullptr;
+                }
+                L.pyr_cap_cur = 0, L.pyr_cap_frames = 0;
+                for (int f = 0; f < n_frames; ++f)
+                    CUDA_TRY(cudaMalloc(&L.pyr_cur[f], npix));
+                L.pyr_cap_cur = npix, L.pyr_cap_frames = n_frames;
+            }
+            for (int f = 0; f < n_frames; ++f)
+            {
+                if (l == 0)
+                {
+                    if (!cur_I0[f])
+                        return fail(MBAVO_EINVAL, "null image");
+                    CUDA_TRY(cudaMemcpyAsync(L.pyr_cur[f], cur_I0[f], npix, mem == MBAVO_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+                }
+                else
+                {
+                    CUDA_TRY(launch_pyr_down_kernel(ctx->levels[l - 1].pyr_cur[f], ctx->levels[l - 1].dev.W, L.pyr_cur[f], L.dev.H, L.dev.W, s));
+                    ctx->launches += 1;
+                }
+                L.dev.cur_I[f] = L.pyr_cur[f];
+            }
+            for (int f = n_frames; f < kMaxFrames; ++f)
+                L.dev.cur_I[f] = nullptr;
+            L.dev.F = n_frames;
+            if (L.flags)
+                CUDA_TRY(cudaMemsetAsync(L.flags, 0, ctx->lim.max_num_keypoints, s)); // tracker.cpp:600-601
+            L.num_bad = 0;
+            L.has_live = true;
+            pyramid_level_ready(L);
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return MBAVO_OK;
+    }
+
+    int mbavo_set_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d)
+    {
+        if (!ctx || !d || level < 0 || level >= MBAVO_MAX_LEVELS)
+            return fail(MBAVO_EINVAL, "bad context / level");
+        if (d->mem != MBAVO_MEM_HOST && d->mem != MBAVO_MEM_DEVICE)
+            return fail(MBAVO_EINVAL, "mem must be MBAVO_MEM_HOST or MBAVO_MEM_DEVICE");
+        if (!d->keypoint_xy || !d->keypoint_z || !d->pattern_xy)
+            return fail(MBAVO_EINVAL, "null keypoint / pattern pointers");
+        if (d->num_keypoints < 1 || d->num_keypoints > ctx->lim.max_num_keypoints)
+            return fail(MBAVO_ECAPACITY, "num_keypoints %d outside [1, %d]", d->num_keypoints, ctx->lim.max_num_keypoints);
+        if (d->patch_size < 1 || d->patch_size > ctx->lim.max_patch_size)
+            return fail(MBAVO_ECAPACITY, "patch_size %d outside [1, %d]", d->patch_size, ctx->lim.max_patch_size);
+        if (d->num_virtual_poses < 1 || d->num_virtual_poses > ctx->lim.max_num_virtual_poses_per_frame)
+            return fail(MBAVO_ECAPACITY, "num_virtual_poses %d outside [1, %d]", d->num_virtual_poses,
+                        ctx->lim.max_num_virtual_poses_per_frame);
+        if (d->keypoint_xy_stride < 16 || d->keypoint_xy_offset < 0 || d->keypoint_xy_offset + 16 > d->keypoint_xy_stride ||
+            d->keypoint_xy_stride % 8 != 0 || d->keypoint_xy_offset % 8 != 0)
+            return fail(MBAVO_EINVAL, "keypoint_xy stride/offset must describe two aligned doubles per record");
+        if (!(d->fx > 0) || !(d->fy > 0))
+            return fail(MBAVO_EINVAL, "fx, fy must be positive");
+        DeviceGuard guard(ctx->device);
+        LevelStore &L = ctx->levels[level];
+        if (L.set && !L.has_key)
+            return fail(MBAVO_EINVAL, "level %d was set by mbavo_set_level; points of such a level are replaced by mbavo_set_level", level);
+        cudaStream_t s = ctx->stream;
+        if (cudaStreamQuery(s) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(s));
+        int rc = ensure_level_scratch(ctx, L);
+        if (rc != MBAVO_OK)
+            return rc;
+        const int P = d->num_keypoints;
+        if (d->mem == MBAVO_MEM_HOST)
+        {
+            if (L.pts_cap < (size_t)P)
+            {
+                cudaFree(L.pts_xy);
+                cudaFree(L.pts_z);
+                L.pts_xy = L.pts_z = nullptr, L.pts_cap = 0;
+                CUDA_TRY(cudaMalloc(&L.pts_xy, sizeof(double) * 2 * P));
+                CUDA_TRY(cudaMalloc(&L.pts_z, sizeof(double) * P));
+                L.pts_cap = P;
+            }
+            CUDA_TRY(cudaMemcpy2DAsync(L.pts_xy, 16, (const char *)d->keypoint_xy + d->keypoint_xy_offset, d->keypoint_xy_stride, 16, P,
+                                       cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(L.pts_z, d->keypoint_z, sizeof(double) * P, cudaMemcpyHostToDevice, s));
+            L.dev.xy = reinterpret_cast<const char *>(L.pts_xy), L.dev.xy_stride = 16, L.dev.xy_offset = 0;
+            L.dev.z = L.pts_z;
+        }
+        else
+        {
+            L.dev.xy = reinterpret_cast<const char *>(d->keypoint_xy);
+            L.dev.xy_stride = d->keypoint_xy_stride, L.dev.xy_offset = d->keypoint_xy_offset;
+            L.dev.z = d->keypoint_z;
+        }
+        CUDA_TRY(cudaMemcpyAsync(L.pattern, d->pattern_xy, sizeof(int2) * d->patch_size, cudaMemcpyDefault, s));
+        CUDA_TRY(cudaMemsetAsync(L.flags, 0, ctx->lim.max_num_keypoints, s));
+        L.num_bad = 0;
+        L.dev.fx = d->fx, L.dev.fy = d->fy, L.dev.cx = d->cx, L.dev.cy = d->cy;
+        L.dev.inv_fx = 1.0 / d->fx, L.dev.inv_fy = 1.0 / d->fy;
+        L.dev.P = P, L.dev.S = d->patch_size, L.dev.N = d->num_virtual_poses;
+        L.dev.pattern = L.pattern;
+        L.dev.flags = L.flags;
+        L.dev.patch_cost = L.patch_cost, L.dev.patch_cost_stride = 1;
+        L.has_pts = true;
+        pyramid_level_ready(L);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return MBAVO_OK;
+    }
+
+    int mbavo_set_live_images(mbavo_ctx *ctx, int level, int mem, const unsigned char *const *cur_I, int n_frames)
+    {
+        if (!ctx || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set || !cur_I)
+            return fail(MBAVO_ENOTREADY, "level not set");
+        LevelStore &L = ctx->levels[level];
+        if (n_frames != L.dev.F)
+            return fail(MBAVO_EINVAL, "n_frames %d differs from the level's %d", n_frames, L.dev.F);
+        if ((mem == MBAVO_MEM_HOST) != L.owns)
+            return fail(MBAVO_EINVAL, "mem must match the memory kind the level was set with");
+        DeviceGuard guard(ctx->device);
+        cudaStream_t s = ctx->stream;
+        if (cudaStreamQuery(s) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(s));
+        const size_t npix = (size_t)L.dev.H * L.dev.W;
+        for (int f = 0; f < n_frames; ++f)
+        {
+            if (!cur_I[f])
+                return fail(MBAVO_EINVAL, "null image");
+            if (L.owns)
+                CUDA_TRY(cudaMemcpyAsync(L.cur_I[f], cur_I[f], npix, cudaMemcpyHostToDevice, s));
+            else
+                L.dev.cur_I[f] = cur_I[f];
+        }
+        CUDA_TRY(cudaMemsetAsync(const_cast<unsigned char *>(L.dev.flags), 0, L.dev.P, s)); // tracker.cpp:600-601
+        L.num_bad = 0;
+        CUDA_TRY(cudaStreamSynchronize(s));
         return MBAVO_OK;
     }
 

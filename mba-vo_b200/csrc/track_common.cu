@@ -43,7 +43,69 @@ namespace mbavo
             pair[i00] = t;
         }
 
+        // ImagePyramid<T>::computePyramid, one level (src/core/measurements/ImagePyramid.h:76-95): T(0.25 * (float sum of the
+        // 2x2 block)) — the sum of four bytes is exact in float and 0.25 * it is exact in double, so the truncating cast is
+        // the integer (a + b + c + d) >> 2.
+        __global__ void pyr_down_kernel(const unsigned char *__restrict__ src, int Ws, unsigned char *__restrict__ dst, int Hd,
+                                        int Wd)
+        {
+            const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+            if (x >= Wd)
+                return;
+            const unsigned char *p = src + (size_t)2 * y * Ws + 2 * x;
+            dst[(size_t)y * Wd + x] = (unsigned char)(((unsigned int)p[0] + p[1] + p[Ws] + p[Ws + 1]) >> 2);
+        }
+
+        // compute_image_gradients (src/core/image_proc/Gradient.h:17-75) fused with the texel packing: 0.5 * central
+        // differences (exact in fp32 and in fp16), zero on the 1-pixel border.  grad (float2, may be null) receives the
+        // reference layout for the direct-gather kernels.
+        __device__ __forceinline__ float2 central_gradient(const unsigned char *__restrict__ I, int H, int W, int x, int y)
+        {
+            if (x == 0 || y == 0 || x == W - 1 || y == H - 1)
+                return make_float2(0.f, 0.f);
+            const unsigned char *c = I + (size_t)y * W + x;
+            return make_float2(0.5f * ((float)c[1] - (float)c[-1]), 0.5f * ((float)c[W] - (float)c[-W]));
+        }
+        __global__ void pack_image_kernel(const unsigned char *__restrict__ I, int H, int W, uint4 *__restrict__ pair,
+                                          unsigned int *__restrict__ quad, float2 *__restrict__ grad)
+        {
+            const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+            if (x >= W)
+                return;
+            const int x1 = min(x + 1, W - 1), y1 = min(y + 1, H - 1);
+            const int i00 = y * W + x;
+            const unsigned int b00 = I[i00], b01 = I[y * W + x1], b10 = I[y1 * W + x], b11 = I[y1 * W + x1];
+            const float2 g0 = central_gradient(I, H, W, x, y), g1 = central_gradient(I, H, W, x1, y);
+            if (grad)
+                grad[i00] = g0;
+            if (pair)
+            {
+                quad[i00] = b00 | (b01 << 8) | (b10 << 16) | (b11 << 24);
+                uint4 t;
+                t.x = (unsigned int)__half_as_ushort(__float2half_rn(g0.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(g0.y)) << 16);
+                t.y = (unsigned int)__half_as_ushort(__float2half_rn(g1.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(g1.y)) << 16);
+                t.z = (unsigned int)__half_as_ushort(__float2half_rn((float)b00)) |
+                      ((unsigned int)__half_as_ushort(__float2half_rn((float)b01)) << 16);
+                t.w = 0u;
+                pair[i00] = t;
+            }
+        }
     } // namespace
+
+    cudaError_t launch_pyr_down_kernel(const unsigned char *src, int Ws, unsigned char *dst, int Hd, int Wd, cudaStream_t stream)
+    {
+        const dim3 block(128, 1, 1), grid((Wd + 127) / 128, Hd, 1);
+        pyr_down_kernel<<<grid, block, 0, stream>>>(src, Ws, dst, Hd, Wd);
+        return cudaGetLastError();
+    }
+
+    cudaError_t launch_pack_image_kernel(const unsigned char *I, int H, int W, uint4 *pair, unsigned int *quad, float *grad,
+                                         cudaStream_t stream)
+    {
+        const dim3 block(128, 1, 1), grid((W + 127) / 128, H, 1);
+        pack_image_kernel<<<grid, block, 0, stream>>>(I, H, W, pair, quad, reinterpret_cast<float2 *>(grad));
+        return cudaGetLastError();
+    }
 
     size_t track_kernel_smem_bytes(int K, int NK, bool with_j, int N, int S, int TP)
     {

@@ -164,6 +164,51 @@ def test_exposure_phase_split(pkg, api, O, orc, synth, monkeypatch, phases):
         assert abs(c2 - orc.evaluate(prob, 0, with_hessian=False)[0]) <= COST_TOL * c2
 
 
+def test_new_live_frame_keeps_the_keyframe(pkg, api, O, orc, synth):
+    """mbavo_set_live_images: only the blurred frame changes between frames (tracker.cpp:112-116)."""
+    prob = synth.make_config("tiny")
+    other = synth.make_config("tiny")
+    other.levels[0].cur_I = [np.ascontiguousarray(np.roll(c, 3, axis=1)) for c in prob.levels[0].cur_I]
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        first = gpu_eval(pkg, api, prob, ctx=ctx)
+        ctx.set_live_images(0, other.levels[0].cur_I)
+        check_parity(O, gpu_eval(pkg, api, other, ctx=ctx), orc.evaluate(other, 0))
+        ctx.set_live_images(0, prob.levels[0].cur_I)
+        again = gpu_eval(pkg, api, prob, ctx=ctx)
+    assert again[0] == first[0] and np.array_equal(again[1], first[1])
+
+
+@pytest.mark.parametrize("no_texels", [False, True])
+def test_device_built_pyramid(pkg, api, O, orc, synth, monkeypatch, no_texels):
+    """mbavo_set_keyframe_pyramid / set_live_pyramid / set_level_points: 2x2-box pyramid (ImagePyramid.h:59-99), central
+    gradients (Gradient.h:17-75) and texels built on the GPU from the level-0 images give, on EVERY level, bit-identical
+    results to the levels built on the CPU by the restatement of the same loops (synth.pyramid_down / image_gradient,
+    pinned to the oracle's C restatement in tests/test_oracle.py)."""
+    if no_texels:
+        monkeypatch.setenv("MBAVO_NO_TEXELS", "1")
+    prob = synth.make_problem("pyr", W=322, H=246, levels=4, P0=1500, N=8, n_knots=2, k=2, seed=5, margin=24)  # odd sizes on the way down
+    with pkg.Context(api.limits_for(prob)) as a, pkg.Context(api.limits_for(prob)) as b:
+        api.upload_problem(a, prob)
+        api.upload_problem_pyramid(b, prob)
+        for level in range(len(prob.levels)):
+            assert b.level_uses_texels(level) == (0 if no_texels else 1)
+            ra, rb = gpu_eval(pkg, api, prob, level, ctx=a), gpu_eval(pkg, api, prob, level, ctx=b)
+            assert ra[0] == rb[0] and np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2]) and np.array_equal(ra[3], rb[3])
+            ca, cb = gpu_eval(pkg, api, prob, level, ctx=a, with_hessian=False), gpu_eval(pkg, api, prob, level, ctx=b, with_hessian=False)
+            assert ca[0] == cb[0]
+        check_parity(O, gpu_eval(pkg, api, prob, 3, ctx=b), orc.evaluate(prob, 3))
+        # a new live frame: only its level 0 is uploaded
+        other = [np.ascontiguousarray(np.roll(c, 2, axis=0)) for c in prob.levels[0].cur_I]
+        b.set_live_pyramid(len(prob.levels), other)
+        cur = other
+        for level, lv in enumerate(prob.levels):
+            if level > 0:
+                cur = [synth.pyramid_down(c) for c in cur]
+            lv.cur_I = [np.ascontiguousarray(c) for c in cur]
+        check_parity(O, gpu_eval(pkg, api, prob, 2, ctx=b), orc.evaluate(prob, 2))
+
+
 def test_multiple_frames(pkg, api, O, orc, synth):
     """n_frames > 1 with frames in different segments (the merge of overlapping frames, test_merge…:1060-1181)."""
     prob = synth.make_problem("frames", W=160, H=120, levels=1, P0=300, N=8, n_knots=3, k=2, seed=8, margin=14, F=2)
