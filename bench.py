@@ -157,18 +157,19 @@ def run_reference(args, pkg):
 # own arm
 # ----------------------------------------------------------------------------------------------------------------
 def gpu_step(ctx, prob, lib_ctx_eval, solve, plus):
-    """One GN iteration per pyramid level, coarse to fine.  Single GPU: the whole iteration is one C-ABI call
-    (mbavo_gn_iteration).  Point-sharded: the same sequence with the NCCL all-reduce between kernel and solve."""
+    """One GN iteration per pyramid level, coarse to fine.  Single GPU and fused sharding: the whole sweep is ONE C-ABI
+    call (mbavo_gn_sweep, collective when sharded).  NCCL form: the same sequence driven from here with the NCCL
+    all-reduce between kernel and solve."""
     kt, kR = prob.knots_t, prob.knots_R
+    if lib_ctx_eval is None:
+        costs, _, _ = ctx.gn_sweep(len(prob.levels) - 1, 0, prob.k, prob.t0, prob.dt, kt, kR, prob.huber_a, 1e4)
+        return costs[-1, 0], costs[-1, 1]
     out = None
     for level in reversed(range(len(prob.levels))):
-        if lib_ctx_eval is None:
-            c, c2, _, _, _ = ctx.gn_iteration(level, prob.k, prob.t0, prob.dt, kt, kR, prob.huber_a, 1e4)
-        else:
-            c, H, g = lib_ctx_eval(level, kt, kR, True)
-            step, model = solve(H, g, 1e4)
-            ct, cR = plus(kt, kR, step)
-            c2, _, _ = lib_ctx_eval(level, ct, cR, False)
+        c, H, g = lib_ctx_eval(level, kt, kR, True)
+        step, model = solve(H, g, 1e4)
+        ct, cR = plus(kt, kR, step)
+        c2, _, _ = lib_ctx_eval(level, ct, cR, False)
         out = (c, c2)
     return out
 

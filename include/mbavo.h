@@ -236,6 +236,14 @@ int mbavo_gn_iteration(mbavo_ctx *ctx, int level, int spline_deg_k, double start
                        int solver_type, double *cost, double *candidate_cost, double *step_out, double *cand_t,
                        double *cand_R);
 
+/* One GN iteration (mbavo_gn_iteration) on every level from level_coarse down to level_fine — the coarse-to-fine loop of
+ * optimizeTrajectory (blur_aware_direct_tracker.cpp:571-575) with a single iteration per level.  chain != 0: a level whose
+ * candidate lowered the cost hands the candidate knots to the next finer level (knots_t / knots_R are updated in place);
+ * chain == 0: every level starts from the given knots.  costs (may be NULL): (cost, candidate cost) per level, coarse first. */
+int mbavo_gn_sweep(mbavo_ctx *ctx, int level_coarse, int level_fine, int chain, int spline_deg_k, double start_time,
+                   double sample_dt, int num_ctrl_knots, double *knots_t, double *knots_R, double radius, double huber_a,
+                   int solver_type, double *costs);
+
 typedef struct mbavo_lm_options
 {
     int max_num_iterations;                 /* 50   blur_aware_direct_tracker.h:39 */

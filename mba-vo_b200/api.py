@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "mbavo_set_level", "mbavo_set_keyframe_pyramid", "mbavo_set_live_pyramid", "mbavo_set_level_points",
     "mbavo_set_live_images", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
-    "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
+    "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
     "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
     "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points",
 ]
@@ -295,6 +295,18 @@ class Context:
                                                 _dp(kt), _dp(kR), C.c_double(radius), C.c_double(huber_a), C.c_int(solver_type),
                                                 C.byref(cost), C.byref(cand), _dp(step), _dp(ct), _dp(cR)))
         return cost.value, cand.value, step, ct, cR
+
+    def gn_sweep(self, level_coarse: int, level_fine: int, k: int, t0: float, dt: float, knots_t, knots_R, huber_a: float,
+                 radius: float = 1e4, chain: bool = False, solver_type: int = SOLVER_SVD_JACOBI):
+        """mbavo_gn_sweep -> (costs [(cost, candidate cost) per level, coarse first], knots_t, knots_R)."""
+        kt = np.array(knots_t, dtype=np.float64, order="C")
+        kR = np.array(knots_R, dtype=np.float64, order="C")
+        n = kt.shape[0]
+        costs = np.zeros((level_coarse - level_fine + 1, 2))
+        self._check(self.lib.mbavo_gn_sweep(self._h, C.c_int(level_coarse), C.c_int(level_fine), C.c_int(1 if chain else 0), C.c_int(k),
+                                            C.c_double(t0), C.c_double(dt), C.c_int(n), _dp(kt), _dp(kR), C.c_double(radius),
+                                            C.c_double(huber_a), C.c_int(solver_type), _dp(costs)))
+        return costs, kt, kR
 
     def optimize_level(self, level: int, k: int, t0: float, dt: float, knots_t, knots_R, huber_a: float = 10.0,
                        max_chi_square_error: float = 3.0, solver_type: int = SOLVER_SVD_JACOBI, **overrides):

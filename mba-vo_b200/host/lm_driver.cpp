@@ -331,6 +331,30 @@ extern "C"
         return MBAVO_OK;
     }
 
+    int mbavo_gn_sweep(mbavo_ctx *ctx, int level_coarse, int level_fine, int chain, int k, double t0, double dt, int n,
+                       double *knots_t, double *knots_R, double radius, double huber_a, int solver_type, double *costs)
+    {
+        if (!ctx || !knots_t || !knots_R || level_coarse < level_fine || level_fine < 0 || level_coarse >= MBAVO_MAX_LEVELS ||
+            n < 2 || n > 16)
+            return MBAVO_EINVAL;
+        double ct[3 * 16], cR[4 * 16];
+        for (int level = level_coarse; level >= level_fine; --level) // optimizeTrajectory, tracker.cpp:571-575
+        {
+            double c = 0, cc = 0;
+            int rc = mbavo_gn_iteration(ctx, level, k, t0, dt, n, knots_t, knots_R, radius, huber_a, solver_type, &c, &cc, nullptr, ct, cR);
+            if (rc != MBAVO_OK)
+                return rc;
+            if (costs)
+                costs[2 * (level_coarse - level)] = c, costs[2 * (level_coarse - level) + 1] = cc;
+            if (chain && cc < c) // the finer level starts from the candidate if it lowered the cost
+            {
+                std::memcpy(knots_t, ct, sizeof(double) * 3 * n);
+                std::memcpy(knots_R, cR, sizeof(double) * 4 * n);
+            }
+        }
+        return MBAVO_OK;
+    }
+
     int mbavo_optimize_level(mbavo_ctx *ctx, int level, int k, double t0, double dt, int n, double *knots_t, double *knots_R,
                              const mbavo_lm_options *opt, mbavo_lm_summary *sum)
     {
