@@ -1,0 +1,75 @@
+"""Target for compute-sanitizer (memcheck / racecheck / initcheck / synccheck): every kernel of the library on small inputs —
+pack, pyramid, pose, tracking (Hessian + cost, texel and direct-gather variants, ragged shapes, borders, k = 4, multi-segment),
+outlier statistics, and a two-rank sharded evaluation on one device.   usage: python scripts/sanitize_target.py"""
+import os
+import sys
+import threading
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+pkg = ge.load_package()
+from mbavo_b200 import api  # noqa: E402
+from mbavo_b200.parallel import shard_bounds  # noqa: E402
+
+synth = pkg.synth
+
+
+def run(prob, pyramid=False):
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        (api.upload_problem_pyramid if pyramid else api.upload_problem)(ctx, prob)
+        for level in range(len(prob.levels)):
+            a = (level, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a)
+            c, H, g = ctx.evaluate(*a, True)
+            c2, _, _ = ctx.evaluate(*a, False)
+            ctx.detect_outliers(level, 3.0)
+            ctx.evaluate(*a, True)
+        print(prob.name, "ok", c, c2, flush=True)
+
+
+probs = [synth.make_config("tiny"),
+         synth.make_problem("ragged", W=192, H=144, levels=1, P0=77, N=5, n_knots=2, k=2, seed=3, margin=14,
+                            pattern=np.array([[0, 0], [1, 2], [-3, 1], [2, -2], [0, 3]], dtype=np.int32)),
+         synth.make_problem("border", W=160, H=120, levels=1, P0=600, N=8, n_knots=2, k=2, seed=77, margin=0, motion_scale=2.0),
+         synth.make_problem("cubic", W=160, H=120, levels=1, P0=200, N=8, n_knots=7, k=4, seed=9, margin=16, motion_scale=2.0),
+         synth.make_problem("multi", W=160, H=120, levels=2, P0=300, N=16, n_knots=5, k=2, seed=11, margin=16)]
+for p in probs:
+    run(p)
+run(synth.make_problem("pyr", W=162, H=122, levels=3, P0=300, N=4, n_knots=2, k=2, seed=5, margin=20), pyramid=True)
+os.environ["MBAVO_NO_TEXELS"] = "1"
+run(probs[0])
+del os.environ["MBAVO_NO_TEXELS"]
+os.environ["MBAVO_PHASES"] = "4"
+run(probs[0])
+del os.environ["MBAVO_PHASES"]
+
+# two ranks on one device
+prob = probs[0]
+ctxs = [pkg.Context(api.limits_for(prob)) for _ in range(2)]
+ptrs = []
+for r, ctx in enumerate(ctxs):
+    ctx.set_frame_times(prob.cap, prob.exp)
+    lo, hi = shard_bounds(prob.levels[0].P, r, 2)
+    ctx.set_level(0, prob.levels[0], slice(lo, hi))
+    ptrs.append(ctx.shard_export()[1])
+for r, ctx in enumerate(ctxs):
+    ctx.shard_connect(2, r, mailbox_ptrs=ptrs)
+    ctx.shard_set_global_points(0, prob.levels[0].P)
+res = [None, None]
+
+
+def body(i):
+    a = (0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a)
+    res[i] = ctxs[i].evaluate(*a, True)[0]
+    ctxs[i].detect_outliers(0, 3.0)
+
+
+th = [threading.Thread(target=body, args=(i,)) for i in range(2)]
+[t.start() for t in th]
+[t.join() for t in th]
+print("sharded ok", res, flush=True)
+for c in ctxs:
+    c.close()
