@@ -98,6 +98,7 @@ struct mbavo_ctx
     LevelStore levels[MBAVO_MAX_LEVELS];
 
     EvalStage stage{};       // spline state of the evaluation being issued (launch parameter of the pose kernel)
+    unsigned long long *phase_times_dev = nullptr; // development (mbavo_debug_phase_times)
     bool use_pdl = true;     // MBAVO_NO_PDL=1: tracking kernel fully serialised behind the pose kernel
 
     // point sharding (mbavo_shard_*): this rank's mailbox, the mapped mailboxes of all ranks, exchange counters
@@ -113,7 +114,9 @@ struct mbavo_ctx
     size_t block_partials_cap = 0;
     unsigned int *counter = nullptr;
     double *packed_dev = nullptr;                          // E_max doubles, device
-    double *result_host = nullptr, *result_map = nullptr;  // E_max doubles + sequence word: mapped pinned memory (host / device view)
+    double *result_host = nullptr, *result_map = nullptr;  // E_max (value, sequence) pairs: mapped pinned memory (host / device view)
+    std::vector<double> result_vals;                       // the values of the last blocking evaluation, compacted
+    int result_len = 0;
     unsigned long long seq = 0;
     int *outlier_result_dev = nullptr, *outlier_result_host = nullptr;
 
@@ -400,6 +403,7 @@ namespace
         prm.block_partials = ctx->block_partials;
         prm.counter = ctx->counter;
         prm.packed_out = packed_dev_out;
+        prm.phase_times = ctx->phase_times_dev;
         if (ctx->shard.world > 1)
         {
             prm.shard = ctx->shard;
@@ -407,9 +411,9 @@ namespace
         }
         if (blocking)
         {
-            prm.host_out = ctx->result_map;
-            prm.host_seq = reinterpret_cast<volatile unsigned long long *>(ctx->result_map + packed_len(MBAVO_MAX_KNOT_WINDOW));
+            prm.host_out = reinterpret_cast<double2 *>(ctx->result_map);
             prm.seq = ++ctx->seq;
+            ctx->result_len = pl.E;
         }
         if (ctx->timing)
             CUDA_TRY(cudaEventRecord(ctx->ev0, s));
@@ -420,30 +424,36 @@ namespace
         return MBAVO_OK;
     }
 
-    // Spin until the tracking kernel has published sequence number ctx->seq (a few microseconds after its last block
-    // finishes); the stream is polled now and then so that a failed launch cannot hang the caller.
+    // Spin until every (value, sequence) pair of the result shows sequence number ctx->seq (a microsecond after the
+    // tracking kernel's last block stores them), then compact the values into ctx->result_vals.  The stream is polled now
+    // and then so that a failed launch cannot hang the caller.
     int wait_result(mbavo_ctx *ctx)
     {
-        volatile unsigned long long *seq =
-            reinterpret_cast<volatile unsigned long long *>(ctx->result_host + packed_len(MBAVO_MAX_KNOT_WINDOW));
-        for (unsigned long long spins = 1;; ++spins)
+        const volatile unsigned long long *pairs = reinterpret_cast<const volatile unsigned long long *>(ctx->result_host);
+        const int E = ctx->result_len;
+        int done = 0; // elements [0, done) have been seen with the right sequence number
+        for (unsigned long long spins = 1; done < E; ++spins)
         {
-            if (*seq == ctx->seq)
-                break;
-            if ((spins & 0xfff) == 0)
+            while (done < E && pairs[2 * done + 1] == ctx->seq)
+                ++done;
+            if (done < E && (spins & 0xfff) == 0)
             {
                 cudaError_t e = cudaStreamQuery(ctx->stream);
+                if (e != cudaSuccess && e != cudaErrorNotReady)
+                    return fail(MBAVO_ECUDA, "evaluation failed: %s", cudaGetErrorString(e));
                 if (e == cudaSuccess)
                 {
-                    if (*seq == ctx->seq)
-                        break;
-                    return fail(MBAVO_ECUDA, "tracking kernel finished without publishing its result");
+                    bool all = true;
+                    for (int i = done; i < E; ++i)
+                        all = all && pairs[2 * i + 1] == ctx->seq;
+                    if (!all)
+                        return fail(MBAVO_ECUDA, "tracking kernel finished without publishing its result");
                 }
-                if (e != cudaErrorNotReady)
-                    return fail(MBAVO_ECUDA, "evaluation failed: %s", cudaGetErrorString(e));
             }
         }
         std::atomic_thread_fence(std::memory_order_acquire);
+        for (int i = 0; i < E; ++i)
+            ctx->result_vals[i] = ctx->result_host[2 * i];
         return MBAVO_OK;
     }
 } // namespace
@@ -491,8 +501,9 @@ extern "C"
         CUDA_TRY(cudaMemset(ctx->counter, 0, sizeof(unsigned int)));
         const int emax = packed_len(MBAVO_MAX_KNOT_WINDOW);
         CUDA_TRY(cudaMalloc(&ctx->packed_dev, sizeof(double) * emax));
-        CUDA_TRY(cudaHostAlloc(&ctx->result_host, sizeof(double) * (emax + 1), cudaHostAllocMapped));
-        std::memset(ctx->result_host, 0, sizeof(double) * (emax + 1));
+        CUDA_TRY(cudaHostAlloc(&ctx->result_host, sizeof(double) * 2 * emax, cudaHostAllocMapped));
+        std::memset(ctx->result_host, 0, sizeof(double) * 2 * emax);
+        ctx->result_vals.assign(emax, 0.0);
         CUDA_TRY(cudaHostGetDevicePointer(&ctx->result_map, ctx->result_host, 0));
         CUDA_TRY(cudaMalloc(&ctx->outlier_result_dev, sizeof(int) * 4));
         CUDA_TRY(cudaMallocHost(&ctx->outlier_result_host, sizeof(int) * 4));
@@ -542,6 +553,7 @@ extern "C"
         cudaFreeHost(ctx->inexact_host);
         mbavo_shard_disconnect(ctx);
         cudaFree(ctx->mailbox);
+        cudaFree(ctx->phase_times_dev);
         cudaFree(ctx->samples);
         cudaFree(ctx->mid);
         cudaFree(ctx->seg_end);
@@ -1029,14 +1041,14 @@ extern "C"
         rc = wait_result(ctx);
         if (rc != MBAVO_OK)
             return rc;
-        if (ctx->shard.world > 1 && ctx->result_host[0] != ctx->result_host[0])
+        if (ctx->shard.world > 1 && ctx->result_vals[0] != ctx->result_vals[0])
             return fail(MBAVO_ENCCL, "sharded evaluation: a peer rank did not arrive within 4 s");
         if (ctx->timing)
         {
             CUDA_TRY(cudaEventSynchronize(ctx->ev1));
             cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1);
         }
-        return mbavo_unpack(ctx->result_host, pl.kmin, pl.NK, sp->num_ctrl_knots, total_cost, H, g);
+        return mbavo_unpack(ctx->result_vals.data(), pl.kmin, pl.NK, sp->num_ctrl_knots, total_cost, H, g);
     }
 
     int mbavo_evaluate_async(mbavo_ctx *ctx, int level, const mbavo_spline *sp, double huber_a, int with_hessian,
@@ -1205,6 +1217,23 @@ extern "C"
         if (!ctx || level < 0 || level >= MBAVO_MAX_LEVELS || num_keypoints_global < 1)
             return fail(MBAVO_EINVAL, "bad level / point count");
         ctx->points_global[level] = num_keypoints_global;
+        return MBAVO_OK;
+    }
+
+    // Development aid (not declared in mbavo.h): globaltimer stamps of the tracking kernel's phases of the last launch;
+    // only MBAVO_PROFILE_PHASES builds of the kernel write them.  out: 16 values (ns).
+    int mbavo_debug_phase_times(mbavo_ctx *ctx, unsigned long long *out)
+    {
+        if (!ctx || !out)
+            return MBAVO_EINVAL;
+        DeviceGuard guard(ctx->device);
+        if (!ctx->phase_times_dev)
+        {
+            CUDA_TRY(cudaMalloc(&ctx->phase_times_dev, 16 * sizeof(unsigned long long)));
+            CUDA_TRY(cudaMemset(ctx->phase_times_dev, 0, 16 * sizeof(unsigned long long)));
+        }
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpy(out, ctx->phase_times_dev, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         return MBAVO_OK;
     }
 

@@ -180,12 +180,14 @@ namespace mbavo
         double *block_partials;   // [gridDim.x * gridDim.y * E]
         unsigned int *counter;    // last-block-done ticket
         double *packed_out;       // [E] device memory
-        // Blocking evaluations: the last block also stores the packed vector straight into mapped pinned host memory and
-        // then publishes `seq` there; the host spins on it instead of waiting for a D2H copy + stream synchronisation.
-        double *host_out;                     // [E] mapped pinned host memory, or nullptr
-        volatile unsigned long long *host_seq;
+        // Blocking evaluations: the last block also stores the packed vector straight into mapped pinned host memory, every
+        // element as ONE 16-byte store of (value, sequence number).  A 16-byte aligned store reaches host memory as a
+        // whole, so each element validates itself: the host spins until all E sequence fields show `seq` — no system-scope
+        // fence, no separate flag, no D2H copy, no stream synchronisation.
+        double2 *host_out;                    // [E] (value, seq as bits) in mapped pinned host memory, or nullptr
         unsigned long long seq;
         ShardParams shard;                    // point sharding: the vector published is the sum over all ranks
+        unsigned long long *phase_times;      // development: globaltimer stamps of kernel phases (MBAVO_PROFILE_PHASES builds)
     };
 
     __host__ __device__ constexpr int packed_len(int NK) { return (6 * NK + 1) * (6 * NK + 2) / 2; }

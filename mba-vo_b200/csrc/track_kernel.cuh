@@ -50,6 +50,20 @@ namespace mbavo
     namespace
     {
         constexpr int kSampleUnroll = MBAVO_UNROLL;
+
+#ifdef MBAVO_PROFILE_PHASES
+#define MBAVO_STAMP(slot)                                                                          \
+    do                                                                                             \
+    {                                                                                              \
+        if (prm.phase_times && threadIdx.x == 0 && (blockIdx.x == 0 || (slot) >= 8))               \
+            prm.phase_times[slot] = global_timer_ns();                                             \
+    } while (0)
+#else
+#define MBAVO_STAMP(slot) \
+    do                    \
+    {                     \
+    } while (0)
+#endif
         __device__ __forceinline__ float u8_to_float(unsigned int b)
         {
             // exact for 0..255: place the byte in the mantissa of 2^23 and subtract 2^23 (full-rate LOP3 + FADD
@@ -350,6 +364,7 @@ namespace mbavo
             constexpr int NJ = WITH_J ? NK : 1;
             constexpr int D1 = G::D1, PITCH = G::PITCH, NT = G::NT, MT = G::MT, E = G::E;
 
+            MBAVO_STAMP(0);
             const LevelDev &lv = prm.lv;
             const int f = blockIdx.y;
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -386,7 +401,9 @@ namespace mbavo
             }
             // everything above is independent of the pose kernel; what follows reads its output (programmatic dependent
             // launch: this grid may have started before the pose kernel finished)
+            MBAVO_STAMP(1);
             cudaGridDependencySynchronize();
+            MBAVO_STAMP(2);
             for (int e = threadIdx.x; e < N * REC; e += blockDim.x)
                 samples_s[e] = prm.samples[(size_t)f * N * REC + e];
             if (threadIdx.x < kMaxSegments)
@@ -395,6 +412,7 @@ namespace mbavo
                 mid_s[threadIdx.x] = prm.mid[f * kMidDoubles + threadIdx.x];
             __syncthreads();
 
+            MBAVO_STAMP(3);
             const double *mid = mid_s;
             const float2 fxy = f2((float)lv.fx, (float)lv.fy);
             const float inv_N = 1.0f / (float)N;
@@ -426,6 +444,7 @@ namespace mbavo
                         my_pix[lane] = setup_pixel(lv, mid, f, in_batch ? p0 + it / S : lv.P, in_batch ? it % S : 0, pattern_s);
                     }
                     __syncwarp();
+                    MBAVO_STAMP(4);
                     // ---- B: exposure samples, PH phases per pixel ---------------------------------------------------
                     const int chunk = min(32, items - base);
                     for (int sub = 0; sub < chunk; sub += Q)
@@ -507,6 +526,7 @@ namespace mbavo
                             }
                         }
                     }
+                    MBAVO_STAMP(5);
                     if constexpr (WITH_J)
                     {
                         // rows of a short last chunk: zero
@@ -556,6 +576,7 @@ namespace mbavo
                 __syncwarp();
             }
 
+            MBAVO_STAMP(6);
             // ---- epilogue: warp -> block -> grid, all in fixed order (deterministic) --------------------------------
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
@@ -606,6 +627,7 @@ namespace mbavo
                     s += red_s[w * E + e];
                 prm.block_partials[(size_t)block_linear * E + e] = s;
             }
+            MBAVO_STAMP(7);
             __threadfence();
             __shared__ unsigned int ticket_s;
             __syncthreads();
@@ -614,42 +636,52 @@ namespace mbavo
             __syncthreads();
             if (ticket_s != (unsigned int)(num_blocks - 1))
                 return;
-            // last block: sum the partials of all blocks in a fixed order — PARTS contiguous block ranges per element summed
-            // by different threads (8 loads in flight each), then combined in range order
+            MBAVO_STAMP(8);
+            // last block: sum the partials of all blocks in a fixed order.  GRP adjacent lanes share one element: lane `part`
+            // sums the blocks b = part, part + GRP, ... (32 loads in flight), the GRP partial sums are combined by a fixed
+            // xor-shuffle tree.  Deterministic: the order depends only on the grid size.
             __threadfence();
-            constexpr int PARTS = E >= kThreads ? 1 : kThreads / E;
-            for (int idx = threadIdx.x; idx < E * PARTS; idx += blockDim.x)
+            constexpr int GRP = E >= kThreads ? 1 : (kThreads / E >= 32 ? 32 : (kThreads / E >= 16 ? 16 : (kThreads / E >= 8 ? 8 : (kThreads / E >= 4 ? 4 : (kThreads / E >= 2 ? 2 : 1)))));
+            double *fin_s = red_s; // this rank's vector, scaled by 1 / num_residuals (global when sharded)
+            for (int e0 = 0; e0 < E; e0 += kThreads / GRP)
             {
-                const int e = idx % E, part = idx / E;
-                const int b0 = (int)((long long)num_blocks * part / PARTS), b1 = (int)((long long)num_blocks * (part + 1) / PARTS);
-                const double *src = prm.block_partials + e;
+                const int e = e0 + threadIdx.x / GRP, part = threadIdx.x % GRP;
                 double s = 0.0;
-                int b = b0;
-                for (; b + 8 <= b1; b += 8)
+                if (e < E)
                 {
-                    double v[8];
+                    const double *src = prm.block_partials + e;
+                    int b = part;
+                    for (; b + 31 * GRP < num_blocks; b += 32 * GRP)
+                    {
+                        double v[32];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        v[u] = __ldcg(src + (size_t)(b + u) * E);
+                        for (int u = 0; u < 32; ++u)
+                            v[u] = __ldcg(src + (size_t)(b + u * GRP) * E);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        s += v[u];
+                        for (int u = 0; u < 32; ++u)
+                            s += v[u];
+                    }
+                    for (; b + 7 * GRP < num_blocks; b += 8 * GRP)
+                    {
+                        double v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            v[u] = __ldcg(src + (size_t)(b + u * GRP) * E);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            s += v[u];
+                    }
+                    for (; b < num_blocks; b += GRP)
+                        s += __ldcg(src + (size_t)b * E);
                 }
-                for (; b < b1; ++b)
-                    s += __ldcg(src + (size_t)b * E);
-                red_s[idx] = s;
-            }
-            __syncthreads();
-            double *fin_s = red_s + E * PARTS; // this rank's vector, scaled by 1 / num_residuals (global when sharded)
-            for (int e = threadIdx.x; e < E; e += blockDim.x)
-            {
-                double s = 0.0;
 #pragma unroll
-                for (int part = 0; part < PARTS; ++part)
-                    s += red_s[part * E + e];
-                fin_s[e] = s * inv_num_residuals;
+                for (int o = 1; o < GRP; o <<= 1)
+                    s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (e < E && part == 0)
+                    fin_s[e] = s * inv_num_residuals;
             }
             __syncthreads();
+            MBAVO_STAMP(9);
             __shared__ int shard_ok_s;
             const ShardParams &sh = prm.shard;
             if (sh.world > 1)
@@ -689,19 +721,11 @@ namespace mbavo
                 const double s = fin_s[e];
                 prm.packed_out[e] = s;
                 if (prm.host_out)
-                    prm.host_out[e] = s;
+                    prm.host_out[e] = make_double2(s, __longlong_as_double((long long)prm.seq)); // one 16-byte store
             }
-            if (prm.host_out)
-            {
-                __threadfence_system(); // the vector is visible to the host before the sequence number is
-                __syncthreads();
-            }
+            MBAVO_STAMP(10);
             if (threadIdx.x == 0)
-            {
                 *prm.counter = 0u; // re-arm for the next launch
-                if (prm.host_out)
-                    *prm.host_seq = prm.seq;
-            }
         }
 
         template <int K, int NK, bool WITH_J, bool PACKED>

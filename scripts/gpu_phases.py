@@ -1,0 +1,31 @@
+"""Development probe: globaltimer stamps of the tracking kernel's phases (needs the MBAVO_PROFILE_PHASES build of the library,
+selected with MBAVO_LIBRARY).  usage: MBAVO_LIBRARY=.../libmbavo_phases.so python scripts/gpu_phases.py C1:0 C2:3 C2:0"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+pkg = ge.load_package()
+from mbavo_b200.api import limits_for, upload_problem  # noqa: E402
+
+NAMES = ["entry", "before griddep", "after griddep", "prologue done", "phase A done (first chunk)", "phase B done (first chunk)",
+         "batches done", "block partials stored", "last block: ticket won", "last block: partials summed", "last block: published"]
+for tgt in sys.argv[1:] or ["C1:0", "C2:3", "C2:0"]:
+    name, level = tgt.split(":")
+    level = int(level)
+    prob = pkg.synth.make_config(name, levels=level + 1)
+    with pkg.Context(limits_for(prob)) as ctx:
+        upload_problem(ctx, prob)
+        buf = (C.c_ulonglong * 16)()
+        ctx.lib.mbavo_debug_phase_times(ctx._h, buf)  # allocates the stamp buffer
+        for with_h in (True, False):
+            for _ in range(3):
+                ctx.evaluate(level, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, with_h)
+            ctx.lib.mbavo_debug_phase_times(ctx._h, buf)
+            t = np.array(list(buf)[:11], dtype=np.float64)
+            print(f"{tgt} {'H' if with_h else 'C'}: " + ", ".join(f"{n} +{(t[i] - t[0]) / 1e3:.1f}us" for i, n in enumerate(NAMES) if i > 0))
