@@ -19,9 +19,9 @@ namespace mbavo
 {
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
                                    double *mid, int *seg_end, cudaStream_t stream);
-    cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
-                                    int *query_occupancy, bool dependent);
-    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, int N, int S, int TP);
+    cudaError_t launch_track_kernel(int K, int NK, bool with_j, bool big, const TrackParams &prm, dim3 grid, size_t smem,
+                                    cudaStream_t stream, int *query_occupancy, bool dependent);
+    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool big, int N, int S, int TP);
     cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,
                                    int *inexact, cudaStream_t stream);
     cudaError_t launch_pyr_down_kernel(const unsigned char *src, int Ws, unsigned char *dst, int Hd, int Wd, cudaStream_t stream);
@@ -99,6 +99,7 @@ struct mbavo_ctx
 
     EvalStage stage{};       // spline state of the evaluation being issued (launch parameter of the pose kernel)
     unsigned long long *phase_times_dev = nullptr; // development (mbavo_debug_phase_times)
+    long long big_block_batches = 2000; // MBAVO_BIG_BLOCK_BATCHES: Hessian pass uses the big block shape from this many batches
     bool use_pdl = true;     // MBAVO_NO_PDL=1: tracking kernel fully serialised behind the pose kernel
 
     // point sharding (mbavo_shard_*): this rank's mailbox, the mapped mailboxes of all ranks, exchange counters
@@ -279,6 +280,7 @@ namespace
     {
         int K, NK, kmin, N, F, P, S, TP, PH, batches_per_frame;
         bool with_h;
+        bool big; // Hessian pass: one block of 20 (16) warps per SM instead of two of 8
         dim3 grid;
         size_t smem;
         int E;
@@ -336,25 +338,33 @@ namespace
             while (pl.PH > pl.N)
                 pl.PH >>= 1;
         }
-        pl.smem = track_kernel_smem_bytes(pl.K, pl.NK, with_h, pl.N, pl.S, pl.TP);
+        // block shape of the Hessian pass: big blocks once the batches occupy most SMs (measured cross-over ~2000 batches)
+        pl.big = with_h && (long long)pl.batches_per_frame * pl.F >= ctx->big_block_batches;
+        pl.smem = track_kernel_smem_bytes(pl.K, pl.NK, with_h, pl.big, pl.N, pl.S, pl.TP);
+        if (pl.big && pl.smem > 200 * 1024)
+        {
+            pl.big = false;
+            pl.smem = track_kernel_smem_bytes(pl.K, pl.NK, with_h, false, pl.N, pl.S, pl.TP);
+        }
         if (pl.smem > 200 * 1024)
             return fail(MBAVO_ECAPACITY, "shared memory need %zu B exceeds 200 KiB (N=%d, S=%d, window=%d)", pl.smem, pl.N, pl.S,
                         pl.NK);
         int occ = 0;
         const int packed = L.dev.ref_pair != nullptr ? 1 : 0;
         for (const auto &c : ctx->occ_cache)
-            if (c.K == pl.K && c.NK == pl.NK && c.with_h == (with_h ? 1 : 0) && c.packed == packed && c.smem == pl.smem)
+            if (c.K == pl.K && c.NK == pl.NK && c.with_h == (with_h ? 1 : 0) && c.packed == packed + 2 * (pl.big ? 1 : 0) && c.smem == pl.smem)
                 occ = c.occ;
         if (occ == 0)
         {
             TrackParams query{};
             query.lv = L.dev; // selects the texel / direct-gather instantiation
-            cudaError_t e = launch_track_kernel(pl.K, pl.NK, with_h, query, dim3(), pl.smem, nullptr, &occ, false);
+            cudaError_t e = launch_track_kernel(pl.K, pl.NK, with_h, pl.big, query, dim3(), pl.smem, nullptr, &occ, false);
             if (e != cudaSuccess)
                 return fail(MBAVO_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e));
-            ctx->occ_cache.push_back({pl.K, pl.NK, with_h ? 1 : 0, packed, pl.smem, occ});
+            ctx->occ_cache.push_back({pl.K, pl.NK, with_h ? 1 : 0, packed + 2 * (pl.big ? 1 : 0), pl.smem, occ});
         }
-        int want = (pl.batches_per_frame + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        const int wpb = track_warps(with_h, pl.NK, pl.big);
+        int want = (pl.batches_per_frame + wpb - 1) / wpb;
         int cap_blocks = ctx->num_sms * occ / pl.F;
         if (cap_blocks < 1)
             cap_blocks = 1;
@@ -418,7 +428,7 @@ namespace
         if (ctx->timing)
             CUDA_TRY(cudaEventRecord(ctx->ev0, s));
         // event timing brackets the tracking kernel alone, so it is then launched fully serialised
-        CUDA_TRY(launch_track_kernel(pl.K, pl.NK, pl.with_h, prm, pl.grid, pl.smem, s, nullptr, ctx->use_pdl && !ctx->timing));
+        CUDA_TRY(launch_track_kernel(pl.K, pl.NK, pl.with_h, pl.big, prm, pl.grid, pl.smem, s, nullptr, ctx->use_pdl && !ctx->timing));
         if (ctx->timing)
             CUDA_TRY(cudaEventRecord(ctx->ev1, s));
         return MBAVO_OK;
@@ -513,6 +523,9 @@ extern "C"
         CUDA_TRY(cudaMallocHost(&ctx->inexact_host, sizeof(int)));
         const char *g = getenv("MBAVO_NO_PDL");
         ctx->use_pdl = !(g && g[0] == '1');
+        g = getenv("MBAVO_BIG_BLOCK_BATCHES");
+        if (g)
+            ctx->big_block_batches = atoll(g);
         g = getenv("MBAVO_NO_TEXELS");
         ctx->use_texels = !(g && g[0] == '1');
         g = getenv("MBAVO_PHASE_FAST");

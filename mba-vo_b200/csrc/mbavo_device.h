@@ -10,8 +10,12 @@ namespace mbavo
     constexpr int kMaxFrames = 16;
     constexpr int kMaxKnotWindow = 8;  // NK
     constexpr int kMaxSegments = 7;    // NK - k + 1 for k = 2
-    constexpr int kWarpsPerBlock = 8;
-    constexpr int kThreads = kWarpsPerBlock * 32;
+    // Warps per block of the tracking kernel.  The cost-only pass runs 4 blocks of 8 warps per SM.  The Hessian pass has
+    // two shapes: "big" = ONE block of 20 warps per SM at <= 96 registers (16 warps for knot windows >= 4, whose rows
+    // need more shared memory) — more resident warps and half as many per-block partials for the last-block reduction,
+    // best once there are enough batches to occupy the SMs — and "small" = two blocks of 8 warps per SM, which spreads
+    // the few batches of a coarse pyramid level over more SMs (profiles/r1_history.md).
+    __host__ __device__ constexpr int track_warps(bool with_j, int NK, bool big) { return (with_j && big) ? (NK <= 3 ? 20 : 16) : 8; }
 
     // One exposure sample (virtual pose) as the tracking kernel consumes it: fp32, 16-byte aligned records laid out so
     // that every operand PAIR of the kernel's packed FFMA2 arithmetic is an aligned pair of one 128-bit shared load.

@@ -5,14 +5,14 @@
 
 namespace mbavo
 {
-    cudaError_t track_dispatch_k2_lo(int NK, bool with_j, bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
-                                     int *query_occupancy, bool dependent);
-    cudaError_t track_dispatch_k2_hi(int NK, bool with_j, bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
-                                     int *query_occupancy, bool dependent);
-    cudaError_t track_dispatch_k4_lo(int NK, bool with_j, bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
-                                     int *query_occupancy, bool dependent);
-    cudaError_t track_dispatch_k4_hi(int NK, bool with_j, bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
-                                     int *query_occupancy, bool dependent);
+    cudaError_t track_dispatch_k2_lo(int NK, bool with_j, bool packed, bool big, const TrackParams &prm, dim3 grid, size_t smem,
+                                     cudaStream_t stream, int *query_occupancy, bool dependent);
+    cudaError_t track_dispatch_k2_hi(int NK, bool with_j, bool packed, bool big, const TrackParams &prm, dim3 grid, size_t smem,
+                                     cudaStream_t stream, int *query_occupancy, bool dependent);
+    cudaError_t track_dispatch_k4_lo(int NK, bool with_j, bool packed, bool big, const TrackParams &prm, dim3 grid, size_t smem,
+                                     cudaStream_t stream, int *query_occupancy, bool dependent);
+    cudaError_t track_dispatch_k4_hi(int NK, bool with_j, bool packed, bool big, const TrackParams &prm, dim3 grid, size_t smem,
+                                     cudaStream_t stream, int *query_occupancy, bool dependent);
 
     namespace
     {
@@ -107,13 +107,14 @@ namespace mbavo
         return cudaGetLastError();
     }
 
-    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, int N, int S, int TP)
+    size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool big, int N, int S, int TP)
     {
         const int REC = sample_rec_floats(K);
         const int D1 = with_j ? 6 * NK + 1 : 1, D1E = (D1 + 1) & ~1;
         const int PITCH = (D1E / 2) % 2 == 1 ? D1E : D1E + 2, T = D1E / 2, NT = T * (T + 1) / 2;
         const int E = with_j ? packed_len(NK) : 1;
         const int rho_per_warp = max(32, TP * S);
+        const int kWarpsPerBlock = track_warps(with_j, NK, big), kThreads = kWarpsPerBlock * 32;
         size_t main_bytes = (size_t)N * REC * 4 + 8 * 4 + kMidDoubles * 8 + (size_t)kWarpsPerBlock * 32 * 32 /* PixelRec */ +
                             (size_t)S * 8 +
                             (size_t)kWarpsPerBlock * rho_per_warp * 4 + (size_t)((NT + 7) & ~7) * 2 +
@@ -134,16 +135,16 @@ namespace mbavo
 
     // with_j: Hessian pass (templated on the window) or cost-only pass (one instantiation per K).  dependent: launch with
     // programmatic stream serialisation (the previous kernel in the stream is the pose kernel).
-    cudaError_t launch_track_kernel(int K, int NK, bool with_j, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
-                                    int *query_occupancy, bool dependent)
+    cudaError_t launch_track_kernel(int K, int NK, bool with_j, bool big, const TrackParams &prm, dim3 grid, size_t smem,
+                                    cudaStream_t stream, int *query_occupancy, bool dependent)
     {
         const bool packed = prm.lv.ref_pair != nullptr;
         if (K == 2)
-            return (!with_j || NK <= 3) ? track_dispatch_k2_lo(NK, with_j, packed, prm, grid, smem, stream, query_occupancy, dependent)
-                                        : track_dispatch_k2_hi(NK, with_j, packed, prm, grid, smem, stream, query_occupancy, dependent);
+            return (!with_j || NK <= 3) ? track_dispatch_k2_lo(NK, with_j, packed, big, prm, grid, smem, stream, query_occupancy, dependent)
+                                        : track_dispatch_k2_hi(NK, with_j, packed, big, prm, grid, smem, stream, query_occupancy, dependent);
         if (K == 4)
-            return (!with_j || NK <= 5) ? track_dispatch_k4_lo(NK, with_j, packed, prm, grid, smem, stream, query_occupancy, dependent)
-                                        : track_dispatch_k4_hi(NK, with_j, packed, prm, grid, smem, stream, query_occupancy, dependent);
+            return (!with_j || NK <= 5) ? track_dispatch_k4_lo(NK, with_j, packed, big, prm, grid, smem, stream, query_occupancy, dependent)
+                                        : track_dispatch_k4_hi(NK, with_j, packed, big, prm, grid, smem, stream, query_occupancy, dependent);
         return cudaErrorInvalidValue;
     }
 } // namespace mbavo

@@ -3,15 +3,15 @@
 
 namespace mbavo
 {
-    cudaError_t track_dispatch_k2_lo(int NK, bool with_j, bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
+    cudaError_t track_dispatch_k2_lo(int NK, bool with_j, bool packed, bool big, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
                                   int *query_occupancy, bool dependent)
     {
         if (!with_j)
-            return dispatch_variant<2, 2, false>(packed, prm, grid, smem, stream, query_occupancy, dependent);
+            return dispatch_variant<2, 2, false>(packed, big, prm, grid, smem, stream, query_occupancy, dependent);
         if (NK == 2)
-            return dispatch_variant<2, 2, true>(packed, prm, grid, smem, stream, query_occupancy, dependent);
+            return dispatch_variant<2, 2, true>(packed, big, prm, grid, smem, stream, query_occupancy, dependent);
         if (NK == 3)
-            return dispatch_variant<2, 3, true>(packed, prm, grid, smem, stream, query_occupancy, dependent);
+            return dispatch_variant<2, 3, true>(packed, big, prm, grid, smem, stream, query_occupancy, dependent);
         return cudaErrorInvalidValue;
     }
 } // namespace mbavo

@@ -33,9 +33,6 @@
 
 #include <cuda_fp16.h>
 
-#ifndef MBAVO_MINB_H
-#define MBAVO_MINB_H 2
-#endif
 // Hessian pass: branch-free sample step, sample loop unrolled by 2 (measured best: profiles/r1_history.md); the cost-only
 // pass keeps the early exit of an invalid sample.
 #ifndef MBAVO_BRANCHLESS
@@ -355,11 +352,12 @@ namespace mbavo
 
         // K: knots per segment, NK: knots in the window (NK - K + 1 segments touched), WITH_J: Hessian pass or cost only,
         // PACKED: keyframe texels available.
-        template <int K, int NK, bool WITH_J, bool PACKED>
-        __global__ void __launch_bounds__(kThreads, WITH_J ? (NK <= 3 ? MBAVO_MINB_H : 1) : 4)
+        template <int K, int NK, bool WITH_J, bool PACKED, bool BIG>
+        __global__ void __launch_bounds__(track_warps(WITH_J, NK, BIG) * 32, WITH_J ? ((!BIG && NK <= 3) ? 2 : 1) : 4)
             track_kernel(const __grid_constant__ TrackParams prm)
         {
             using G = RowGeom<NK, WITH_J>;
+            constexpr int kWarpsPerBlock = track_warps(WITH_J, NK, BIG), kThreads = kWarpsPerBlock * 32;
             constexpr int REC = sample_rec_floats(K);
             constexpr int NJ = WITH_J ? NK : 1;
             constexpr int D1 = G::D1, PITCH = G::PITCH, NT = G::NT, MT = G::MT, E = G::E;
@@ -728,7 +726,7 @@ namespace mbavo
                 *prm.counter = 0u; // re-arm for the next launch
         }
 
-        template <int K, int NK, bool WITH_J, bool PACKED>
+        template <int K, int NK, bool WITH_J, bool PACKED, bool BIG>
         cudaError_t launch_one(const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream, bool dependent)
         {
             static unsigned long long configured = 0; // per instantiation and per device (attribute of the device function)
@@ -736,7 +734,7 @@ namespace mbavo
             cudaGetDevice(&dev);
             if (!(configured >> dev & 1ull))
             {
-                cudaError_t e = cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                cudaError_t e = cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      200 * 1024);
                 if (e != cudaSuccess)
                     return e;
@@ -745,36 +743,49 @@ namespace mbavo
             // Programmatic dependent launch: the kernel may start while the pose kernel before it in the stream is still
             // running; it waits (griddepcontrol.wait) right before it reads what the pose kernel wrote.
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = grid, cfg.blockDim = dim3(kThreads, 1, 1), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+            cfg.gridDim = grid, cfg.blockDim = dim3(track_warps(WITH_J, NK, BIG) * 32, 1, 1), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr, cfg.numAttrs = dependent ? 1 : 0;
-            return cudaLaunchKernelEx(&cfg, track_kernel<K, NK, WITH_J, PACKED>, prm);
+            return cudaLaunchKernelEx(&cfg, track_kernel<K, NK, WITH_J, PACKED, BIG>, prm);
         }
 
         // Occupancy-derived grid width for one instantiation
-        template <int K, int NK, bool WITH_J, bool PACKED>
+        template <int K, int NK, bool WITH_J, bool PACKED, bool BIG>
         int blocks_per_sm(size_t smem)
         {
             int n = 0;
-            cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, track_kernel<K, NK, WITH_J, PACKED>, kThreads, smem);
+            cudaFuncSetAttribute(track_kernel<K, NK, WITH_J, PACKED, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, track_kernel<K, NK, WITH_J, PACKED, BIG>, track_warps(WITH_J, NK, BIG) * 32, smem);
             return n > 0 ? n : 1;
         }
 
-        // One (K, NK, WITH_J): texel / direct-gather variant
+        // One (K, NK, WITH_J): texel / direct-gather variant x block shape (the cost-only pass has one shape)
         template <int K, int NK, bool WITH_J>
-        cudaError_t dispatch_variant(bool packed, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
+        cudaError_t dispatch_variant(bool packed, bool big, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream,
                                      int *query_occupancy, bool dependent)
         {
-            if (query_occupancy)
+#define MBAVO_VARIANT(P_, B_)                                                             \
+    if (packed == P_ && big == B_)                                                        \
+    {                                                                                     \
+        if (query_occupancy)                                                              \
+        {                                                                                 \
+            *query_occupancy = blocks_per_sm<K, NK, WITH_J, P_, B_>(smem);                \
+            return cudaSuccess;                                                           \
+        }                                                                                 \
+        return launch_one<K, NK, WITH_J, P_, B_>(prm, grid, smem, stream, dependent);     \
+    }
+            if constexpr (WITH_J)
             {
-                *query_occupancy = packed ? blocks_per_sm<K, NK, WITH_J, true>(smem) : blocks_per_sm<K, NK, WITH_J, false>(smem);
-                return cudaSuccess;
+                MBAVO_VARIANT(true, true)
+                MBAVO_VARIANT(false, true)
             }
-            return packed ? launch_one<K, NK, WITH_J, true>(prm, grid, smem, stream, dependent)
-                          : launch_one<K, NK, WITH_J, false>(prm, grid, smem, stream, dependent);
+            big = false;
+            MBAVO_VARIANT(true, false)
+            MBAVO_VARIANT(false, false)
+#undef MBAVO_VARIANT
+            return cudaErrorInvalidValue;
         }
     } // namespace
 } // namespace mbavo
