@@ -277,6 +277,15 @@ int mbavo_optimize_level(mbavo_ctx *ctx, int level, int spline_deg_k, double sta
                          int num_ctrl_knots, double *knots_t, double *knots_R, const mbavo_lm_options *opt,
                          mbavo_lm_summary *summary);
 
+/* ---- synthetic blurred frame ---------------------------------------------------------------
+ * warp_image + synthesize_motion_blurred_img (src/ba_tracker/generate_synthetic_data.cpp:127-180): the mean over num_poses
+ * plane-induced warps of the keyframe (plane Z = plane_depth), each truncated to 8 bits, the mean rounded to nearest even.
+ * poses_tq: num_poses x 7 doubles (tx ty tz qx qy qz qw) — what SplineSE3::GetPose returns for every sample time (:166-169);
+ * at most 256 poses.  ref_I / out: H*W bytes, both host or both device (`mem`).  device < 0: the current device.
+ * Bit-exact with the reference arithmetic (the unit is compiled without FMA contraction). */
+int mbavo_synthesize_blurred(int device, int mem, const unsigned char *ref_I, int H, int W, double plane_depth, double fx,
+                             double fy, double cx, double cy, const double *poses_tq, int num_poses, unsigned char *out);
+
 /* ---- introspection for benchmarks ---------------------------------------------------------------------------- */
 
 /* Number of kernels this library has launched on behalf of ctx since creation */

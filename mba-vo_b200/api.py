@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
     "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
-    "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points",
+    "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points", "mbavo_synthesize_blurred",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -362,6 +362,22 @@ class Context:
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.mbavo_last_kernel_ms(self._h))
+
+
+def synthesize_blurred(ref_I: np.ndarray, plane_depth: float, fx: float, fy: float, cx: float, cy: float,
+                       poses_tq: np.ndarray, device: int = -1) -> np.ndarray:
+    """mbavo_synthesize_blurred with host images: poses_tq is (N, 7) = tx ty tz qx qy qz qw per exposure sample."""
+    lib = load_library()
+    ref_I = np.ascontiguousarray(ref_I, dtype=np.uint8)
+    poses = np.ascontiguousarray(poses_tq, dtype=np.float64).reshape(-1, 7)
+    H, W = ref_I.shape
+    out = np.zeros((H, W), dtype=np.uint8)
+    rc = lib.mbavo_synthesize_blurred(C.c_int(device), C.c_int(MEM_HOST), C.c_void_p(ref_I.ctypes.data), C.c_int(H), C.c_int(W),
+                                      C.c_double(plane_depth), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy),
+                                      _dp(poses), C.c_int(poses.shape[0]), C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise MbavoError(f"mbavo_synthesize_blurred failed: {rc}")
+    return out
 
 
 def limits_for(prob, n_frames: Optional[int] = None) -> Limits:

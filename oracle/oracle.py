@@ -198,6 +198,20 @@ class OracleLib(_Lib):
         self.fn("pyramid_down")(_ptr(np.ascontiguousarray(I), _u8p), C.c_int(H), C.c_int(W), _ptr(out, _u8p))
         return out
 
+    def warp_mean(self, I, D, fx, fy, cx, cy, poses_tq):
+        """Mean of the plane-induced warps of I through the given poses ((n, 7): tx ty tz qx qy qz qw), oracle port only."""
+        I = np.ascontiguousarray(I, dtype=np.uint8)
+        poses = np.ascontiguousarray(poses_tq, dtype=np.float64).reshape(-1, 7)
+        H, W = I.shape
+        out = np.zeros((H, W), dtype=np.uint8)
+        f = self.fn("warp_mean")
+        f.restype = C.c_int
+        rc = f(_ptr(I, _u8p), C.c_int(H), C.c_int(W), C.c_double(D), C.c_double(fx), C.c_double(fy), C.c_double(cx),
+               C.c_double(cy), _ptr(poses, _dp), C.c_int(poses.shape[0]), _ptr(out, _u8p))
+        if rc != 0:
+            raise RuntimeError(f"warp_mean rc={rc}")
+        return out
+
     def synthesize_blurred(self, I, D, fx, fy, cx, cy, k, t0, dt, knots_t, knots_R, cap, exp, num_samples):
         H, W = I.shape
         kt = np.ascontiguousarray(knots_t, dtype=np.float64)

@@ -209,6 +209,27 @@ def test_device_built_pyramid(pkg, api, O, orc, synth, monkeypatch, no_texels):
         check_parity(O, gpu_eval(pkg, api, prob, 2, ctx=b), orc.evaluate(prob, 2))
 
 
+def test_synthetic_blurred_frame_bit_exact(pkg, api, orc, synth):
+    """mbavo_synthesize_blurred (generate_synthetic_data.cpp:127-180) is byte work: bit-exact against the oracle's
+    restatement on the same poses, and equal to the reference-generated golden frame up to the pose rounding."""
+    prob = synth.make_problem("blur", W=160, H=120, levels=1, P0=4, N=4, n_knots=3, k=2, seed=5, margin=10, motion_scale=3.0)
+    I = prob.levels[0].ref_I
+    ts = 0.1 + np.arange(24) * 1.7 / 23
+    poses = np.array([np.concatenate(synth.spline_pose(2, prob.gt_knots_t, prob.gt_knots_R, 0.0, 1.0, t)) for t in ts])
+    got = api.synthesize_blurred(I, 7.5, 80.0, 80.0, 80.0, 60.0, poses)
+    want = orc.warp_mean(I, 7.5, 80.0, 80.0, 80.0, 60.0, poses)
+    assert np.array_equal(got, want)
+    assert (got == 0).any() and (got > 0).any()  # the strong motion leaves part of the frame without keyframe coverage
+    z = golden("blurred.npz")
+    n, cap, exp = int(z["n"]), float(z["cap"]), float(z["exp"])
+    ts = [cap - exp * 0.5 + i * exp / (n - 1) for i in range(n)]
+    poses = np.array([np.concatenate(synth.spline_pose(2, z["knots_t"], z["knots_R"], 0.0, 1.0, t)) for t in ts])
+    got = api.synthesize_blurred(np.ascontiguousarray(z["ref_I"]), float(z["D"]), float(z["fx"]), float(z["fy"]), float(z["cx"]),
+                                 float(z["cy"]), poses)
+    diff = np.abs(got.astype(int) - z["out"].astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
 def test_multiple_frames(pkg, api, O, orc, synth):
     """n_frames > 1 with frames in different segments (the merge of overlapping frames, test_merge…:1060-1181)."""
     prob = synth.make_problem("frames", W=160, H=120, levels=1, P0=300, N=8, n_knots=3, k=2, seed=8, margin=14, F=2)
