@@ -291,6 +291,10 @@ int mbavo_synthesize_blurred(int device, int mem, const unsigned char *ref_I, in
 /* Number of kernels this library has launched on behalf of ctx since creation */
 long long mbavo_kernel_launches(const mbavo_ctx *ctx);
 
+/* Number of mbavo_gn_sweep calls that ran on the device-resident path (solve, candidate and commit inside the kernels,
+ * one host wait) rather than evaluation by evaluation. */
+long long mbavo_device_sweeps(const mbavo_ctx *ctx);
+
 /* 1 if the kernels of `level` read the keyframe through the packed fp16 texels built by mbavo_set_level (every
  * gradient value exactly representable in fp16 — always the case for Gradient.h's central differences of an 8-bit
  * image), 0 if they gather ref_I / ref_dIxy directly, -1 if the level is not set.  Results are identical either way. */

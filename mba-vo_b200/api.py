@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "mbavo_set_live_images", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
-    "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
+    "mbavo_device_sweeps", "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
     "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points", "mbavo_synthesize_blurred",
 ]
 IPC_HANDLE_BYTES = 64
@@ -101,6 +101,7 @@ def load_library() -> C.CDLL:
     lib = C.CDLL(path)
     lib.mbavo_last_error.restype = C.c_char_p
     lib.mbavo_kernel_launches.restype = C.c_longlong
+    lib.mbavo_device_sweeps.restype = C.c_longlong
     lib.mbavo_last_kernel_ms.restype = C.c_float
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)
@@ -353,6 +354,9 @@ class Context:
     # -- introspection ----------------------------------------------------------------------------------------
     def kernel_launches(self) -> int:
         return int(self.lib.mbavo_kernel_launches(self._h))
+
+    def device_sweeps(self) -> int:
+        return int(self.lib.mbavo_device_sweeps(self._h))
 
     def level_uses_texels(self, level: int) -> int:
         return int(self.lib.mbavo_level_uses_texels(self._h, C.c_int(level)))

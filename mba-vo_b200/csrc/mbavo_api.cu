@@ -18,7 +18,7 @@
 namespace mbavo
 {
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
-                                   double *mid, int *seg_end, cudaStream_t stream);
+                                   double *mid, int *seg_end, cudaStream_t stream, GnState *gn, int knots_from, bool dependent);
     cudaError_t launch_track_kernel(int K, int NK, bool with_j, bool big, const TrackParams &prm, dim3 grid, size_t smem,
                                     cudaStream_t stream, int *query_occupancy, bool dependent);
     size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool big, int N, int S, int TP);
@@ -99,6 +99,10 @@ struct mbavo_ctx
 
     EvalStage stage{};       // spline state of the evaluation being issued (launch parameter of the pose kernel)
     unsigned long long *phase_times_dev = nullptr; // development (mbavo_debug_phase_times)
+    int trace_row = 0;
+    GnState *gn_state = nullptr;                   // device-resident Gauss-Newton sweep (mbavo_gn_sweep)
+    long long device_sweeps = 0;                   // sweeps completed on the device-resident path
+    bool use_device_sweep = true;                  // MBAVO_NO_DEVICE_SWEEP=1: every evaluation returns to the host
     long long big_block_batches = 2000; // MBAVO_BIG_BLOCK_BATCHES: Hessian pass uses the big block shape from this many batches
     bool use_pdl = true;     // MBAVO_NO_PDL=1: tracking kernel fully serialised behind the pose kernel
 
@@ -382,8 +386,16 @@ namespace
 
     // pose kernel -> tracking kernel on ctx->stream.  blocking: the tracking kernel also publishes the result into the
     // context's mapped pinned buffer under a fresh sequence number (wait_result picks it up).
+    // Extras of a launch that belongs to a device-resident Gauss-Newton sweep
+    struct SweepLaunch
+    {
+        GnParams gn{};          // gn.state == nullptr: plain evaluation
+        int knots_from = 0;     // pose kernel: 0 launch parameter, 1 state->cur, 2 state->cand
+        bool first = false;     // first launch of the sweep: its pose kernel is not launched programmatically
+    };
+
     int run_evaluation(mbavo_ctx *ctx, int level, const EvalPlan &pl, double *packed_dev_out, bool blocking, double inv_num_residuals,
-                       double huber_a)
+                       double huber_a, const SweepLaunch *sweep = nullptr)
     {
         LevelStore &L = ctx->levels[level];
         cudaStream_t s = ctx->stream;
@@ -398,7 +410,8 @@ namespace
         }
         L.last_eval_frames = pl.F;
         ctx->launches += 2;
-        CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, pl.with_h ? 1 : 0, ctx->samples, ctx->mid, ctx->seg_end, s));
+        CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, pl.with_h ? 1 : 0, ctx->samples, ctx->mid, ctx->seg_end, s,
+                                    sweep ? sweep->gn.state : nullptr, sweep ? sweep->knots_from : 0, sweep && !sweep->first));
         TrackParams prm{};
         prm.lv = L.dev;
         prm.samples = ctx->samples;
@@ -414,6 +427,9 @@ namespace
         prm.counter = ctx->counter;
         prm.packed_out = packed_dev_out;
         prm.phase_times = ctx->phase_times_dev;
+        prm.trace_row = ctx->trace_row++;
+        if (sweep)
+            prm.gn = sweep->gn;
         if (ctx->shard.world > 1)
         {
             prm.shard = ctx->shard;
@@ -523,6 +539,8 @@ extern "C"
         CUDA_TRY(cudaMallocHost(&ctx->inexact_host, sizeof(int)));
         const char *g = getenv("MBAVO_NO_PDL");
         ctx->use_pdl = !(g && g[0] == '1');
+        g = getenv("MBAVO_NO_DEVICE_SWEEP");
+        ctx->use_device_sweep = !(g && g[0] == '1');
         g = getenv("MBAVO_BIG_BLOCK_BATCHES");
         if (g)
             ctx->big_block_batches = atoll(g);
@@ -567,6 +585,7 @@ extern "C"
         mbavo_shard_disconnect(ctx);
         cudaFree(ctx->mailbox);
         cudaFree(ctx->phase_times_dev);
+        cudaFree(ctx->gn_state);
         cudaFree(ctx->samples);
         cudaFree(ctx->mid);
         cudaFree(ctx->seg_end);
@@ -1088,6 +1107,110 @@ extern "C"
         return rc;
     }
 
+    // mbavo_gn_sweep without host round trips between the evaluations: the kernels of all levels are enqueued at once
+    // (pose -> Hessian pass [+ solve, candidate] -> pose at the candidate -> cost pass [+ record, commit]), chained by
+    // programmatic dependent launches; the host waits once.  Returns 1 (not an error) when the caller has to fall back to
+    // the evaluation-by-evaluation path: feature disabled, event timing on, or the device-side solve met normal equations
+    // that are not safely positive definite / a negative model decrease.
+    int mbavo_gn_sweep_device(mbavo_ctx *ctx, int level_coarse, int level_fine, int chain, int k, double t0, double dt, int n,
+                              double *knots_t, double *knots_R, double radius, double huber_a, double *costs)
+    {
+        if (!ctx || !ctx->use_device_sweep || ctx->timing || ctx->force_phases > 0)
+            return 1;
+        const int nlev = level_coarse - level_fine + 1;
+        if (nlev < 1 || nlev > MBAVO_MAX_LEVELS || n < 2 || n > 16)
+            return 1;
+        DeviceGuard guard(ctx->device);
+        if (!ctx->gn_state)
+        {
+            CUDA_TRY(cudaMalloc(&ctx->gn_state, sizeof(GnState)));
+            CUDA_TRY(cudaMemset(ctx->gn_state, 0, sizeof(GnState)));
+        }
+        mbavo_spline sp{k, t0, dt, n, knots_t, knots_R};
+        unsigned long long seq_of_level[MBAVO_MAX_LEVELS] = {};
+        for (int li = 0; li < nlev; ++li)
+        {
+            const int level = level_coarse - li;
+            LevelStore &L = ctx->levels[level];
+            for (int pass = 0; pass < 2; ++pass)
+            {
+                EvalPlan pl{};
+                int rc = plan_evaluation(ctx, level, &sp, pass == 0, pl);
+                if (rc != MBAVO_OK)
+                    return rc;
+                const long long pts = ctx->shard.world > 1 ? ctx->points_global[level] : pl.P;
+                if (ctx->shard.world > 1 && pts < pl.P)
+                    return fail(MBAVO_ENOTREADY, "mbavo_shard_set_global_points has not been called for level %d", level);
+                const long long nres = (pts - L.num_bad) * pl.F * pl.S;
+                SweepLaunch sw;
+                sw.gn.state = ctx->gn_state;
+                sw.gn.mode = pass == 0 ? 1 : 2;
+                sw.gn.n_knots = n, sw.gn.kmin = pl.kmin;
+                sw.gn.chain = chain, sw.gn.slot = li, sw.gn.last = (li == nlev - 1) ? 1 : 0;
+                sw.gn.radius = radius;
+                sw.knots_from = pass == 1 ? 2 : (li == 0 ? 0 : 1);
+                sw.first = li == 0 && pass == 0;
+                rc = run_evaluation(ctx, level, pl, ctx->packed_dev, true, 1.0 / (double)nres, huber_a, &sw);
+                if (rc != MBAVO_OK)
+                    return rc;
+                if (pass == 1)
+                    seq_of_level[li] = ctx->seq;
+            }
+        }
+        // wait for the last level's scalars and the final knots, then check the earlier levels' tags
+        const volatile unsigned long long *pairs = reinterpret_cast<const volatile unsigned long long *>(ctx->result_host);
+        const int first_pair[2] = {4 * (nlev - 1), 4 * MBAVO_MAX_LEVELS}, num_pairs[2] = {4, 7 * n};
+        for (int part = 0; part < 2; ++part)
+        {
+            int done = 0;
+            for (unsigned long long spins = 1; done < num_pairs[part]; ++spins)
+            {
+                while (done < num_pairs[part] && pairs[2 * (first_pair[part] + done) + 1] == ctx->seq)
+                    ++done;
+                if (done < num_pairs[part] && (spins & 0xfff) == 0)
+                {
+                    cudaError_t e = cudaStreamQuery(ctx->stream);
+                    if (e != cudaSuccess && e != cudaErrorNotReady)
+                        return fail(MBAVO_ECUDA, "sweep failed: %s", cudaGetErrorString(e));
+                    if (e == cudaSuccess && pairs[2 * (first_pair[part] + done) + 1] != ctx->seq)
+                        return fail(MBAVO_ECUDA, "sweep finished without publishing its result");
+                }
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        bool fallback = false, peer_lost = false;
+        for (int li = 0; li < nlev; ++li)
+        {
+            for (int e = 0; e < 4; ++e)
+                if (pairs[2 * (4 * li + e) + 1] != seq_of_level[li])
+                    return fail(MBAVO_ECUDA, "sweep: level %d did not publish", level_coarse - li);
+            const double c = ctx->result_host[2 * (4 * li)], cc = ctx->result_host[2 * (4 * li + 1)];
+            if (ctx->result_host[2 * (4 * li + 2)] != 0.0)
+                fallback = true;
+            if (ctx->shard.world > 1 && (c != c || cc != cc))
+                peer_lost = true;
+            if (costs)
+                costs[2 * li] = c, costs[2 * li + 1] = cc;
+        }
+        if (peer_lost)
+            return fail(MBAVO_ENCCL, "sharded sweep: a peer rank did not arrive within 4 s");
+        if (fallback)
+        {
+            fail(1, "device sweep declined: solve status %g %g %g %g ...", ctx->result_host[2 * 2], ctx->result_host[2 * 6],
+                 ctx->result_host[2 * 10], ctx->result_host[2 * 14]);
+            return 1;
+        }
+        ++ctx->device_sweeps;
+        if (chain)
+        {
+            for (int e = 0; e < 3 * n; ++e)
+                knots_t[e] = ctx->result_host[2 * (4 * MBAVO_MAX_LEVELS + e)];
+            for (int e = 0; e < 4 * n; ++e)
+                knots_R[e] = ctx->result_host[2 * (4 * MBAVO_MAX_LEVELS + 3 * n + e)];
+        }
+        return MBAVO_OK;
+    }
+
     int mbavo_patch_costs(mbavo_ctx *ctx, int level, double *out)
     {
         if (!ctx || !out || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
@@ -1234,23 +1357,27 @@ extern "C"
     }
 
     // Development aid (not declared in mbavo.h): globaltimer stamps of the tracking kernel's phases of the last launch;
-    // only MBAVO_PROFILE_PHASES builds of the kernel write them.  out: 16 values (ns).
+    // only MBAVO_PROFILE_PHASES builds of the kernel write them.  out: 64 rows (launches since the last call) x 16 stamps (ns).
     int mbavo_debug_phase_times(mbavo_ctx *ctx, unsigned long long *out)
     {
         if (!ctx || !out)
             return MBAVO_EINVAL;
         DeviceGuard guard(ctx->device);
+        const size_t bytes = 64 * 16 * sizeof(unsigned long long);
         if (!ctx->phase_times_dev)
         {
-            CUDA_TRY(cudaMalloc(&ctx->phase_times_dev, 16 * sizeof(unsigned long long)));
-            CUDA_TRY(cudaMemset(ctx->phase_times_dev, 0, 16 * sizeof(unsigned long long)));
+            CUDA_TRY(cudaMalloc(&ctx->phase_times_dev, bytes));
+            CUDA_TRY(cudaMemset(ctx->phase_times_dev, 0, bytes));
         }
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        CUDA_TRY(cudaMemcpy(out, ctx->phase_times_dev, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(out, ctx->phase_times_dev, bytes, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemset(ctx->phase_times_dev, 0, bytes));
+        ctx->trace_row = 0; // re-arm: the next launch writes row 0
         return MBAVO_OK;
     }
 
     long long mbavo_kernel_launches(const mbavo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+    long long mbavo_device_sweeps(const mbavo_ctx *ctx) { return ctx ? ctx->device_sweeps : 0; }
 
     int mbavo_level_uses_texels(const mbavo_ctx *ctx, int level)
     {

@@ -169,6 +169,31 @@ namespace mbavo
     }
 #endif
 
+    // ---- device-resident Gauss-Newton sweep (mbavo_gn_sweep) -----------------------------------------------------------
+    // The control knots of a sweep live in device memory: the Hessian-pass kernel's last block solves the damped normal
+    // equations and forms the candidate knots, the candidate's pose kernel reads them from here, the cost-pass kernel's
+    // last block records the candidate cost (and, when chaining, commits the candidate).  The host enqueues the kernels
+    // of all levels at once and waits once.
+    struct GnState
+    {
+        double cur_t[3 * 16], cur_R[4 * 16];   // knots the sweep currently stands on
+        double cand_t[3 * 16], cand_R[4 * 16]; // candidate of the level in flight
+        double step[6 * 16];                   // first LM step of the level in flight, full ordering [dt(3n), dw(3n)]
+        double cost, cand_cost, model;
+        int status;                            // 0 ok, 1 normal equations not safely positive definite, 2 model decrease < 0
+        int pad_;
+    };
+    struct GnParams
+    {
+        GnState *state;     // nullptr: plain evaluation
+        int mode;           // 1: Hessian pass -> solve + candidate;  2: cost pass at the candidate -> record / commit
+        int n_knots, kmin;  // kmin: first knot of the packed window
+        int chain;          // mode 2: commit the candidate when it lowered the cost
+        int slot;           // mode 2: (cost, candidate cost, status, model) go to host_out[4 slot ..]; last != 0: knots follow
+        int last;
+        double radius;
+    };
+
     struct TrackParams
     {
         LevelDev lv;
@@ -191,7 +216,9 @@ namespace mbavo
         double2 *host_out;                    // [E] (value, seq as bits) in mapped pinned host memory, or nullptr
         unsigned long long seq;
         ShardParams shard;                    // point sharding: the vector published is the sum over all ranks
-        unsigned long long *phase_times;      // development: globaltimer stamps of kernel phases (MBAVO_PROFILE_PHASES builds)
+        GnParams gn;                          // device-resident Gauss-Newton sweep
+        unsigned long long *phase_times;      // development: globaltimer stamps of kernel phases (MBAVO_PROFILE_PHASES builds),
+        int trace_row;                        // 16 stamps per row; row = ordinal of the launch since the trace was armed
     };
 
     __host__ __device__ constexpr int packed_len(int NK) { return (6 * NK + 1) * (6 * NK + 2) / 2; }

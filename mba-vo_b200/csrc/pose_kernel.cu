@@ -283,8 +283,8 @@ namespace mbavo
 
         // Sample g = f * N + i of the evaluation: record, mid-exposure pose of its frame, segment ranges.
         template <int K>
-        __host__ __device__ inline void pose_one(const EvalStage *st, int g, int with_jacobian, float *samples, double *mid,
-                                                 int *seg_end)
+        __host__ __device__ inline void pose_one(const EvalStage *st, const double *knots_t, const double *knots_R, int g,
+                                                 int with_jacobian, float *samples, double *mid, int *seg_end)
         {
             const int N = st->N;
             const int f = g / N, i = g % N;
@@ -296,7 +296,7 @@ namespace mbavo
 
             double tt[3], wt[K], Theta[K * 9];
             Q q;
-            spline_pose<K>(st->knots_t + 3 * idx, st->knots_R + 4 * idx, u, tt, q, wt, with_jacobian ? Theta : nullptr);
+            spline_pose<K>(knots_t + 3 * idx, knots_R + 4 * idx, u, tt, q, wt, with_jacobian ? Theta : nullptr);
 
             double R[9];
             rotation_matrix(q, R);
@@ -347,27 +347,53 @@ namespace mbavo
                     seg_end[f * kMaxSegments + s] = 0;
         }
 
-        // one thread per (frame, sample)
+        // one thread per (frame, sample).  knots_from: 0 = the launch parameter (and, if gn != nullptr, the sweep state is
+        // initialised from it), 1 = gn->cur_*, 2 = gn->cand_* (device-resident Gauss-Newton sweep).
         template <int K>
         __global__ void pose_kernel(const __grid_constant__ EvalStage stage, int with_jacobian, float *__restrict__ samples,
-                                    double *__restrict__ mid, int *__restrict__ seg_end)
+                                    double *__restrict__ mid, int *__restrict__ seg_end, GnState *gn, int knots_from)
         {
             cudaTriggerProgrammaticLaunchCompletion(); // the tracking kernel may start its prologue now
+            const double *kt = stage.knots_t, *kR = stage.knots_R;
+            if (gn)
+            {
+                // this grid may itself have been launched programmatically behind the previous tracking kernel
+                cudaGridDependencySynchronize();
+                if (knots_from == 1)
+                    kt = gn->cur_t, kR = gn->cur_R;
+                else if (knots_from == 2)
+                    kt = gn->cand_t, kR = gn->cand_R;
+                else if (blockIdx.x == 0)
+                {
+                    for (int e = threadIdx.x; e < 3 * stage.n_knots; e += blockDim.x)
+                        gn->cur_t[e] = stage.knots_t[e];
+                    for (int e = threadIdx.x; e < 4 * stage.n_knots; e += blockDim.x)
+                        gn->cur_R[e] = stage.knots_R[e];
+                    if (threadIdx.x == 0)
+                        gn->status = 0;
+                }
+            }
             const int g = blockIdx.x * blockDim.x + threadIdx.x;
             if (g < stage.N * stage.F)
-                pose_one<K>(&stage, g, with_jacobian, samples, mid, seg_end);
+                pose_one<K>(&stage, kt, kR, g, with_jacobian, samples, mid, seg_end);
         }
     } // namespace
 
+    // gn / knots_from: see pose_kernel.  dependent: launch programmatically behind the previous kernel of the stream (the
+    // kernel then waits for it before it reads the sweep state).
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
-                                   double *mid, int *seg_end, cudaStream_t stream)
+                                   double *mid, int *seg_end, cudaStream_t stream, GnState *gn, int knots_from, bool dependent)
     {
         const int threads = 64;
         const int blocks = (total_samples + threads - 1) / threads;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(blocks, 1, 1), cfg.blockDim = dim3(threads, 1, 1), cfg.dynamicSmemBytes = 0, cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr, cfg.numAttrs = (dependent && gn) ? 1 : 0;
         if (K == 2)
-            pose_kernel<2><<<blocks, threads, 0, stream>>>(stage, with_jacobian, samples, mid, seg_end);
-        else
-            pose_kernel<4><<<blocks, threads, 0, stream>>>(stage, with_jacobian, samples, mid, seg_end);
-        return cudaGetLastError();
+            return cudaLaunchKernelEx(&cfg, pose_kernel<2>, stage, with_jacobian, samples, mid, seg_end, gn, knots_from);
+        return cudaLaunchKernelEx(&cfg, pose_kernel<4>, stage, with_jacobian, samples, mid, seg_end, gn, knots_from);
     }
 } // namespace mbavo

@@ -122,7 +122,11 @@ namespace mbavo
         const int MT = with_j ? (NT + 31) / 32 : 1;
         main_bytes += 8 + (with_j ? (size_t)kWarpsPerBlock * MT * 4 * 32 * 8 : 0); // fp64 tile accumulators
         size_t red_bytes = (size_t)(kWarpsPerBlock > (kThreads / E + 1) ? kWarpsPerBlock : kThreads / E + 1) * E * 8;
-        return (main_bytes > red_bytes ? main_bytes : red_bytes) + 16;
+        // the device-resident Gauss-Newton step of the last block: packed vector + dense window system + 4 vectors
+        const size_t solve_bytes = with_j ? ((size_t)((E + 1) & ~1) + 72 * NK * NK + 18 * NK + 8) * 8 : 0;
+        size_t need = main_bytes > red_bytes ? main_bytes : red_bytes;
+        need = need > solve_bytes ? need : solve_bytes;
+        return need + 16;
     }
 
     cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,

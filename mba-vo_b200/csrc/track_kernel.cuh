@@ -47,13 +47,14 @@ namespace mbavo
     namespace
     {
         constexpr int kSampleUnroll = MBAVO_UNROLL;
+        constexpr int MBAVO_MAX_LEVELS_DEV = 8; // host_out layout of a sweep: 4 scalars per level, then the final knots
 
 #ifdef MBAVO_PROFILE_PHASES
 #define MBAVO_STAMP(slot)                                                                          \
     do                                                                                             \
     {                                                                                              \
         if (prm.phase_times && threadIdx.x == 0 && (blockIdx.x == 0 || (slot) >= 8))               \
-            prm.phase_times[slot] = global_timer_ns();                                             \
+            prm.phase_times[16 * (prm.trace_row & 63) + (slot)] = global_timer_ns();                                             \
     } while (0)
 #else
 #define MBAVO_STAMP(slot) \
@@ -325,6 +326,151 @@ namespace mbavo
             return x;
         }
 
+        // ---- device-resident Gauss-Newton step (one warp of the last block) -------------------------------------------------
+        // computeTrustRegionStep (blur_aware_direct_tracker.cpp:799-831) + Plus_t / Plus_R (Spline.h:307-330) on the packed
+        // window vector v = [cost, g(D), triu(H) row-major], D = 6 NK: damp the diagonal by (1 + 1/radius), solve by LDL^T
+        // (same pivot test as the host's fast path, lm_driver.cpp), step = -H^-1 g, model decrease with the damped H, candidate
+        // = knots [+] step.  Knots outside the window keep a zero step (what the pseudo-inverse of the full system gives).
+        // A (2 D x D) and w (3 D) are shared-memory scratch.  Executed by ONE warp; right-looking factorisation so that every
+        // step is a handful of parallel FMAs instead of long serial dot products.
+        template <int NK>
+        __device__ void gn_solve_step(const double *__restrict__ v, const GnParams &gp, double *__restrict__ A, double *__restrict__ w)
+        {
+            constexpr int D = 6 * NK, D1 = D + 1;
+            const int lane = threadIdx.x & 31;
+            GnState *st = gp.state;
+            double *Hd = A + D * D;                 // the damped H (kept for the model decrease); A becomes its LDL^T factor
+            double *g = w, *y = w + D, *sv = w + 2 * D;
+            const double damp = 1.0 / gp.radius;
+            for (int e = lane; e < D * D; e += 32)
+            {
+                const int r = e / D, c = e % D, ra = (r < c ? r : c) + 1, cb = (r < c ? c : r) + 1;
+                double h = v[ra * D1 - ra * (ra - 1) / 2 + (cb - ra)]; // element (ra, cb) of the (D+1) x (D+1) upper triangle
+                if (r == c)
+                    h += h * damp;
+                A[e] = h, Hd[e] = h;
+            }
+            for (int e = lane; e < D; e += 32)
+                g[e] = v[1 + e], y[e] = v[1 + e];
+            __syncwarp();
+            // right-looking LDL^T: after step j column j of A holds L(:, j) below the diagonal and d_j on it
+            bool ok = true;
+            double dmax = 0.0;
+            for (int j = 0; j < D; ++j)
+            {
+                const double d = A[j * D + j];
+                dmax = d > dmax ? d : dmax;
+                if (!(d > 1e-9 * dmax))
+                    ok = false;
+                const double id = 1.0 / d;
+                __syncwarp();
+                const int m = D - j - 1; // trailing size
+                for (int e = lane; e < m * m; e += 32)
+                {
+                    const int i = j + 1 + e / m, k = j + 1 + e % m;
+                    if (k <= i) // lower triangle only
+                        A[i * D + k] -= A[i * D + j] * A[k * D + j] * id;
+                }
+                __syncwarp();
+                for (int i = j + 1 + lane; i < D; i += 32)
+                    A[i * D + j] *= id; // L(i, j)
+                __syncwarp();
+            }
+            // L y = g (column sweeps), y /= d, L^T x = y
+            for (int k = 0; k < D; ++k)
+            {
+                const double yk = y[k];
+                __syncwarp();
+                for (int i = k + 1 + lane; i < D; i += 32)
+                    y[i] -= A[i * D + k] * yk;
+                __syncwarp();
+            }
+            for (int e = lane; e < D; e += 32)
+                y[e] /= A[e * D + e];
+            __syncwarp();
+            for (int k = D - 1; k >= 0; --k)
+            {
+                const double xk = y[k];
+                __syncwarp();
+                for (int i = lane; i < k; i += 32)
+                    y[i] -= A[k * D + i] * xk;
+                __syncwarp();
+            }
+            for (int e = lane; e < D; e += 32)
+                sv[e] = -y[e]; // solve_normal_equation.h:33
+            __syncwarp();
+            // model decrease -(g^T s + s^T H s / 2) with the damped H (tracker.cpp:821-823)
+            double part = 0.0;
+            for (int r = lane; r < D; r += 32)
+            {
+                double hr = 0.0;
+                for (int c = 0; c < D; ++c)
+                    hr += Hd[r * D + c] * sv[c];
+                part += g[r] * sv[r] + 0.5 * sv[r] * hr;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                part += __shfl_xor_sync(0xffffffffu, part, o);
+            const double model = -part;
+            const int n = gp.n_knots;
+            // full-ordering step and candidate knots
+            for (int e = lane; e < 6 * n; e += 32)
+                st->step[e] = 0.0;
+            __syncwarp();
+            for (int e = lane; e < 3 * NK; e += 32)
+            {
+                st->step[3 * gp.kmin + e] = sv[e];
+                st->step[3 * n + 3 * gp.kmin + e] = sv[3 * NK + e];
+            }
+            for (int e = lane; e < 3 * n; e += 32)
+            {
+                const int a = e / 3 - gp.kmin;
+                st->cand_t[e] = st->cur_t[e] + ((a >= 0 && a < NK) ? sv[3 * a + e % 3] : 0.0);
+            }
+            for (int j = lane; j < n; j += 32)
+            {
+                const int a = j - gp.kmin;
+                const double *q = st->cur_R + 4 * j;
+                double dq[4] = {0, 0, 0, 1};
+                if (a >= 0 && a < NK)
+                {
+                    // Sophus::SO3d::exp(w).unit_quaternion() (Spline.h:326), as lm_driver.cpp so3_exp
+                    const double *om = sv + 3 * NK + 3 * a;
+                    const double t2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+                    double fi, fr;
+                    if (t2 < 1e-20)
+                    {
+                        const double t4 = t2 * t2;
+                        fi = 0.5 - t2 / 48.0 + t4 / 3840.0;
+                        fr = 1.0 - t2 / 8.0 + t4 / 384.0;
+                    }
+                    else
+                    {
+                        const double t = sqrt(t2);
+                        double sh, ch;
+                        sincos(0.5 * t, &sh, &ch);
+                        fi = sh / t;
+                        fr = ch;
+                    }
+                    dq[0] = fi * om[0], dq[1] = fi * om[1], dq[2] = fi * om[2], dq[3] = fr;
+                }
+                double *o = st->cand_R + 4 * j;
+                o[0] = q[3] * dq[0] + q[0] * dq[3] + q[1] * dq[2] - q[2] * dq[1];
+                o[1] = q[3] * dq[1] + q[1] * dq[3] + q[2] * dq[0] - q[0] * dq[2];
+                o[2] = q[3] * dq[2] + q[2] * dq[3] + q[0] * dq[1] - q[1] * dq[0];
+                o[3] = q[3] * dq[3] - q[0] * dq[0] - q[1] * dq[1] - q[2] * dq[2];
+            }
+            if (lane == 0)
+            {
+                st->cost = v[0];
+                st->model = model;
+                if (!ok || !(model == model))
+                    st->status = 1;
+                else if (model < 0.0 && st->status == 0)
+                    st->status = 2;
+            }
+        }
+
         // tile id -> (ta << 8) | tb, row-major upper triangle of the T x T tile grid
         __device__ __forceinline__ unsigned int tile_s_copy(int id, int T)
         {
@@ -363,6 +509,8 @@ namespace mbavo
             constexpr int D1 = G::D1, PITCH = G::PITCH, NT = G::NT, MT = G::MT, E = G::E;
 
             MBAVO_STAMP(0);
+            if (prm.gn.state)
+                cudaTriggerProgrammaticLaunchCompletion(); // the next pose kernel of the sweep may queue up behind this grid
             const LevelDev &lv = prm.lv;
             const int f = blockIdx.y;
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -714,11 +862,52 @@ namespace mbavo
                 }
                 __syncthreads();
             }
+            const GnParams &gp = prm.gn;
+            if (gp.state)
+            {
+                // device-resident Gauss-Newton sweep: solve / record on the spot, publish the level's scalars
+                GnState *st = gp.state;
+                if constexpr (WITH_J)
+                {
+                    double *A = fin_s + ((E + 1) & ~1), *w = A + 72 * NK * NK;
+                    if (warp == 0)
+                        gn_solve_step<NK>(fin_s, gp, A, w);
+                }
+                else if (threadIdx.x == 0)
+                {
+                    const double cc = fin_s[0];
+                    st->cand_cost = cc;
+                    if (prm.host_out)
+                    {
+                        const double tag = __longlong_as_double((long long)prm.seq);
+                        double2 *o = prm.host_out + 4 * gp.slot;
+                        o[0] = make_double2(st->cost, tag), o[1] = make_double2(cc, tag);
+                        o[2] = make_double2((double)st->status, tag), o[3] = make_double2(st->model, tag);
+                    }
+                    if (gp.chain && st->status == 0 && cc < st->cost) // the finer level starts from the candidate
+                    {
+                        for (int e = 0; e < 3 * gp.n_knots; ++e)
+                            st->cur_t[e] = st->cand_t[e];
+                        for (int e = 0; e < 4 * gp.n_knots; ++e)
+                            st->cur_R[e] = st->cand_R[e];
+                    }
+                    if (gp.last && prm.host_out)
+                    {
+                        const double tag = __longlong_as_double((long long)prm.seq);
+                        double2 *o = prm.host_out + 4 * MBAVO_MAX_LEVELS_DEV;
+                        for (int e = 0; e < 3 * gp.n_knots; ++e)
+                            o[e] = make_double2(st->cur_t[e], tag);
+                        for (int e = 0; e < 4 * gp.n_knots; ++e)
+                            o[3 * gp.n_knots + e] = make_double2(st->cur_R[e], tag);
+                    }
+                }
+                __syncthreads();
+            }
             for (int e = threadIdx.x; e < E; e += blockDim.x)
             {
                 const double s = fin_s[e];
                 prm.packed_out[e] = s;
-                if (prm.host_out)
+                if (prm.host_out && !gp.state)
                     prm.host_out[e] = make_double2(s, __longlong_as_double((long long)prm.seq)); // one 16-byte store
             }
             MBAVO_STAMP(10);

@@ -232,6 +232,9 @@ namespace
     };
 } // namespace
 
+extern "C" int mbavo_gn_sweep_device(mbavo_ctx *ctx, int level_coarse, int level_fine, int chain, int k, double t0, double dt, int n,
+                                     double *knots_t, double *knots_R, double radius, double huber_a, double *costs);
+
 extern "C"
 {
     int mbavo_trust_region_step(double *H, const double *g, int dim, double radius, int solver_type, double *step,
@@ -337,6 +340,22 @@ extern "C"
         if (!ctx || !knots_t || !knots_R || level_coarse < level_fine || level_fine < 0 || level_coarse >= MBAVO_MAX_LEVELS ||
             n < 2 || n > 16)
             return MBAVO_EINVAL;
+        // fast path: the whole sweep on the device, one wait (mbavo_api.cu); it declines (returns 1) when it cannot
+        // reproduce the host semantics, e.g. normal equations that need the SVD branch
+        if (solver_type == MBAVO_SOLVER_SVD_JACOBI || solver_type == MBAVO_SOLVER_LDLT)
+        {
+            std::vector<double> kt(knots_t, knots_t + 3 * n), kR(knots_R, knots_R + 4 * n);
+            const int rc = mbavo_gn_sweep_device(ctx, level_coarse, level_fine, chain, k, t0, dt, n, kt.data(), kR.data(), radius,
+                                                 huber_a, costs);
+            if (rc == MBAVO_OK)
+            {
+                std::memcpy(knots_t, kt.data(), sizeof(double) * 3 * n);
+                std::memcpy(knots_R, kR.data(), sizeof(double) * 4 * n);
+                return MBAVO_OK;
+            }
+            if (rc < 0)
+                return rc;
+        }
         double ct[3 * 16], cR[4 * 16];
         for (int level = level_coarse; level >= level_fine; --level) // optimizeTrajectory, tracker.cpp:571-575
         {

@@ -472,3 +472,28 @@ def test_shard_peer_timeout_is_an_error(pkg, api, synth):
     finally:
         a.close()
         b.close()
+
+
+@pytest.mark.parametrize("name,chain", [("tiny", False), ("C2", True), ("C2", False), ("C5cubic", True)])
+def test_device_resident_sweep_matches_host_path(pkg, api, synth, monkeypatch, name, chain):
+    """mbavo_gn_sweep: the device-resident form (solve, candidate and commit in the kernels' last blocks, one host wait)
+    against the evaluation-by-evaluation form (MBAVO_NO_DEVICE_SWEEP=1)."""
+    prob = synth.make_config(name)
+    top = len(prob.levels) - 1
+
+    def sweep():
+        with pkg.Context(api.limits_for(prob)) as ctx:
+            api.upload_problem(ctx, prob)
+            out = [ctx.gn_sweep(top, 0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, 1e4, chain=chain)
+                   for _ in range(2)]
+            assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])  # deterministic
+            return out[0] + (ctx.device_sweeps(), ctx.lib.mbavo_last_error().decode())
+
+    dev = sweep()
+    monkeypatch.setenv("MBAVO_NO_DEVICE_SWEEP", "1")
+    host = sweep()
+    assert np.abs(dev[0] - host[0]).max() <= 1e-9 * np.abs(host[0]).max(), (dev[0], host[0])
+    assert np.abs(dev[1] - host[1]).max() <= 1e-9 and np.abs(dev[2] - host[2]).max() <= 1e-9
+    if chain:
+        assert np.abs(dev[1] - prob.knots_t).max() > 0  # a candidate was committed
+    assert dev[3] == 2 and host[3] == 0, (dev[3], dev[4])  # the device-resident path really ran
