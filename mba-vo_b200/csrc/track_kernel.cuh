@@ -35,6 +35,9 @@
 
 // Hessian pass: branch-free sample step, sample loop unrolled by 2 (measured best: profiles/r1_history.md); the cost-only
 // pass keeps the early exit of an invalid sample.
+#ifndef MBAVO_MINB_C
+#define MBAVO_MINB_C 4 // resident blocks per SM of the cost-only pass (8 warps each)
+#endif
 #ifndef MBAVO_BRANCHLESS
 #define MBAVO_BRANCHLESS 1
 #endif
@@ -499,7 +502,7 @@ namespace mbavo
         // K: knots per segment, NK: knots in the window (NK - K + 1 segments touched), WITH_J: Hessian pass or cost only,
         // PACKED: keyframe texels available.
         template <int K, int NK, bool WITH_J, bool PACKED, bool BIG>
-        __global__ void __launch_bounds__(track_warps(WITH_J, NK, BIG) * 32, WITH_J ? ((!BIG && NK <= 3) ? 2 : 1) : 4)
+        __global__ void __launch_bounds__(track_warps(WITH_J, NK, BIG) * 32, WITH_J ? ((!BIG && NK <= 3) ? 2 : 1) : MBAVO_MINB_C)
             track_kernel(const __grid_constant__ TrackParams prm)
         {
             using G = RowGeom<NK, WITH_J>;
