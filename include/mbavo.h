@@ -277,6 +277,15 @@ int mbavo_optimize_level(mbavo_ctx *ctx, int level, int spline_deg_k, double sta
                          int num_ctrl_knots, double *knots_t, double *knots_R, const mbavo_lm_options *opt,
                          mbavo_lm_summary *summary);
 
+/* ---- keyframe test statistics --------------------------------------------------------------
+ * BlurAwareDirectTracker::isKeyframe (blur_aware_direct_tracker.cpp:205-248): over the host-map points of `level` (the
+ * tracker uses level 0), avg_flow = sqrtf(mean |pi(T0^-1 P) - p|^2) and avg_kernel_len = sqrtf(mean |pi(T-^-1 P) -
+ * pi(T+^-1 P)|^2), P the point un-projected with its depth, T the live-camera-to-keyframe pose at the capture time (T0)
+ * and at -/+ half the exposure (T-, T+), pi the pinhole projection.  poses_tq: 3 x 7 doubles (tx ty tz qx qy qz qw) in
+ * the order T0, T-, T+ — SplineSE3::GetPose at those times.  Collective in a sharded context (means over all ranks).
+ * The caller applies its thresholds (keyframe_max_flow_mag0 / _mag1, keyframe_max_blur_kernel_mag, :250-262). */
+int mbavo_keyframe_stats(mbavo_ctx *ctx, int level, const double *poses_tq, double *avg_flow, double *avg_kernel_len);
+
 /* ---- synthetic blurred frame ---------------------------------------------------------------
  * warp_image + synthesize_motion_blurred_img (src/ba_tracker/generate_synthetic_data.cpp:127-180): the mean over num_poses
  * plane-induced warps of the keyframe (plane Z = plane_depth), each truncated to 8 bits, the mean rounded to nearest even.

@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = [
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
     "mbavo_device_sweeps", "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
     "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points", "mbavo_synthesize_blurred",
+    "mbavo_keyframe_stats",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -350,6 +351,13 @@ class Context:
 
     def shard_set_global_points(self, level: int, num_keypoints_global: int):
         self._check(self.lib.mbavo_shard_set_global_points(self._h, C.c_int(level), C.c_int(num_keypoints_global)))
+
+    def keyframe_stats(self, level: int, poses_tq) -> tuple:
+        """mbavo_keyframe_stats -> (avg_flow, avg_kernel_len); poses_tq is (3, 7): T0, T-, T+ as tx ty tz qx qy qz qw."""
+        poses = np.ascontiguousarray(poses_tq, dtype=np.float64).reshape(3, 7)
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self.lib.mbavo_keyframe_stats(self._h, C.c_int(level), _dp(poses), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # -- introspection ----------------------------------------------------------------------------------------
     def kernel_launches(self) -> int:

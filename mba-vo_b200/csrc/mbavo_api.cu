@@ -101,6 +101,7 @@ struct mbavo_ctx
     unsigned long long *phase_times_dev = nullptr; // development (mbavo_debug_phase_times)
     int trace_row = 0;
     GnState *gn_state = nullptr;                   // device-resident Gauss-Newton sweep (mbavo_gn_sweep)
+    double *kf_dev = nullptr, *kf_host = nullptr;  // keyframe statistics: sums + poses (device / pinned)
     long long device_sweeps = 0;                   // sweeps completed on the device-resident path
     bool use_device_sweep = true;                  // MBAVO_NO_DEVICE_SWEEP=1: every evaluation returns to the host
     long long big_block_batches = 2000; // MBAVO_BIG_BLOCK_BATCHES: Hessian pass uses the big block shape from this many batches
@@ -266,6 +267,64 @@ namespace
             result[0] = (int)s_x[0];
             result[1] = ok ? 0 : 1;
         }
+    }
+
+    // isKeyframe statistics (blur_aware_direct_tracker.cpp:205-248): every host-map point is un-projected with its depth,
+    // moved into the live camera at three poses T_cur2ref (capture time, -/+ half the exposure) and projected (pinhole,
+    // CameraPinhole.cpp:79-110 without distortion).  out[0] = sum |flow|^2, out[1] = sum |blur kernel|^2 (fixed-order tree
+    // sums, all-reduced through the mailboxes when sharded), out[2] = 1 if a peer timed out.
+    __global__ void __launch_bounds__(256) keyframe_kernel(const char *__restrict__ xy, int xy_stride, int xy_offset, const double *__restrict__ z, int P,
+                                    double fx, double fy, double cx, double cy, const double *__restrict__ poses_tq,
+                                    double *__restrict__ out, const ShardParams sh)
+    {
+        __shared__ double s_a[256];
+        __shared__ double s_b[256];
+        __shared__ double s_x[8];
+        __shared__ double Rt[3][12]; // per pose: R (row-major) and t
+        const int tid = threadIdx.x;
+        if (tid < 3)
+        {
+            const double *p = poses_tq + 7 * tid, qx = p[3], qy = p[4], qz = p[5], qw = p[6];
+            double *R = Rt[tid];
+            R[0] = qw * qw + qx * qx - qy * qy - qz * qz, R[1] = 2 * (qx * qy - qw * qz), R[2] = 2 * (qx * qz + qw * qy);
+            R[3] = 2 * (qx * qy + qw * qz), R[4] = qw * qw - qx * qx + qy * qy - qz * qz, R[5] = 2 * (qy * qz - qw * qx);
+            R[6] = 2 * (qx * qz - qw * qy), R[7] = 2 * (qy * qz + qw * qx), R[8] = qw * qw - qx * qx - qy * qy + qz * qz;
+            R[9] = p[0], R[10] = p[1], R[11] = p[2];
+        }
+        __syncthreads();
+        double flow = 0, kern = 0;
+        for (int i = tid; i < P; i += blockDim.x)
+        {
+            const double *pt = reinterpret_cast<const double *>(xy + (size_t)i * xy_stride + xy_offset);
+            const double x = pt[0], y = pt[1], d = z[i];
+            const double Pr[3] = {d * ((x - cx) / fx), d * ((y - cy) / fy), d};
+            double u[3], v[3];
+            for (int k = 0; k < 3; ++k)
+            {
+                const double *R = Rt[k];
+                const double a = Pr[0] - R[9], b = Pr[1] - R[10], c = Pr[2] - R[11];
+                const double X = R[0] * a + R[3] * b + R[6] * c, Y = R[1] * a + R[4] * b + R[7] * c, Z = R[2] * a + R[5] * b + R[8] * c; // R^T (P - t)
+                u[k] = fx * X / Z + cx, v[k] = fy * Y / Z + cy;
+            }
+            flow += (u[0] - x) * (u[0] - x) + (v[0] - y) * (v[0] - y);
+            kern += (u[1] - u[2]) * (u[1] - u[2]) + (v[1] - v[2]) * (v[1] - v[2]);
+        }
+        s_a[tid] = flow, s_b[tid] = kern;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1)
+        {
+            if (tid < o)
+                s_a[tid] += s_a[tid + o], s_b[tid] += s_b[tid + o];
+            __syncthreads();
+        }
+        if (tid == 0)
+            s_x[0] = s_a[0], s_x[1] = s_b[0];
+        __syncthreads();
+        bool ok = true;
+        if (sh.world > 1)
+            ok = shard_allreduce_small(sh, sh.seq, s_x, 2);
+        if (tid == 0)
+            out[0] = s_x[0], out[1] = s_x[1], out[2] = ok ? 0.0 : 1.0;
     }
 
     // Sample time and segment of (frame, sample): compute_virtual_camera_poses.cu:33 + SplineFunctor.h:13-19.  The device
@@ -586,6 +645,8 @@ extern "C"
         cudaFree(ctx->mailbox);
         cudaFree(ctx->phase_times_dev);
         cudaFree(ctx->gn_state);
+        cudaFree(ctx->kf_dev);
+        cudaFreeHost(ctx->kf_host);
         cudaFree(ctx->samples);
         cudaFree(ctx->mid);
         cudaFree(ctx->seg_end);
@@ -1208,6 +1269,37 @@ extern "C"
             for (int e = 0; e < 4 * n; ++e)
                 knots_R[e] = ctx->result_host[2 * (4 * MBAVO_MAX_LEVELS + 3 * n + e)];
         }
+        return MBAVO_OK;
+    }
+
+    int mbavo_keyframe_stats(mbavo_ctx *ctx, int level, const double *poses_tq, double *avg_flow, double *avg_kernel_len)
+    {
+        if (!ctx || !poses_tq || !avg_flow || !avg_kernel_len || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
+            return fail(MBAVO_ENOTREADY, "level not set");
+        DeviceGuard guard(ctx->device);
+        LevelStore &L = ctx->levels[level];
+        cudaStream_t s = ctx->stream;
+        if (!ctx->kf_dev)
+        {
+            CUDA_TRY(cudaMalloc(&ctx->kf_dev, sizeof(double) * 32));
+            CUDA_TRY(cudaMallocHost(&ctx->kf_host, sizeof(double) * 32));
+        }
+        std::memcpy(ctx->kf_host + 8, poses_tq, sizeof(double) * 21);
+        CUDA_TRY(cudaMemcpyAsync(ctx->kf_dev + 8, ctx->kf_host + 8, sizeof(double) * 21, cudaMemcpyHostToDevice, s));
+        ShardParams sh = ctx->shard;
+        if (sh.world > 1)
+            sh.seq = ++ctx->aux_seq;
+        keyframe_kernel<<<1, 256, 0, s>>>(L.dev.xy, L.dev.xy_stride, L.dev.xy_offset, L.dev.z, L.dev.P, L.dev.fx, L.dev.fy, L.dev.cx,
+                                           L.dev.cy, ctx->kf_dev + 8, ctx->kf_dev, sh);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(ctx->kf_host, ctx->kf_dev, sizeof(double) * 3, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (ctx->kf_host[2] != 0.0)
+            return fail(MBAVO_ENCCL, "sharded keyframe statistics: a peer rank did not arrive within 4 s");
+        const double n = ctx->shard.world > 1 && ctx->points_global[level] > 0 ? ctx->points_global[level] : L.dev.P;
+        *avg_flow = (double)sqrtf((float)(ctx->kf_host[0] / n));        // tracker.cpp:244-245: sqrtf of the mean
+        *avg_kernel_len = (double)sqrtf((float)(ctx->kf_host[1] / n));
         return MBAVO_OK;
     }
 

@@ -254,6 +254,26 @@ class RefLib(_Lib):
         return out
 
 
+def keyframe_stats(xy, z, fx, fy, cx, cy, poses_tq):
+    """isKeyframe statistics (blur_aware_direct_tracker.cpp:205-248), numpy fp64 restatement: -> (avg_flow, avg_kernel_len).
+    poses_tq: (3, 7) = T_cur2ref at the capture time, at -half and at +half the exposure (tx ty tz qx qy qz qw)."""
+    xy = np.asarray(xy, dtype=np.float64)
+    z = np.asarray(z, dtype=np.float64)
+    Pr = np.stack([z * ((xy[:, 0] - cx) / fx), z * ((xy[:, 1] - cy) / fy), z], axis=1)  # CameraPinhole::unproject
+    uv = []
+    for p in np.asarray(poses_tq, dtype=np.float64).reshape(3, 7):
+        t, (qx, qy, qz, qw) = p[:3], p[3:]
+        R = np.array([[qw * qw + qx * qx - qy * qy - qz * qz, 2 * (qx * qy - qw * qz), 2 * (qx * qz + qw * qy)],
+                      [2 * (qx * qy + qw * qz), qw * qw - qx * qx + qy * qy - qz * qz, 2 * (qy * qz - qw * qx)],
+                      [2 * (qx * qz - qw * qy), 2 * (qy * qz + qw * qx), qw * qw - qx * qx - qy * qy + qz * qz]])
+        Pc = (Pr - t) @ R  # T.inverse() * P = R^T (P - t)
+        uv.append(np.stack([fx * Pc[:, 0] / Pc[:, 2] + cx, fy * Pc[:, 1] / Pc[:, 2] + cy], axis=1))
+    flow = ((uv[0] - xy) ** 2).sum()
+    kern = ((uv[1] - uv[2]) ** 2).sum()
+    n = xy.shape[0]
+    return float(np.sqrt(np.float32(flow / n))), float(np.sqrt(np.float32(kern / n)))
+
+
 def best_cpu_lib() -> _Lib:
     """oracle/_ref when present (kind 'reference'), else the C port (kind 'port')."""
     return RefLib() if RefLib.available() else OracleLib()

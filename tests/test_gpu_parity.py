@@ -230,6 +230,21 @@ def test_synthetic_blurred_frame_bit_exact(pkg, api, orc, synth):
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
 
 
+def test_keyframe_statistics(pkg, api, O, synth):
+    """mbavo_keyframe_stats (isKeyframe, tracker.cpp:205-248): mean flow and mean blur-kernel length of the host-map points."""
+    prob = synth.make_config("C1")
+    lv = prob.levels[0]
+    cap, exp = float(prob.cap[0]), float(prob.exp[0])
+    poses = np.array([np.concatenate(synth.spline_pose(prob.k, prob.gt_knots_t, prob.gt_knots_R, prob.t0, prob.dt, t))
+                      for t in (cap, cap - 0.5 * exp, cap + 0.5 * exp)])
+    want = O.keyframe_stats(lv.xy, lv.z, lv.fx, lv.fy, lv.cx, lv.cy, poses)
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        got = ctx.keyframe_stats(0, poses)
+    assert want[0] > 0.1 and want[1] > 0.1
+    assert abs(got[0] - want[0]) <= 1e-6 * want[0] and abs(got[1] - want[1]) <= 1e-6 * want[1]  # float sqrt of fp64 sums
+
+
 def test_multiple_frames(pkg, api, O, orc, synth):
     """n_frames > 1 with frames in different segments (the merge of overlapping frames, test_merge…:1060-1181)."""
     prob = synth.make_problem("frames", W=160, H=120, levels=1, P0=300, N=8, n_knots=3, k=2, seed=8, margin=14, F=2)
@@ -437,6 +452,13 @@ def test_fused_shard_allreduce(pkg, api, O, orc, synth, world):
         got = _run_ranks([lambda c=c: c.evaluate(0, prob.k, prob.t0, prob.dt, kt, prob.knots_R, prob.huber_a, True) for c in ctxs])
         want2 = orc.evaluate(prob, 0, kt, prob.knots_R, flags=want_flags, num_bad=want_n)
         assert abs(got[0][0] - want2[0]) <= COST_TOL * want2[0] and max_rel(got[0][1], want2[1]) <= 1e-4
+        # collective keyframe statistics: means over the points of all ranks
+        cap, exp = float(prob.cap[0]), float(prob.exp[0])
+        poses = np.array([np.concatenate(synth.spline_pose(prob.k, prob.gt_knots_t, prob.gt_knots_R, prob.t0, prob.dt, t))
+                          for t in (cap, cap - 0.5 * exp, cap + 0.5 * exp)])
+        kf = _run_ranks([lambda c=c: c.keyframe_stats(0, poses) for c in ctxs])
+        kf_want = O.keyframe_stats(lv.xy, lv.z, lv.fx, lv.fy, lv.cx, lv.cy, poses)
+        assert all(k == kf[0] for k in kf) and abs(kf[0][0] - kf_want[0]) <= 1e-6 * kf_want[0] and abs(kf[0][1] - kf_want[1]) <= 1e-6 * kf_want[1]
         # a whole collective LM loop: every rank commits the same knots, equal to the single-context run
         for c in ctxs:
             c.set_outliers(0, None)
