@@ -27,7 +27,13 @@ def run(prob, pyramid=False):
             c2, _, _ = ctx.evaluate(*a, False)
             ctx.detect_outliers(level, 3.0)
             ctx.evaluate(*a, True)
-        print(prob.name, "ok", c, c2, flush=True)
+        top = len(prob.levels) - 1
+        costs, kt, kR = ctx.gn_sweep(top, 0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, 1e4, chain=True)
+        cap, exp = float(prob.cap[0]), float(prob.exp[0])
+        poses = np.array([np.concatenate(synth.spline_pose(prob.k, prob.gt_knots_t, prob.gt_knots_R, prob.t0, prob.dt, t))
+                          for t in (cap, cap - 0.4 * exp, cap + 0.4 * exp)])
+        kf = ctx.keyframe_stats(0, poses)
+        print(prob.name, "ok", c, c2, "sweeps on device", ctx.device_sweeps(), "kf", kf, flush=True)
 
 
 probs = [synth.make_config("tiny"),
@@ -45,6 +51,10 @@ del os.environ["MBAVO_NO_TEXELS"]
 os.environ["MBAVO_PHASES"] = "4"
 run(probs[0])
 del os.environ["MBAVO_PHASES"]
+
+img = api.synthesize_blurred(probs[0].levels[0].ref_I, 7.5, 48.0, 48.0, 48.0, 32.0,
+                             np.array([[0.01 * i, 0.0, 0.0, 0.0, 0.0, 0.001 * i, 1.0] for i in range(6)]))
+print("synth ok", int(img.sum()), flush=True)
 
 # two ranks on one device
 prob = probs[0]
