@@ -225,8 +225,7 @@ def run_own(args, pkg):
     def upload_all():
         ctx.set_keyframe_pyramid(n_levels, pinned[0].ref_I)
         ctx.set_live_pyramid(n_levels, pinned[0].cur_I)
-        for l, lv in enumerate(pinned):
-            ctx.set_level_points(l, lv)
+        ctx.set_points_pyramid(pinned)
 
     upload_all()
     fused = world > 1 and args.collective == "fused"

@@ -136,6 +136,8 @@ typedef struct mbavo_level_points
 int mbavo_set_keyframe_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0);
 int mbavo_set_live_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *const *cur_I0, int n_frames);
 int mbavo_set_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *points);
+/* the points of levels 0 .. n_levels-1 in one call (one synchronisation): points[l] describes level l */
+int mbavo_set_points_pyramid(mbavo_ctx *ctx, int n_levels, const mbavo_level_points *points);
 
 /* A new live (blurred) frame for an already set level — what BlurAwareDirectTracker::trackFrame uploads per frame
  * (blur_aware_direct_tracker.cpp:112-116) while keyframe image, gradient, texels and host-map points stay resident.

@@ -18,7 +18,7 @@ SOLVER_SVD_JACOBI, SOLVER_LDLT = 0, 1
 # every symbol include/mbavo.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
     "mbavo_last_error", "mbavo_version", "mbavo_create", "mbavo_destroy", "mbavo_set_stream", "mbavo_set_frame_times",
-    "mbavo_set_level", "mbavo_set_keyframe_pyramid", "mbavo_set_live_pyramid", "mbavo_set_level_points",
+    "mbavo_set_level", "mbavo_set_keyframe_pyramid", "mbavo_set_live_pyramid", "mbavo_set_level_points", "mbavo_set_points_pyramid",
     "mbavo_set_live_images", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
@@ -194,6 +194,14 @@ class Context:
         d = _LevelPoints(MEM_HOST, lv.fx, lv.fy, lv.cx, lv.cy, xy.ctypes.data, 16, 0, z.ctypes.data, xy.shape[0],
                          lv.pattern.ctypes.data, lv.S, lv.N)
         self._check(self.lib.mbavo_set_level_points(self._h, C.c_int(level), C.byref(d)))
+
+    def set_points_pyramid(self, levels: Sequence):
+        """mbavo_set_points_pyramid from a list of synth.Level (level 0 first)."""
+        arr = (_LevelPoints * len(levels))()
+        for l, lv in enumerate(levels):
+            arr[l] = _LevelPoints(MEM_HOST, lv.fx, lv.fy, lv.cx, lv.cy, lv.xy.ctypes.data, 16, 0, lv.z.ctypes.data, lv.xy.shape[0],
+                                  lv.pattern.ctypes.data, lv.S, lv.N)
+        self._check(self.lib.mbavo_set_points_pyramid(self._h, C.c_int(len(levels)), arr))
 
     def set_live_images(self, level: int, cur_I: Sequence[np.ndarray]):
         """mbavo_set_live_images with host images: a new blurred frame for a level whose keyframe stays resident."""
@@ -412,8 +420,7 @@ def upload_problem_pyramid(ctx: Context, prob) -> None:
     n = len(prob.levels)
     ctx.set_keyframe_pyramid(n, prob.levels[0].ref_I)
     ctx.set_live_pyramid(n, prob.levels[0].cur_I)
-    for l, lv in enumerate(prob.levels):
-        ctx.set_level_points(l, lv)
+    ctx.set_points_pyramid(prob.levels)
 
 
 def optimize_trajectory(ctx: Context, prob, **kw):

@@ -951,7 +951,8 @@ extern "C"
         return MBAVO_OK;
     }
 
-    int mbavo_set_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d)
+    // enqueue the uploads of one level's points on the context's stream (no synchronisation)
+    static int enqueue_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d)
     {
         if (!ctx || !d || level < 0 || level >= MBAVO_MAX_LEVELS)
             return fail(MBAVO_EINVAL, "bad context / level");
@@ -971,13 +972,10 @@ extern "C"
             return fail(MBAVO_EINVAL, "keypoint_xy stride/offset must describe two aligned doubles per record");
         if (!(d->fx > 0) || !(d->fy > 0))
             return fail(MBAVO_EINVAL, "fx, fy must be positive");
-        DeviceGuard guard(ctx->device);
         LevelStore &L = ctx->levels[level];
         if (L.set && !L.has_key)
             return fail(MBAVO_EINVAL, "level %d was set by mbavo_set_level; points of such a level are replaced by mbavo_set_level", level);
         cudaStream_t s = ctx->stream;
-        if (cudaStreamQuery(s) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(s));
         int rc = ensure_level_scratch(ctx, L);
         if (rc != MBAVO_OK)
             return rc;
@@ -993,8 +991,11 @@ extern "C"
                 CUDA_TRY(cudaMalloc(&L.pts_z, sizeof(double) * P));
                 L.pts_cap = P;
             }
-            CUDA_TRY(cudaMemcpy2DAsync(L.pts_xy, 16, (const char *)d->keypoint_xy + d->keypoint_xy_offset, d->keypoint_xy_stride, 16, P,
-                                       cudaMemcpyHostToDevice, s));
+            if (d->keypoint_xy_stride == 16 && d->keypoint_xy_offset == 0)
+                CUDA_TRY(cudaMemcpyAsync(L.pts_xy, d->keypoint_xy, sizeof(double) * 2 * P, cudaMemcpyHostToDevice, s));
+            else // compact the records to packed double2 on the way in
+                CUDA_TRY(cudaMemcpy2DAsync(L.pts_xy, 16, (const char *)d->keypoint_xy + d->keypoint_xy_offset, d->keypoint_xy_stride, 16, P,
+                                           cudaMemcpyHostToDevice, s));
             CUDA_TRY(cudaMemcpyAsync(L.pts_z, d->keypoint_z, sizeof(double) * P, cudaMemcpyHostToDevice, s));
             L.dev.xy = reinterpret_cast<const char *>(L.pts_xy), L.dev.xy_stride = 16, L.dev.xy_offset = 0;
             L.dev.z = L.pts_z;
@@ -1006,7 +1007,7 @@ extern "C"
             L.dev.z = d->keypoint_z;
         }
         CUDA_TRY(cudaMemcpyAsync(L.pattern, d->pattern_xy, sizeof(int2) * d->patch_size, cudaMemcpyDefault, s));
-        CUDA_TRY(cudaMemsetAsync(L.flags, 0, ctx->lim.max_num_keypoints, s));
+        CUDA_TRY(cudaMemsetAsync(L.flags, 0, P, s));
         L.num_bad = 0;
         L.dev.fx = d->fx, L.dev.fy = d->fy, L.dev.cx = d->cx, L.dev.cy = d->cy;
         L.dev.inv_fx = 1.0 / d->fx, L.dev.inv_fy = 1.0 / d->fy;
@@ -1016,8 +1017,38 @@ extern "C"
         L.dev.patch_cost = L.patch_cost, L.dev.patch_cost_stride = 1;
         L.has_pts = true;
         pyramid_level_ready(L);
-        CUDA_TRY(cudaStreamSynchronize(s));
         return MBAVO_OK;
+    }
+
+
+    int mbavo_set_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d)
+    {
+        if (!ctx)
+            return fail(MBAVO_EINVAL, "null context");
+        DeviceGuard guard(ctx->device);
+        if (cudaStreamQuery(ctx->stream) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        int rc = enqueue_level_points(ctx, level, d);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream); // host buffers are only borrowed for the call
+        if (rc == MBAVO_OK && e != cudaSuccess)
+            return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e));
+        return rc;
+    }
+
+    int mbavo_set_points_pyramid(mbavo_ctx *ctx, int n_levels, const mbavo_level_points *points)
+    {
+        if (!ctx || !points || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS)
+            return fail(MBAVO_EINVAL, "bad arguments");
+        DeviceGuard guard(ctx->device);
+        if (cudaStreamQuery(ctx->stream) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        int rc = MBAVO_OK;
+        for (int l = 0; l < n_levels && rc == MBAVO_OK; ++l)
+            rc = enqueue_level_points(ctx, l, points + l);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream); // one synchronisation for all levels
+        if (rc == MBAVO_OK && e != cudaSuccess)
+            return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e));
+        return rc;
     }
 
     int mbavo_set_live_images(mbavo_ctx *ctx, int level, int mem, const unsigned char *const *cur_I, int n_frames)

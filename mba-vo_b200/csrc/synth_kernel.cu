@@ -110,7 +110,8 @@ extern "C" int mbavo_synthesize_blurred(int device, int mem, const unsigned char
     }
     if (rc == MBAVO_OK)
     {
-        static SynthPoses poses; // 14 KB launch parameter
+        SynthPoses poses; // 14 KB launch parameter
+        std::memset(&poses, 0, sizeof poses);
         std::memcpy(poses.tq, poses_tq, sizeof(double) * 7 * num_poses);
         const dim3 block(128, 1, 1), grid((W + 127) / 128, H, 1);
         synth_blur_kernel<<<grid, block>>>(src, H, W, plane_depth, fx, fy, cx, cy, poses, num_poses, dst);
