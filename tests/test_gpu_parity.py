@@ -519,3 +519,28 @@ def test_device_resident_sweep_matches_host_path(pkg, api, synth, monkeypatch, n
     if chain:
         assert np.abs(dev[1] - prob.knots_t).max() > 0  # a candidate was committed
     assert dev[3] == 2 and host[3] == 0, (dev[3], dev[4])  # the device-resident path really ran
+
+
+def test_device_sweep_with_unobserved_knots(pkg, api, O, orc, synth, monkeypatch):
+    """A spline with a control knot that no exposure sample touches: the normal equations are singular in that knot.  The
+    host path solves them by the pseudo-inverse (zero step on the unobserved knot); the device-resident sweep solves the
+    window system only, which is the same step."""
+    prob = synth.make_problem("unobs", W=192, H=144, levels=2, P0=900, N=8, n_knots=3, k=2, seed=21, margin=16)
+    prob.dt = float(prob.exp[0]) * 1.0001  # the whole exposure lies in segment 0: knot 2 is unobserved
+    prob.cap[:] = prob.t0 + 0.5 * prob.exp[0]
+
+    def sweep():
+        with pkg.Context(api.limits_for(prob)) as ctx:
+            api.upload_problem(ctx, prob)
+            out = ctx.gn_sweep(1, 0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, 1e4, chain=True)
+            return out + (ctx.device_sweeps(),)
+
+    dev = sweep()
+    monkeypatch.setenv("MBAVO_NO_DEVICE_SWEEP", "1")
+    host = sweep()
+    assert dev[3] == 1 and host[3] == 0
+    assert np.abs(dev[0] - host[0]).max() <= 1e-8 * np.abs(host[0]).max()
+    assert np.abs(dev[1] - host[1]).max() <= 1e-8 and np.abs(dev[2] - host[2]).max() <= 1e-8
+    assert np.array_equal(dev[1][2], prob.knots_t[2]) and np.array_equal(dev[2][2], prob.knots_R[2])  # untouched
+    want = orc.evaluate(prob, 1)
+    assert abs(dev[0][0, 0] - want[0]) <= COST_TOL * want[0]
