@@ -279,6 +279,33 @@ int mbavo_optimize_level(mbavo_ctx *ctx, int level, int spline_deg_k, double sta
                          int num_ctrl_knots, double *knots_t, double *knots_R, const mbavo_lm_options *opt,
                          mbavo_lm_summary *summary);
 
+/* ---- semi-dense host-map point selection -------------------------------------------------------
+ * What BlurAwareDirectTracker::tmpProcessKeyframe does on the CPU for a new keyframe (blur_aware_direct_tracker.cpp:355-409),
+ * for levels 0 .. n_levels-1 of the keyframe pyramid already built by mbavo_set_keyframe_pyramid:
+ *   FeatureDetectorSemiDense::detect (src/core/feature_detectors/FeatureDetectorSemiDense.cpp:16-59): the pixels whose gradient
+ *     magnitude (src/core/image_proc/Gradient.h:57-72) exceeds score_threshold;
+ *   FeatureDetectorBase::gridSelection (FeatureDetectorBase.cpp:49-92): per cell of (int)(cell / 1.414^l) pixels the strongest
+ *     of them (the first in row-major order on ties), in cell order;
+ *   the depth look-up (:389-409): z = depth_z[(int)(y 2^l + .5)][(int)(x 2^l + .5)], points with z < 1e-2 dropped.
+ * Bit-exact with the reference.  The selected points become the level's points (as mbavo_set_level_points would set them,
+ * intrinsics divided by 2^l as in :765-771) and never leave HBM; num_selected[l] returns how many there are (a level with
+ * none cannot be evaluated).  In a sharded context every rank selects the same points and keeps its contiguous block.
+ * mbavo_get_points copies a level's points to the host for a caller that wants them (xy: 2 doubles per point; either
+ * pointer may be NULL; both NULL just returns the count). */
+typedef struct mbavo_point_selection
+{
+    float score_threshold;         /* 25      (blur_aware_direct_tracker.cpp:357) */
+    int cell_H, cell_W;            /* 30, 30  (:358-359); must be positive */
+    int depth_mem;                 /* MBAVO_MEM_HOST or MBAVO_MEM_DEVICE */
+    const float *depth_z;          /* level-0 depth along the optical axis, H0 x W0 floats, row-major */
+    double fx, fy, cx, cy;         /* level-0 intrinsics */
+    const int *pattern_xy;         /* residual pattern (host memory), as in mbavo_level */
+    int patch_size;
+    int num_virtual_poses;
+} mbavo_point_selection;
+int mbavo_select_points(mbavo_ctx *ctx, int n_levels, const mbavo_point_selection *selection, int *num_selected);
+int mbavo_get_points(mbavo_ctx *ctx, int level, int capacity, double *xy, double *z, int *num_points);
+
 /* ---- keyframe test statistics --------------------------------------------------------------
  * BlurAwareDirectTracker::isKeyframe (blur_aware_direct_tracker.cpp:205-248): over the host-map points of `level` (the
  * tracker uses level 0), avg_flow = sqrtf(mean |pi(T0^-1 P) - p|^2) and avg_kernel_len = sqrtf(mean |pi(T-^-1 P) -

@@ -24,13 +24,19 @@ EXPORTED_SYMBOLS = [
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
     "mbavo_device_sweeps", "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
     "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points", "mbavo_synthesize_blurred",
-    "mbavo_keyframe_stats",
+    "mbavo_keyframe_stats", "mbavo_select_points", "mbavo_get_points",
 ]
 IPC_HANDLE_BYTES = 64
 
 
 class MbavoError(RuntimeError):
     pass
+
+
+class _PointSelection(C.Structure):
+    _fields_ = [("score_threshold", C.c_float), ("cell_H", C.c_int), ("cell_W", C.c_int), ("depth_mem", C.c_int),
+                ("depth_z", C.c_void_p), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("pattern_xy", C.c_void_p), ("patch_size", C.c_int), ("num_virtual_poses", C.c_int)]
 
 
 class _Limits(C.Structure):
@@ -366,6 +372,27 @@ class Context:
         a, b = C.c_double(0), C.c_double(0)
         self._check(self.lib.mbavo_keyframe_stats(self._h, C.c_int(level), _dp(poses), C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def select_points(self, n_levels: int, depth_z: np.ndarray, fx: float, fy: float, cx: float, cy: float, pattern: np.ndarray,
+                      num_virtual_poses: int, score_threshold: float = 25.0, cell_H: int = 30, cell_W: int = 30):
+        """mbavo_select_points (semi-dense selection + grid selection + depth look-up on the GPU) -> points per level."""
+        depth = np.ascontiguousarray(depth_z, dtype=np.float32)
+        pat = np.ascontiguousarray(pattern, dtype=np.int32)
+        sel = _PointSelection(score_threshold, cell_H, cell_W, MEM_HOST, depth.ctypes.data, fx, fy, cx, cy, pat.ctypes.data,
+                              pat.shape[0], num_virtual_poses)
+        counts = (C.c_int * n_levels)()
+        self._check(self.lib.mbavo_select_points(self._h, C.c_int(n_levels), C.byref(sel), counts))
+        return [int(c) for c in counts]
+
+    def get_points(self, level: int):
+        """mbavo_get_points -> (xy (P, 2), z (P,)) of a level, copied from the device."""
+        n = C.c_int(0)
+        self._check(self.lib.mbavo_get_points(self._h, C.c_int(level), C.c_int(0), None, None, C.byref(n)))
+        xy = np.zeros((n.value, 2))
+        z = np.zeros(n.value)
+        if n.value:
+            self._check(self.lib.mbavo_get_points(self._h, C.c_int(level), C.c_int(n.value), _dp(xy), _dp(z), C.byref(n)))
+        return xy, z
 
     # -- introspection ----------------------------------------------------------------------------------------
     def kernel_launches(self) -> int:

@@ -25,6 +25,7 @@ namespace mbavo
     cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,
                                    int *inexact, cudaStream_t stream);
     cudaError_t launch_pyr_down_kernel(const unsigned char *src, int Ws, unsigned char *dst, int Hd, int Wd, cudaStream_t stream);
+    cudaError_t launch_select_kernels(const SelectParams &prm, int total_cells, cudaStream_t stream);
     cudaError_t launch_pack_image_kernel(const unsigned char *I, int H, int W, uint4 *pair, unsigned int *quad, float *grad,
                                          cudaStream_t stream);
 } // namespace mbavo
@@ -102,6 +103,11 @@ struct mbavo_ctx
     int trace_row = 0;
     GnState *gn_state = nullptr;                   // device-resident Gauss-Newton sweep (mbavo_gn_sweep)
     double *kf_dev = nullptr, *kf_host = nullptr;  // keyframe statistics: sums + poses (device / pinned)
+    // semi-dense point selection (mbavo_select_points): cell records, level-0 depth map, counts (device / pinned)
+    int4 *sel_cells = nullptr;
+    float *sel_depth = nullptr;
+    size_t sel_cells_cap = 0, sel_depth_cap = 0;
+    int *sel_count_dev = nullptr, *sel_count_host = nullptr;
     long long device_sweeps = 0;                   // sweeps completed on the device-resident path
     bool use_device_sweep = true;                  // MBAVO_NO_DEVICE_SWEEP=1: every evaluation returns to the host
     long long big_block_batches = 2000; // MBAVO_BIG_BLOCK_BATCHES: Hessian pass uses the big block shape from this many batches
@@ -647,6 +653,10 @@ extern "C"
         cudaFree(ctx->gn_state);
         cudaFree(ctx->kf_dev);
         cudaFreeHost(ctx->kf_host);
+        cudaFree(ctx->sel_cells);
+        cudaFree(ctx->sel_depth);
+        cudaFree(ctx->sel_count_dev);
+        cudaFreeHost(ctx->sel_count_host);
         cudaFree(ctx->samples);
         cudaFree(ctx->mid);
         cudaFree(ctx->seg_end);
@@ -1049,6 +1059,154 @@ extern "C"
         if (rc == MBAVO_OK && e != cudaSuccess)
             return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e));
         return rc;
+    }
+
+    int mbavo_select_points(mbavo_ctx *ctx, int n_levels, const mbavo_point_selection *sel, int *num_selected)
+    {
+        if (!ctx || !sel || !num_selected || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS)
+            return fail(MBAVO_EINVAL, "bad arguments");
+        if (!sel->depth_z || !sel->pattern_xy || (sel->depth_mem != MBAVO_MEM_HOST && sel->depth_mem != MBAVO_MEM_DEVICE))
+            return fail(MBAVO_EINVAL, "null depth map / pattern, or bad depth_mem");
+        if (sel->cell_H < 1 || sel->cell_W < 1)
+            return fail(MBAVO_EINVAL, "grid_selection cells must be positive (the tracker uses 30 x 30)");
+        if (sel->patch_size < 1 || sel->patch_size > ctx->lim.max_patch_size)
+            return fail(MBAVO_ECAPACITY, "patch_size %d outside [1, %d]", sel->patch_size, ctx->lim.max_patch_size);
+        if (sel->num_virtual_poses < 1 || sel->num_virtual_poses > ctx->lim.max_num_virtual_poses_per_frame)
+            return fail(MBAVO_ECAPACITY, "num_virtual_poses %d outside [1, %d]", sel->num_virtual_poses,
+                        ctx->lim.max_num_virtual_poses_per_frame);
+        if (!(sel->fx > 0) || !(sel->fy > 0))
+            return fail(MBAVO_EINVAL, "fx, fy must be positive");
+        for (int l = 0; l < n_levels; ++l)
+            if (!ctx->levels[l].has_key)
+                return fail(MBAVO_ENOTREADY, "level %d has no keyframe pyramid (mbavo_set_keyframe_pyramid comes first)", l);
+        DeviceGuard guard(ctx->device);
+        cudaStream_t s = ctx->stream;
+        if (cudaStreamQuery(s) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(s));
+        const int H0 = ctx->levels[0].dev.H, W0 = ctx->levels[0].dev.W;
+        SelectParams prm{};
+        int total_cells = 0;
+        const int cap = ctx->lim.max_num_keypoints;
+        for (int l = 0; l < n_levels; ++l)
+        {
+            LevelStore &L = ctx->levels[l];
+            SelectLevel &S = prm.lv[l];
+            S.I = L.dev.ref_I, S.H = L.dev.H, S.W = L.dev.W;
+            S.ch = (int)(sel->cell_H / std::pow(1.414, l)), S.cw = (int)(sel->cell_W / std::pow(1.414, l)); // FeatureDetectorBase.cpp:60-61
+            if (S.ch < 1 || S.cw < 1)
+                return fail(MBAVO_EINVAL, "cell %d x %d shrinks to nothing at level %d", sel->cell_H, sel->cell_W, l);
+            if (S.H != H0 / (1 << l) || S.W != W0 / (1 << l))
+                return fail(MBAVO_ENOTREADY, "level %d does not belong to the pyramid of level 0", l);
+            S.nch = S.H / S.ch + 1, S.ncw = S.W / S.cw + 1; // :63-64
+            S.cell_base = total_cells;
+            total_cells += S.nch * S.ncw;
+            if (L.pts_cap < (size_t)cap)
+            {
+                cudaFree(L.pts_xy);
+                cudaFree(L.pts_z);
+                L.pts_xy = L.pts_z = nullptr, L.pts_cap = 0;
+                CUDA_TRY(cudaMalloc(&L.pts_xy, sizeof(double) * 2 * cap));
+                CUDA_TRY(cudaMalloc(&L.pts_z, sizeof(double) * cap));
+                L.pts_cap = cap;
+            }
+            S.xy = reinterpret_cast<double2 *>(L.pts_xy), S.z = L.pts_z;
+            int rc = ensure_level_scratch(ctx, L);
+            if (rc != MBAVO_OK)
+                return rc;
+        }
+        if (ctx->sel_cells_cap < (size_t)total_cells)
+        {
+            cudaFree(ctx->sel_cells);
+            ctx->sel_cells = nullptr, ctx->sel_cells_cap = 0;
+            CUDA_TRY(cudaMalloc(&ctx->sel_cells, sizeof(int4) * total_cells));
+            ctx->sel_cells_cap = total_cells;
+        }
+        if (!ctx->sel_count_dev)
+        {
+            CUDA_TRY(cudaMalloc(&ctx->sel_count_dev, sizeof(int) * MBAVO_MAX_LEVELS));
+            CUDA_TRY(cudaMallocHost(&ctx->sel_count_host, sizeof(int) * MBAVO_MAX_LEVELS));
+        }
+        const float *depth = sel->depth_z;
+        if (sel->depth_mem == MBAVO_MEM_HOST)
+        {
+            const size_t npix = (size_t)H0 * W0;
+            if (ctx->sel_depth_cap < npix)
+            {
+                cudaFree(ctx->sel_depth);
+                ctx->sel_depth = nullptr, ctx->sel_depth_cap = 0;
+                CUDA_TRY(cudaMalloc(&ctx->sel_depth, sizeof(float) * npix));
+                ctx->sel_depth_cap = npix;
+            }
+            CUDA_TRY(cudaMemcpyAsync(ctx->sel_depth, sel->depth_z, sizeof(float) * npix, cudaMemcpyHostToDevice, s));
+            depth = ctx->sel_depth;
+        }
+        prm.n_levels = n_levels, prm.score_threshold = sel->score_threshold, prm.depth_z = depth, prm.W0 = W0, prm.capacity = cap;
+        prm.cell_rec = ctx->sel_cells, prm.count = ctx->sel_count_dev;
+        CUDA_TRY(launch_select_kernels(prm, total_cells, s));
+        ctx->launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(ctx->sel_count_host, ctx->sel_count_dev, sizeof(int) * n_levels, cudaMemcpyDeviceToHost, s));
+        for (int l = 0; l < n_levels; ++l)
+        {
+            LevelStore &L = ctx->levels[l];
+            CUDA_TRY(cudaMemcpyAsync(L.pattern, sel->pattern_xy, sizeof(int2) * sel->patch_size, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemsetAsync(L.flags, 0, cap, s));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s));
+        for (int l = 0; l < n_levels; ++l)
+        {
+            LevelStore &L = ctx->levels[l];
+            const int n = ctx->sel_count_host[l];
+            num_selected[l] = n;
+            if (n > cap)
+                return fail(MBAVO_ECAPACITY, "level %d: %d points selected, max_num_keypoints is %d", l, n, cap);
+            // a sharded context keeps its contiguous block of the selection (every rank selects the same points)
+            int lo = 0, hi = n;
+            if (ctx->shard.world > 1)
+            {
+                const int base = n / ctx->shard.world, rem = n % ctx->shard.world, r = ctx->shard.rank;
+                lo = r * base + (r < rem ? r : rem), hi = lo + base + (r < rem ? 1 : 0);
+                ctx->points_global[l] = n;
+            }
+            const double scale = (double)(1 << l); // tracker.cpp:765-771
+            L.dev.xy = reinterpret_cast<const char *>(L.pts_xy + 2 * (size_t)lo), L.dev.xy_stride = 16, L.dev.xy_offset = 0;
+            L.dev.z = L.pts_z + lo;
+            L.num_bad = 0;
+            L.dev.fx = sel->fx / scale, L.dev.fy = sel->fy / scale, L.dev.cx = sel->cx / scale, L.dev.cy = sel->cy / scale;
+            L.dev.inv_fx = 1.0 / L.dev.fx, L.dev.inv_fy = 1.0 / L.dev.fy;
+            L.dev.P = hi - lo, L.dev.S = sel->patch_size, L.dev.N = sel->num_virtual_poses;
+            L.dev.pattern = L.pattern;
+            L.dev.flags = L.flags;
+            L.dev.patch_cost = L.patch_cost, L.dev.patch_cost_stride = 1;
+            L.has_pts = hi > lo; // a level without points cannot be evaluated
+            pyramid_level_ready(L);
+        }
+        return MBAVO_OK;
+    }
+
+    int mbavo_get_points(mbavo_ctx *ctx, int level, int capacity, double *xy, double *z, int *num_points)
+    {
+        if (!ctx || !num_points || level < 0 || level >= MBAVO_MAX_LEVELS)
+            return fail(MBAVO_EINVAL, "bad arguments");
+        LevelStore &L = ctx->levels[level];
+        if (!L.has_pts && !(L.set && !L.has_key))
+        {
+            *num_points = 0;
+            return L.has_key ? MBAVO_OK : fail(MBAVO_ENOTREADY, "level %d has no points", level);
+        }
+        const int P = L.dev.P;
+        *num_points = P;
+        if (!xy && !z)
+            return MBAVO_OK;
+        if (capacity < P)
+            return fail(MBAVO_ECAPACITY, "level %d holds %d points, capacity is %d", level, P, capacity);
+        DeviceGuard guard(ctx->device);
+        cudaStream_t s = ctx->stream;
+        if (xy)
+            CUDA_TRY(cudaMemcpy2DAsync(xy, 16, L.dev.xy + L.dev.xy_offset, L.dev.xy_stride, 16, P, cudaMemcpyDeviceToHost, s));
+        if (z)
+            CUDA_TRY(cudaMemcpyAsync(z, L.dev.z, sizeof(double) * P, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return MBAVO_OK;
     }
 
     int mbavo_set_live_images(mbavo_ctx *ctx, int level, int mem, const unsigned char *const *cur_I, int n_frames)

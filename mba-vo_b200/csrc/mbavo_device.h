@@ -221,6 +221,30 @@ namespace mbavo
         int trace_row;                        // 16 stamps per row; row = ordinal of the launch since the trace was armed
     };
 
+    // ---- semi-dense point selection (select_kernel.cu) -------------------------------------------------------------------
+    constexpr int kSelectMaxLevels = 8; // MBAVO_MAX_LEVELS of include/mbavo.h
+    struct SelectLevel
+    {
+        const unsigned char *I; // keyframe image of the level
+        int H, W;
+        int ch, cw;             // cell size at this level: (int)(cell / 1.414^level)   FeatureDetectorBase.cpp:60-61
+        int nch, ncw;           // H / ch + 1, W / cw + 1                                :63-64
+        int cell_base;          // first cell of the level in the concatenated cell list
+        double2 *xy;            // selected points of the level, in cell order
+        double *z;
+    };
+    struct SelectParams
+    {
+        SelectLevel lv[kSelectMaxLevels];
+        int n_levels;
+        float score_threshold;
+        const float *depth_z;   // level-0 depth map, H0 x W0
+        int W0;
+        int capacity;           // points the xy / z arrays hold per level
+        int4 *cell_rec;         // per cell: (x, y, bits of z, selected)
+        int *count;             // [n_levels] points selected (may exceed capacity: the excess is not stored)
+    };
+
     __host__ __device__ constexpr int packed_len(int NK) { return (6 * NK + 1) * (6 * NK + 2) / 2; }
 } // namespace mbavo
 

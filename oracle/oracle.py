@@ -10,6 +10,8 @@ Restated host logic (reference file:line):
     Plus_t / Plus_R                   src/core/common/Spline.h:307-330  (Sophus SO3::exp == quaternion exp map)
     optimizePyramidLevel / LM loop    src/ba_tracker/blur_aware_direct_tracker.cpp:590-637, 885-924
     detectOutliersAndUploadToGpu      src/ba_tracker/blur_aware_direct_tracker.cpp:639-699
+    semi-dense point selection        src/core/feature_detectors/FeatureDetectorSemiDense.cpp:16-59, FeatureDetectorBase.cpp:49-92,
+                                      src/core/image_proc/Gradient.h:57-72, blur_aware_direct_tracker.cpp:389-409
     LevenbergMarquardtStrategy        src/ba_tracker/levenberg_marquardt_strategy.cpp:9-44
     TrustRegionStepEvaluator          src/ba_tracker/trust_region_step_evaluator.cpp:45-126
 """
@@ -272,6 +274,93 @@ def keyframe_stats(xy, z, fx, fy, cx, cy, poses_tq):
     kern = ((uv[1] - uv[2]) ** 2).sum()
     n = xy.shape[0]
     return float(np.sqrt(np.float32(flow / n))), float(np.sqrt(np.float32(kern / n)))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# semi-dense host-map point selection (numpy restatement; pinned against oracle/_ref/libmbavo_refselect.so)
+# ---------------------------------------------------------------------------------------------------------
+
+def pyramid_numpy(I0, n_levels):
+    """ImagePyramid<uchar>::computePyramid (ImagePyramid.h:59-99): level l has H0 / 2^l x W0 / 2^l pixels, each the truncated
+    quarter of the float sum of its 2 x 2 parents."""
+    out = [np.ascontiguousarray(I0, dtype=np.uint8)]
+    H0, W0 = out[0].shape
+    for lv in range(1, n_levels):
+        p = out[-1].astype(np.uint32)
+        H, W = H0 // (1 << lv), W0 // (1 << lv)
+        s = p[0:2 * H:2, 0:2 * W:2] + p[0:2 * H:2, 1:2 * W:2] + p[1:2 * H:2, 0:2 * W:2] + p[1:2 * H:2, 1:2 * W:2]
+        out.append((s >> 2).astype(np.uint8))  # T(0.25f * sum): the sum (<= 1020) is exact in float
+    return out
+
+
+def gradient_magnitude(I):
+    """Magnitude image of compute_image_gradients (Gradient.h:33-72) for one channel: sqrt(dx^2 + dy^2) of the halved central
+    differences (float products and sum — exact for 8-bit inputs — square root in double, stored as float), 0 on the border."""
+    f = I.astype(np.float32)
+    H, W = f.shape
+    dx = np.zeros((H, W), np.float32)
+    dy = np.zeros((H, W), np.float32)
+    dx[1:-1, 1:-1] = np.float32(0.5) * (f[1:-1, 2:] - f[1:-1, :-2])
+    dy[1:-1, 1:-1] = np.float32(0.5) * (f[2:, 1:-1] - f[:-2, 1:-1])
+    return np.sqrt((dx * dx + dy * dy).astype(np.float64)).astype(np.float32)
+
+
+def select_points(I0, n_levels, score_threshold, cell_H, cell_W, depth_z):
+    """FeatureDetectorSemiDense::detect + FeatureDetectorBase::gridSelection + the depth look-up of tmpProcessKeyframe.
+    -> per level (xy (P, 2) float64 in level coordinates, z (P,) float64), points in cell order."""
+    H0, W0 = I0.shape
+    depth_z = np.ascontiguousarray(depth_z, dtype=np.float32)
+    thr = np.float32(score_threshold)
+    out = []
+    for lv, I in enumerate(pyramid_numpy(I0, n_levels)):
+        mag = gradient_magnitude(I)
+        H_lv, W_lv = H0 // int(2.0 ** lv), W0 // int(2.0 ** lv)        # FeatureDetectorBase.cpp:57-59
+        ch, cw = int(cell_H / 1.414 ** lv), int(cell_W / 1.414 ** lv)  # :60-61
+        ncw = W_lv // cw + 1                                           # :63-64
+        ys, xs = np.nonzero(mag > thr)                                 # row-major scan, SemiDense.cpp:29-43
+        resp = mag[ys, xs]
+        # float division then truncation, as `pt.y / cell_H_lv` (:70-72)
+        cell = (ys.astype(np.float32) / np.float32(ch)).astype(np.int64) * ncw + (xs.astype(np.float32) / np.float32(cw)).astype(np.int64)
+        order = np.lexsort((np.arange(len(cell)), -resp.astype(np.float64), cell))  # per cell: strongest, first in scan order on ties
+        first = np.ones(len(order), bool)
+        first[1:] = cell[order][1:] != cell[order][:-1]
+        pick = order[first]
+        pick = pick[resp[pick] >= np.float32(1e-6)]                    # :85-88
+        px, py = xs[pick].astype(np.float32), ys[pick].astype(np.float32)
+        scale = 2.0 ** lv
+        x0 = (px.astype(np.float64) * scale + 0.5).astype(np.int64)    # tracker.cpp:397-398
+        y0 = (py.astype(np.float64) * scale + 0.5).astype(np.int64)
+        z = depth_z[y0, x0]
+        keep = ~(z.astype(np.float64) < 1e-2)                          # :401-404
+        out.append((np.stack([px[keep], py[keep]], axis=1).astype(np.float64), z[keep].astype(np.float64)))
+    return out
+
+
+class RefSelect:
+    """oracle/_ref/libmbavo_refselect.so — the reference's own detector sources, where they were built."""
+
+    PATH = os.path.join(_HERE, "_ref", "libmbavo_refselect.so")
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(RefSelect.PATH)
+
+    def __init__(self):
+        self.lib = C.CDLL(self.PATH)
+
+    def select_points(self, I0, n_levels, score_threshold, cell_H, cell_W, depth_z, max_points=None, want_mag=False):
+        H0, W0 = I0.shape
+        max_points = max_points or H0 * W0
+        xy = np.zeros((n_levels, max_points, 2), np.float64)
+        z = np.zeros((n_levels, max_points), np.float64)
+        cnt = np.zeros(n_levels, np.int32)
+        mag = np.zeros((H0, W0), np.float32) if want_mag else None
+        self.lib.mbavo_refselect_points(_ptr(np.ascontiguousarray(I0, dtype=np.uint8), _u8p), C.c_int(H0), C.c_int(W0), C.c_int(n_levels),
+                                        C.c_float(score_threshold), C.c_int(cell_H), C.c_int(cell_W),
+                                        _ptr(np.ascontiguousarray(depth_z, dtype=np.float32), _fp), C.c_int(max_points),
+                                        _ptr(xy, _dp), _ptr(z, _dp), _ptr(cnt, _ip), _ptr(mag, _fp))
+        res = [(xy[l, :cnt[l]].copy(), z[l, :cnt[l]].copy()) for l in range(n_levels)]
+        return (res, mag) if want_mag else res
 
 
 def best_cpu_lib() -> _Lib:

@@ -77,6 +77,25 @@ def main():
                                  prob.gt_knots_R, 0.45, 0.9, 16)
     np.savez_compressed(os.path.join(HERE, "blurred.npz"), ref_I=prob.levels[0].ref_I, knots_t=prob.gt_knots_t,
                         knots_R=prob.gt_knots_R, D=7.5, fx=48.0, fy=48.0, cx=48.0, cy=32.0, cap=0.45, exp=0.9, n=16, out=out)
+    # 5. semi-dense point selection by the reference's own detector sources (oracle/_ref/libmbavo_refselect.so):
+    #    a textured image and the reference test's ramp image (ties in every cell), a depth map with holes
+    sel = O.RefSelect()
+    rng = np.random.default_rng(7)
+    cases = {}
+    for name, img in (("tex", synth.make_problem("golden_sel", W=160, H=120, levels=1, P0=4, N=4, n_knots=2, seed=9, margin=10).levels[0].ref_I),
+                      ("ramp", synth.ramp_image(120, 160))):
+        depth = rng.uniform(0.5, 10.0, img.shape).astype(np.float32)
+        depth[rng.random(img.shape) < 0.15] = 0.0
+        thr, cell = (4.0, 12) if name == "tex" else (0.25, 9)
+        res = sel.select_points(img, 3, thr, cell, cell, depth)
+        cases[name + "_I"] = img
+        cases[name + "_depth"] = depth
+        cases[name + "_thr"] = thr
+        cases[name + "_cell"] = cell
+        cases[name + "_count"] = np.array([len(z) for _, z in res])
+        cases[name + "_xy"] = np.concatenate([xy for xy, _ in res])
+        cases[name + "_z"] = np.concatenate([z for _, z in res])
+    np.savez_compressed(os.path.join(HERE, "point_selection.npz"), **cases)
     print("golden vectors written to", HERE)
 
 

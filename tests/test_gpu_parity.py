@@ -230,6 +230,71 @@ def test_synthetic_blurred_frame_bit_exact(pkg, api, orc, synth):
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
 
 
+def test_point_selection_bit_exact(pkg, api, O, orc, synth):
+    """mbavo_select_points (FeatureDetectorSemiDense::detect, FeatureDetectorBase::gridSelection, the depth look-up of
+    tmpProcessKeyframe) is byte / index work: the same points, in the same order, as the oracle — on the golden cases the
+    reference's own detector produced, on VGA pyramids with the tracker's parameters, on a flat image (no points) — and the
+    selected points are the level's points: an evaluation on them equals one on the same points uploaded from the host."""
+    pattern = synth.make_config("C1").levels[0].pattern
+    z = golden("point_selection.npz")
+    for name in ("tex", "ramp"):
+        I, depth = np.ascontiguousarray(z[name + "_I"]), np.ascontiguousarray(z[name + "_depth"])
+        cnt = z[name + "_count"]
+        offs = np.concatenate([[0], np.cumsum(cnt)])
+        lim = api.Limits(max_num_keypoints=4096, max_num_virtual_poses_per_frame=8, max_patch_size=len(pattern))
+        with pkg.Context(lim) as ctx:
+            ctx.set_keyframe_pyramid(len(cnt), I)
+            got_cnt = ctx.select_points(len(cnt), depth, 80.0, 80.0, 80.0, 60.0, pattern, 4, float(z[name + "_thr"]), int(z[name + "_cell"]),
+                                        int(z[name + "_cell"]))
+            assert got_cnt == list(cnt)
+            for l in range(len(cnt)):
+                xy, zz = ctx.get_points(l)
+                assert np.array_equal(xy, z[name + "_xy"][offs[l]:offs[l + 1]]) and np.array_equal(zz, z[name + "_z"][offs[l]:offs[l + 1]])
+        with pkg.Context(api.Limits(max_num_keypoints=50, max_num_virtual_poses_per_frame=8, max_patch_size=len(pattern))) as ctx:
+            ctx.set_keyframe_pyramid(len(cnt), I)
+            with pytest.raises(pkg.MbavoError):  # more points than max_num_keypoints
+                ctx.select_points(len(cnt), depth, 80.0, 80.0, 80.0, 60.0, pattern, 4, float(z[name + "_thr"]), int(z[name + "_cell"]),
+                                  int(z[name + "_cell"]))
+            with pytest.raises(pkg.MbavoError):  # grid selection off is not the tracker's mode
+                ctx.select_points(len(cnt), depth, 80.0, 80.0, 80.0, 60.0, pattern, 4, 25.0, -1, -1)
+    rng = np.random.default_rng(11)
+    prob = synth.make_config("C2")
+    H, W = prob.levels[0].H, prob.levels[0].W
+    depth = np.full((H, W), 7.5, np.float32)
+    depth[rng.random((H, W)) < 0.05] = 0.0
+    images = {"tex": prob.levels[0].ref_I, "ramp": synth.ramp_image(H, W), "noise": rng.integers(0, 256, (H, W)).astype(np.uint8),
+              "flat": np.full((H, W), 9, np.uint8)}
+    lim = api.limits_for(prob)
+    with pkg.Context(lim) as ctx:
+        for name, I in images.items():
+            for thr, ch, cw in ((25.0, 30, 30), (2.0, 7, 5), (0.5, 17, 23)):
+                ctx.set_keyframe_pyramid(4, I)
+                want = O.select_points(I, 4, thr, ch, cw, depth)
+                cnt = ctx.select_points(4, depth, 320.0, 320.0, 320.0, 240.0, pattern, 16, thr, ch, cw)
+                assert cnt == [len(zz) for _, zz in want], (name, thr)
+                for l in range(4):
+                    xy, zz = ctx.get_points(l)
+                    assert np.array_equal(xy, want[l][0]) and np.array_equal(zz, want[l][1]), (name, thr, l)
+                if name == "flat":
+                    assert cnt == [0, 0, 0, 0]
+        # the selected points drive the tracker: same result as the same points set from the host
+        ctx.set_frame_times(prob.cap, prob.exp)
+        ctx.set_keyframe_pyramid(4, prob.levels[0].ref_I)
+        ctx.set_live_pyramid(4, prob.levels[0].cur_I)
+        cnt = ctx.select_points(4, depth, prob.levels[0].fx, prob.levels[0].fy, prob.levels[0].cx, prob.levels[0].cy, pattern,
+                                prob.levels[0].N, 2.0, 7, 5)
+        want = O.select_points(prob.levels[0].ref_I, 4, 2.0, 7, 5, depth)
+        with pkg.Context(lim) as other:
+            api.upload_problem_pyramid(other, prob)
+            for l in (0, 2, 3):
+                lv = prob.levels[l]
+                lv.xy, lv.z = np.ascontiguousarray(want[l][0]), np.ascontiguousarray(want[l][1])
+                other.set_level_points(l, lv)
+                a = ctx.evaluate(l, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, True)
+                b = other.evaluate(l, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, True)
+                assert cnt[l] > 500 and a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
 def test_keyframe_statistics(pkg, api, O, synth):
     """mbavo_keyframe_stats (isKeyframe, tracker.cpp:205-248): mean flow and mean blur-kernel length of the host-map points."""
     prob = synth.make_config("C1")

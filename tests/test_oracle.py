@@ -66,6 +66,25 @@ def test_golden_blurred(orc):
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3  # a float-rounding tie may move a pixel by one grey level
 
 
+def _selection_cases():
+    z = golden("point_selection.npz")
+    for name in ("tex", "ramp"):
+        cnt = z[name + "_count"]
+        offs = np.concatenate([[0], np.cumsum(cnt)])
+        want = [(z[name + "_xy"][offs[l]:offs[l + 1]], z[name + "_z"][offs[l]:offs[l + 1]]) for l in range(len(cnt))]
+        yield name, np.ascontiguousarray(z[name + "_I"]), np.ascontiguousarray(z[name + "_depth"]), float(z[name + "_thr"]), int(z[name + "_cell"]), want
+
+
+def test_golden_point_selection(O):
+    """numpy restatement of FeatureDetectorSemiDense::detect + gridSelection + the depth look-up against the points the
+    reference's own detector sources selected (tests/golden/make_golden.py, section 5): bit-exact, same order."""
+    for name, I, depth, thr, cell, want in _selection_cases():
+        got = O.select_points(I, len(want), thr, cell, cell, depth)
+        assert sum(len(zz) for _, zz in want) > 100
+        for (xy, zz), (xy_w, zz_w) in zip(got, want):
+            assert np.array_equal(xy, xy_w) and np.array_equal(zz, zz_w), name
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # directly against oracle/_ref (skipped where it is not built)
 # ----------------------------------------------------------------------------------------------------------------
@@ -287,3 +306,24 @@ def test_input_format_helpers(orc, synth):
     assert np.array_equal(orc.pyramid_down(I), synth.pyramid_down(I))
     g = synth.image_gradient(I)
     assert np.all(g[0] == 0) and np.all(g[-1] == 0) and np.all(g[:, 0] == 0) and np.all(g[:, -1] == 0)
+
+
+@pytest.mark.parametrize("thr,cell", [(25.0, (30, 30)), (5.0, (30, 30)), (0.5, (17, 23)), (60.0, (8, 8))])
+def test_oracle_matches_reference_point_selection(O, synth, thr, cell):
+    """Directly against the reference's detector (oracle/_ref/libmbavo_refselect.so): textured, ramp (ties), noise and flat
+    VGA images over 4 levels, the tracker's parameters (25, 30 x 30) and others; also the magnitude image itself."""
+    if not O.RefSelect.available():
+        pytest.skip("oracle/_ref/libmbavo_refselect.so not built (no /root/reference here)")
+    rs = O.RefSelect()
+    rng = np.random.default_rng(5)
+    H, W = 480, 640
+    images = [synth.make_config("C1").levels[0].ref_I, synth.ramp_image(H, W), rng.integers(0, 256, (H, W)).astype(np.uint8),
+              np.full((H, W), 77, np.uint8)]
+    for I in images:
+        depth = rng.uniform(0.0, 10.0, (H, W)).astype(np.float32)
+        depth[rng.random((H, W)) < 0.1] = 0.0
+        want, mag = rs.select_points(I, 4, thr, cell[0], cell[1], depth, want_mag=True)
+        got = O.select_points(I, 4, thr, cell[0], cell[1], depth)
+        assert np.array_equal(mag, O.gradient_magnitude(I))
+        for (xy, zz), (xy_w, zz_w) in zip(got, want):
+            assert np.array_equal(xy, xy_w) and np.array_equal(zz, zz_w)
