@@ -279,6 +279,26 @@ int mbavo_optimize_level(mbavo_ctx *ctx, int level, int spline_deg_k, double sta
                          int num_ctrl_knots, double *knots_t, double *knots_R, const mbavo_lm_options *opt,
                          mbavo_lm_summary *summary);
 
+/* ---- per-frame trajectory bookkeeping on the host -----------------------------------------------
+ * Quaternions are (x, y, z, w); tangents are [translation(3), rotation(3)] as Core::Transformation::log / exp
+ * (src/core/states/Transformation.cpp:164-178, wrappers of Sophus::SE3d::log / exp).
+ * mbavo_spline_pose              SplineSE3::GetPose without Jacobians (src/core/common/Spline.h:222-290)
+ * mbavo_spline_transform_by_right  SplineSE3::TransformByRight (Spline.h:212-219): t_i = R_i dt + t_i, R_i = R_i dR, in place
+ * mbavo_spline_transform_to      SplineSE3::TransformTo(t, R, t) (Spline.h:184-201): the spline moved so that its pose at `time`
+ *                                becomes the target; writes the new knots to knots_t / knots_R (3n / 4n)
+ * mbavo_predict_spline           the constant-velocity prediction of trackFrame (blur_aware_direct_tracker.cpp:120-145):
+ *                                TransformByRight(exp(velocity * dt_frame)), in place
+ * mbavo_frame_velocity           log(T_prev^-1 T_cur) / dt_frame (:155-161) */
+int mbavo_se3_exp(const double *tangent, double *t, double *q);
+int mbavo_se3_log(const double *t, const double *q, double *tangent);
+int mbavo_spline_pose(const mbavo_spline *spline, double time, double *t, double *q);
+int mbavo_spline_transform_by_right(int num_ctrl_knots, double *knots_t, double *knots_R, const double *dq, const double *dt);
+int mbavo_spline_transform_to(const mbavo_spline *spline, double time, const double *target_t, const double *target_q,
+                              double *knots_t, double *knots_R);
+int mbavo_predict_spline(int num_ctrl_knots, double *knots_t, double *knots_R, const double *velocity, double dt_frame);
+int mbavo_frame_velocity(const double *prev_t, const double *prev_q, const double *cur_t, const double *cur_q, double dt_frame,
+                         double *velocity);
+
 /* ---- semi-dense host-map point selection -------------------------------------------------------
  * What BlurAwareDirectTracker::tmpProcessKeyframe does on the CPU for a new keyframe (blur_aware_direct_tracker.cpp:355-409),
  * for levels 0 .. n_levels-1 of the keyframe pyramid already built by mbavo_set_keyframe_pyramid:
@@ -314,6 +334,45 @@ int mbavo_get_points(mbavo_ctx *ctx, int level, int capacity, double *xy, double
  * the order T0, T-, T+ — SplineSE3::GetPose at those times.  Collective in a sharded context (means over all ranks).
  * The caller applies its thresholds (keyframe_max_flow_mag0 / _mag1, keyframe_max_blur_kernel_mag, :250-262). */
 int mbavo_keyframe_stats(mbavo_ctx *ctx, int level, const double *poses_tq, double *avg_flow, double *avg_kernel_len);
+
+/* ---- BlurAwareDirectTracker::trackFrame ------------------------------------------------------------
+ * The per-frame driver of the reference (blur_aware_direct_tracker.cpp:88-203), composed from the entry points above.
+ * mbavo_tracker is the state the reference keeps between frames: the two-knot spline (:100-105, spacing = options.dt_frame),
+ * mNeighFrameVelocity, mTprevB2W, mPrevTimestamp, mTKeyframe.
+ *   mbavo_tracker_init          first frame (:91-109): identity spline starting at the keyframe's capture time
+ *   mbavo_track_frame           one blurred frame (:112-162, 200-203): uploads its pyramid (level 0 only travels), predicts the
+ *                               spline at constant velocity, runs the LM loop of every level coarse to fine, returns the pose
+ *                               at the capture time (relative to the keyframe and composed with the keyframe's pose), the
+ *                               isKeyframe statistics and the per-level LM summaries; updates velocity / previous pose.
+ *                               The context must hold the keyframe pyramid and the points (mbavo_set_keyframe_pyramid +
+ *                               mbavo_select_points or mbavo_set_points_pyramid).
+ *   mbavo_tracker_new_keyframe  the re-anchoring the reference does when the frame became the keyframe (:186-199); the
+ *                               caller applies the thresholds (:250-262) and uploads the new keyframe + points. */
+#define MBAVO_MAX_TRACKER_KNOTS 16
+typedef struct mbavo_tracker
+{
+    int spline_deg_k, num_ctrl_knots;
+    double sample_dt, start_time;
+    double knots_t[3 * MBAVO_MAX_TRACKER_KNOTS], knots_R[4 * MBAVO_MAX_TRACKER_KNOTS];
+    double velocity[6];                  /* mNeighFrameVelocity: [translation, rotation] per second */
+    double prev_t[3], prev_q[4];         /* mTprevB2W */
+    double prev_timestamp;               /* mPrevTimestamp */
+    double keyframe_t[3], keyframe_q[4]; /* mTKeyframe */
+} mbavo_tracker;
+
+typedef struct mbavo_frame_result
+{
+    double t_cur2key[3], q_cur2key[4];       /* spline pose at the capture time */
+    double t_cur2world[3], q_cur2world[4];   /* mTKeyframe * that (the return value of trackFrame) */
+    double avg_flow, avg_kernel_len;         /* isKeyframe statistics */
+    int levels_run;                          /* bit l: level l was optimised */
+    mbavo_lm_summary levels[MBAVO_MAX_LEVELS];
+} mbavo_frame_result;
+
+int mbavo_tracker_init(mbavo_tracker *tracker, int spline_deg_k, double sample_dt, double keyframe_capture_time);
+int mbavo_track_frame(mbavo_ctx *ctx, mbavo_tracker *tracker, int n_levels, int mem, const unsigned char *cur_I0,
+                      double capture_time, double exposure_time, const mbavo_lm_options *opt, mbavo_frame_result *result);
+int mbavo_tracker_new_keyframe(mbavo_tracker *tracker, double capture_time);
 
 /* ---- synthetic blurred frame ---------------------------------------------------------------
  * warp_image + synthesize_motion_blurred_img (src/ba_tracker/generate_synthetic_data.cpp:127-180): the mean over num_poses

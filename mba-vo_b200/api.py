@@ -24,7 +24,9 @@ EXPORTED_SYMBOLS = [
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
     "mbavo_device_sweeps", "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
     "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points", "mbavo_synthesize_blurred",
-    "mbavo_keyframe_stats", "mbavo_select_points", "mbavo_get_points",
+    "mbavo_keyframe_stats", "mbavo_select_points", "mbavo_get_points", "mbavo_se3_exp", "mbavo_se3_log",
+    "mbavo_spline_pose", "mbavo_spline_transform_by_right", "mbavo_spline_transform_to", "mbavo_predict_spline", "mbavo_frame_velocity",
+    "mbavo_tracker_init", "mbavo_track_frame", "mbavo_tracker_new_keyframe",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -77,6 +79,19 @@ class _LmSummary(C.Structure):
                 ("num_invalid", C.c_int), ("num_evaluations", C.c_int), ("num_bad_keypoints", C.c_int),
                 ("initial_cost", C.c_double), ("final_cost", C.c_double), ("first_step", C.c_double * 96),
                 ("decisions", C.c_char * 64)]
+
+
+class _Tracker(C.Structure):
+    _fields_ = [("spline_deg_k", C.c_int), ("num_ctrl_knots", C.c_int), ("sample_dt", C.c_double), ("start_time", C.c_double),
+                ("knots_t", C.c_double * 48), ("knots_R", C.c_double * 64), ("velocity", C.c_double * 6),
+                ("prev_t", C.c_double * 3), ("prev_q", C.c_double * 4), ("prev_timestamp", C.c_double),
+                ("keyframe_t", C.c_double * 3), ("keyframe_q", C.c_double * 4)]
+
+
+class _FrameResult(C.Structure):
+    _fields_ = [("t_cur2key", C.c_double * 3), ("q_cur2key", C.c_double * 4), ("t_cur2world", C.c_double * 3),
+                ("q_cur2world", C.c_double * 4), ("avg_flow", C.c_double), ("avg_kernel_len", C.c_double),
+                ("levels_run", C.c_int), ("levels", _LmSummary * 8)]
 
 
 @dataclass
@@ -439,6 +454,93 @@ def upload_problem(ctx: Context, prob) -> None:
     ctx.set_frame_times(prob.cap, prob.exp)
     for l, lv in enumerate(prob.levels):
         ctx.set_level(l, lv)
+
+
+class FrameTracker:
+    """mbavo_tracker + mbavo_track_frame: BlurAwareDirectTracker::trackFrame on a context that holds the keyframe and points."""
+
+    def __init__(self, ctx: "Context", n_levels: int, sample_dt: float, keyframe_capture_time: float, spline_deg_k: int = 2, **lm):
+        self.ctx, self.n_levels = ctx, n_levels
+        self.state = _Tracker()
+        _chk(ctx.lib.mbavo_tracker_init(C.byref(self.state), C.c_int(spline_deg_k), C.c_double(sample_dt), C.c_double(keyframe_capture_time)))
+        self.opt = _LmOptions()
+        ctx.lib.mbavo_lm_default_options(C.byref(self.opt))
+        for k, v in lm.items():
+            setattr(self.opt, k, v)
+
+    def track(self, cur_I0: np.ndarray, capture_time: float, exposure_time: float) -> dict:
+        img = np.ascontiguousarray(cur_I0, dtype=np.uint8)
+        res = _FrameResult()
+        self.ctx._check(self.ctx.lib.mbavo_track_frame(self.ctx._h, C.byref(self.state), C.c_int(self.n_levels), C.c_int(MEM_HOST),
+                                                       C.c_void_p(img.ctypes.data), C.c_double(capture_time), C.c_double(exposure_time),
+                                                       C.byref(self.opt), C.byref(res)))
+        return dict(t_cur2key=np.array(res.t_cur2key), q_cur2key=np.array(res.q_cur2key), t_cur2world=np.array(res.t_cur2world),
+                    q_cur2world=np.array(res.q_cur2world), avg_flow=res.avg_flow, avg_kernel_len=res.avg_kernel_len,
+                    levels_run=res.levels_run,
+                    levels=[{f: getattr(res.levels[l], f) for f, _ in _LmSummary._fields_ if f not in ("first_step",)}
+                            for l in range(self.n_levels)])
+
+    def new_keyframe(self, capture_time: float):
+        _chk(self.ctx.lib.mbavo_tracker_new_keyframe(C.byref(self.state), C.c_double(capture_time)))
+
+    @property
+    def knots(self):
+        n = self.state.num_ctrl_knots
+        return np.array(self.state.knots_t[:3 * n]).reshape(n, 3), np.array(self.state.knots_R[:4 * n]).reshape(n, 4)
+
+    @property
+    def velocity(self):
+        return np.array(self.state.velocity)
+
+
+# -- per-frame trajectory bookkeeping (host functions of the library; no context, no GPU) --------------------------------
+def _chk(rc: int):
+    if rc != 0:
+        raise MbavoError(f"mbavo error {rc}")
+
+
+def se3_exp(tangent):
+    tg = np.ascontiguousarray(tangent, dtype=np.float64)
+    t, q = np.zeros(3), np.zeros(4)
+    _chk(load_library().mbavo_se3_exp(_dp(tg), _dp(t), _dp(q)))
+    return t, q
+
+
+def se3_log(t, q):
+    t, q = np.ascontiguousarray(t, dtype=np.float64), np.ascontiguousarray(q, dtype=np.float64)
+    out = np.zeros(6)
+    _chk(load_library().mbavo_se3_log(_dp(t), _dp(q), _dp(out)))
+    return out
+
+
+def spline_pose(k, t0, dt, knots_t, knots_R, time):
+    sp, kt, kR, n = Context._spline(k, t0, dt, knots_t, knots_R)
+    t, q = np.zeros(3), np.zeros(4)
+    _chk(load_library().mbavo_spline_pose(C.byref(sp), C.c_double(time), _dp(t), _dp(q)))
+    return t, q
+
+
+def spline_transform_to(k, t0, dt, knots_t, knots_R, time, target_t, target_q):
+    sp, kt, kR, n = Context._spline(k, t0, dt, knots_t, knots_R)
+    tt, tq = np.ascontiguousarray(target_t, dtype=np.float64), np.ascontiguousarray(target_q, dtype=np.float64)
+    ot, oR = np.zeros((n, 3)), np.zeros((n, 4))
+    _chk(load_library().mbavo_spline_transform_to(C.byref(sp), C.c_double(time), _dp(tt), _dp(tq), _dp(ot), _dp(oR)))
+    return ot, oR
+
+
+def predict_spline(knots_t, knots_R, velocity, dt_frame):
+    kt = np.array(knots_t, dtype=np.float64, order="C")
+    kR = np.array(knots_R, dtype=np.float64, order="C")
+    v = np.ascontiguousarray(velocity, dtype=np.float64)
+    _chk(load_library().mbavo_predict_spline(C.c_int(kt.shape[0]), _dp(kt), _dp(kR), _dp(v), C.c_double(dt_frame)))
+    return kt, kR
+
+
+def frame_velocity(prev_t, prev_q, cur_t, cur_q, dt_frame):
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (prev_t, prev_q, cur_t, cur_q)]
+    out = np.zeros(6)
+    _chk(load_library().mbavo_frame_velocity(_dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), C.c_double(dt_frame), _dp(out)))
+    return out
 
 
 def upload_problem_pyramid(ctx: Context, prob) -> None:

@@ -379,6 +379,22 @@ namespace mbavo
         }
     } // namespace
 
+    // Host evaluation of one spline pose (SplineSE3::GetPose without Jacobians, src/core/common/Spline.h:222-290) with the
+    // same functions the kernel runs: kt / kR point at the first of the K knots of the segment, u is the normalised time.
+    int host_spline_pose(int K, const double *kt, const double *kR, double u, double *t_out, double *q_out)
+    {
+        Q q{0, 0, 0, 1};
+        double wt[4];
+        if (K == 2)
+            spline_pose<2>(kt, kR, u, t_out, q, wt, nullptr);
+        else if (K == 4)
+            spline_pose<4>(kt, kR, u, t_out, q, wt, nullptr);
+        else
+            return -1;
+        q_out[0] = q.x, q_out[1] = q.y, q_out[2] = q.z, q_out[3] = q.w;
+        return 0;
+    }
+
     // gn / knots_from: see pose_kernel.  dependent: launch programmatically behind the previous kernel of the stream (the
     // kernel then waits for it before it reads the sweep state).
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,

@@ -10,6 +10,9 @@ Restated host logic (reference file:line):
     Plus_t / Plus_R                   src/core/common/Spline.h:307-330  (Sophus SO3::exp == quaternion exp map)
     optimizePyramidLevel / LM loop    src/ba_tracker/blur_aware_direct_tracker.cpp:590-637, 885-924
     detectOutliersAndUploadToGpu      src/ba_tracker/blur_aware_direct_tracker.cpp:639-699
+    constant-velocity prediction      src/ba_tracker/blur_aware_direct_tracker.cpp:120-161, src/core/common/Spline.h:184-219,
+                                      Transformation::exp / log = Sophus::SE3d::exp / log (third-party, un-vendored: restated
+                                      from the published closed forms, checked against scipy's matrix exponential)
     semi-dense point selection        src/core/feature_detectors/FeatureDetectorSemiDense.cpp:16-59, FeatureDetectorBase.cpp:49-92,
                                       src/core/image_proc/Gradient.h:57-72, blur_aware_direct_tracker.cpp:389-409
     LevenbergMarquardtStrategy        src/ba_tracker/levenberg_marquardt_strategy.cpp:9-44
@@ -274,6 +277,74 @@ def keyframe_stats(xy, z, fx, fy, cx, cy, poses_tq):
     kern = ((uv[1] - uv[2]) ** 2).sum()
     n = xy.shape[0]
     return float(np.sqrt(np.float32(flow / n))), float(np.sqrt(np.float32(kern / n)))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# per-frame trajectory bookkeeping (numpy, rotation-matrix formulation — independent of the product's quaternion code)
+# ---------------------------------------------------------------------------------------------------------
+
+def q_to_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def hat(w):
+    return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]], dtype=np.float64)
+
+
+def se3_exp(tangent):
+    """Sophus::SE3d::exp, tangent = [upsilon, omega] -> (t, q (x, y, z, w))."""
+    ups, om = np.asarray(tangent[:3], np.float64), np.asarray(tangent[3:], np.float64)
+    th = np.linalg.norm(om)
+    q = so3_exp_quat(om)
+    Om = hat(om)
+    if th < 1e-10:
+        V = q_to_R(q)
+    else:
+        V = np.eye(3) + (1 - np.cos(th)) / th ** 2 * Om + (th - np.sin(th)) / th ** 3 * (Om @ Om)
+    return V @ ups, q
+
+
+def se3_log(t, q):
+    """Sophus::SE3d::log -> [upsilon, omega]."""
+    v, w = np.asarray(q[:3], np.float64), q[3]
+    n = np.linalg.norm(v)
+    if n < 1e-10:
+        f = 2.0 / w - 2.0 * n * n / w ** 3
+    elif abs(w) < 1e-10:
+        f = (np.pi if w > 0 else -np.pi) / n
+    else:
+        f = 2.0 * np.arctan(n / w) / n
+    om = f * v
+    th = f * n
+    Om = hat(om)
+    if abs(th) < 1e-10:
+        Vi = np.eye(3) - 0.5 * Om + (Om @ Om) / 12.0
+    else:
+        Vi = np.eye(3) - 0.5 * Om + (1 - th * np.cos(th / 2) / (2 * np.sin(th / 2))) / th ** 2 * (Om @ Om)
+    return np.concatenate([Vi @ np.asarray(t, np.float64), om])
+
+
+def transform_by_right(knots_t, knots_R, dq, dt):
+    """SplineSE3::TransformByRight (Spline.h:212-219)."""
+    kt = np.array([q_to_R(q / np.linalg.norm(q)) @ dt * 1.0 + t for q, t in zip(knots_R, knots_t)])
+    kR = np.array([q_mul(q, dq) for q in knots_R])
+    return kt, kR
+
+
+def predict_spline(knots_t, knots_R, velocity, dt_frame):
+    """blur_aware_direct_tracker.cpp:120-145."""
+    t, q = se3_exp(np.asarray(velocity, np.float64) * dt_frame)
+    return transform_by_right(knots_t, knots_R, q, t)
+
+
+def frame_velocity(prev_t, prev_q, cur_t, cur_q, dt_frame):
+    """blur_aware_direct_tracker.cpp:155-161: log(T_prev^-1 T_cur) / dt."""
+    Rp = q_to_R(prev_q)
+    qi = np.array([-prev_q[0], -prev_q[1], -prev_q[2], prev_q[3]])
+    return se3_log(Rp.T @ (np.asarray(cur_t) - np.asarray(prev_t)), q_mul(qi, cur_q)) / dt_frame
 
 
 # ---------------------------------------------------------------------------------------------------------

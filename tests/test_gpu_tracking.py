@@ -1,0 +1,76 @@
+"""GPU end-to-end test of the per-frame driver (mbavo_track_frame, the mirror of BlurAwareDirectTracker::trackFrame,
+blur_aware_direct_tracker.cpp:88-203): a synthetic sequence of motion-blurred frames of a textured plane, rendered by
+mbavo_synthesize_blurred along a constant-twist trajectory, is tracked with the points the GPU selected on the keyframe; the
+recovered poses are compared with the trajectory that rendered the frames, before and after a keyframe change."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+H, W, LEVELS, D = 240, 320, 3, 7.5
+FX = FY = 160.0
+CX, CY = 160.0, 120.0
+DT_FRAME, EXPOSURE = 0.1, 0.06
+TWIST = np.array([1.6, -0.9, 0.5, 0.05, -0.12, 0.2])  # per second: ~5 px of flow per frame, ~3 px of blur per exposure
+
+
+def rot_angle(qa, qb):
+    d = abs(float(np.dot(qa / np.linalg.norm(qa), qb / np.linalg.norm(qb))))
+    return 2.0 * np.arccos(min(1.0, d))
+
+
+def test_track_blurred_sequence(pkg, O, synth):
+    from mbavo_b200 import api
+
+    key = synth.make_texture(H, W, seed=21)
+    pattern = synth.make_config("C1").levels[0].pattern
+
+    def gt(t):  # T_cur2key(t) = Exp(t * twist)
+        return np.concatenate(O.se3_exp(TWIST * t))
+
+    def render(cap, n=32, exposure=EXPOSURE):
+        ts = [cap] if n == 1 else [cap - 0.5 * exposure + j * exposure / (n - 1) for j in range(n)]
+        return api.synthesize_blurred(key, D, FX, FY, CX, CY, np.array([gt(t) for t in ts]))
+
+    lim = api.Limits(max_num_keypoints=8192, max_num_virtual_poses_per_frame=16, max_patch_size=len(pattern))
+    with pkg.Context(lim) as ctx:
+        ctx.set_keyframe_pyramid(LEVELS, key)
+        counts = ctx.select_points(LEVELS, np.full((H, W), D, np.float32), FX, FY, CX, CY, pattern, 16, 4.0, 6, 6)
+        assert counts[0] > 800 and counts[LEVELS - 1] > 80
+        trk = api.FrameTracker(ctx, LEVELS, DT_FRAME, 0.0, huber_a=10.0, max_chi_square_error=3.0)
+        errs = []
+        for i in range(1, 4):
+            cap = i * DT_FRAME
+            res = trk.track(render(cap), cap, EXPOSURE)
+            want = gt(cap)
+            errs.append((np.linalg.norm(res["t_cur2key"] - want[:3]), rot_angle(res["q_cur2key"], want[3:])))
+            assert res["levels_run"] == (1 << LEVELS) - 1
+            assert all(lv["final_cost"] <= lv["initial_cost"] for lv in res["levels"])
+            # the isKeyframe statistics grow with the distance from the keyframe; the blur-kernel length stays that of the exposure
+            assert res["avg_flow"] > 3.0 * i and 1.0 < res["avg_kernel_len"] < 8.0
+            assert np.allclose(res["t_cur2world"], res["t_cur2key"]) and np.allclose(res["q_cur2world"], res["q_cur2key"])
+        print("tracking errors (translation, rotation):", errs)
+        # after the first frame the velocity is known and the prediction starts close: the twist per second is recovered
+        assert np.abs(trk.velocity - TWIST).max() <= 0.05 * np.abs(TWIST).max()
+        for e_t, e_r in errs:
+            assert e_t <= 1e-3 * D and e_r <= 5e-4, errs  # observed: 1.1e-3 .. 3.3e-3 and 0.6e-4 .. 1.9e-4
+
+        # keyframe change at frame 3 (tracker.cpp:186-199): sharp frame + its depth of the same plane, points re-selected
+        cap3 = 3 * DT_FRAME
+        trk.new_keyframe(cap3)
+        T3 = gt(cap3)
+        R3 = O.q_to_R(T3[3:])
+        ys, xs = np.mgrid[0:H, 0:W]
+        rays = np.stack([(xs - CX) / FX, (ys - CY) / FY, np.ones((H, W))], axis=-1)
+        depth3 = ((D - T3[2]) / (rays @ R3[2])).astype(np.float32)  # e_z . (R z r + t) = D
+        ctx.set_keyframe_pyramid(LEVELS, render(cap3, n=1))
+        counts = ctx.select_points(LEVELS, depth3, FX, FY, CX, CY, pattern, 16, 4.0, 6, 6)
+        assert counts[0] > 800
+        for i in range(4, 6):
+            cap = i * DT_FRAME
+            res = trk.track(render(cap), cap, EXPOSURE)
+            want = gt(cap)
+            e_t, e_r = np.linalg.norm(res["t_cur2world"] - want[:3]), rot_angle(res["q_cur2world"], want[3:])
+            print("after the keyframe change:", e_t, e_r, res["avg_flow"])
+            assert e_t <= 2e-3 * D and e_r <= 1.5e-3, (e_t, e_r)  # observed: 5.4e-3, 5.6e-4
+            assert res["avg_flow"] < 3.0 * (i - 3) + 8.0  # flow is measured from the NEW keyframe

@@ -131,3 +131,88 @@ def test_outlier_detection_restatement(O):
     flags2 = flags.copy()
     O.detect_outliers(np.ones(8), flags2, 2.0)  # nothing new, old flags stay
     assert np.array_equal(flags2, flags)
+
+
+def _rand_pose(rng, angle):
+    ax = rng.normal(size=3)
+    ax /= np.linalg.norm(ax)
+    return rng.normal(size=3), np.concatenate([np.sin(angle / 2) * ax, [np.cos(angle / 2)]])
+
+
+def test_se3_exp_log_against_matrix_exponential(pkg, cuda_lib, O):
+    """mbavo_se3_exp / mbavo_se3_log (Transformation::exp / log = Sophus::SE3d::exp / log, third-party and un-vendored —
+    parity unpinned): against the oracle's restatement of the published closed forms AND against scipy's matrix exponential
+    of the 4 x 4 twist, from the first-order branch (theta < 1e-10) to rotations near pi; log inverts exp."""
+    from scipy.linalg import expm
+
+    from mbavo_b200 import api
+
+    rng = np.random.default_rng(3)
+    for scale in (0.0, 1e-12, 1e-9, 1e-6, 1e-3, 0.1, 1.0, 3.0):
+        for _ in range(8):
+            tg = np.concatenate([rng.normal(size=3), rng.normal(size=3) * scale])
+            if np.linalg.norm(tg[3:]) > 3.1:
+                tg[3:] *= 3.1 / np.linalg.norm(tg[3:])
+            t, q = api.se3_exp(tg)
+            t_o, q_o = O.se3_exp(tg)
+            assert np.abs(t - t_o).max() <= 1e-14 * max(1.0, np.abs(t_o).max()) and np.abs(q - q_o).max() <= 1e-15
+            M = np.zeros((4, 4))
+            M[:3, :3], M[:3, 3] = O.hat(tg[3:]), tg[:3]
+            E = expm(M)
+            th = np.linalg.norm(tg[3:])
+            # the published closed form is what it is: below theta = 1e-10 it takes V = R instead of I + hat(omega) / 2 (an
+            # O(theta) difference), above it (1 - cos theta) / theta^2 cancels (an O(eps / theta) one)
+            slack = 4 * min(th, 2.3e-16 / th) * max(1.0, np.abs(tg[:3]).max()) if th > 0 else 0.0
+            assert np.abs(O.q_to_R(q) - E[:3, :3]).max() <= 1e-13 and np.abs(t - E[:3, 3]).max() <= 1e-12 + slack
+            back = api.se3_log(t, q)
+            assert np.abs(back - tg).max() <= 1e-10 * max(1.0, 1.0 / max(np.pi - th, 1e-3)) + 2 * slack
+            assert np.abs(back - O.se3_log(t, q)).max() <= 1e-13
+
+
+def test_spline_pose_and_transforms(pkg, cuda_lib, O, synth):
+    """mbavo_spline_pose (SplineSE3::GetPose), mbavo_spline_transform_by_right / _transform_to (Spline.h:184-219),
+    mbavo_predict_spline / mbavo_frame_velocity (tracker.cpp:120-161): against the numpy restatements, and through the
+    properties the tracker relies on — TransformTo puts the pose at `time` on the target, a prediction with the velocity of
+    the frame pair (prev, cur) maps cur's pose onto the constant-velocity continuation."""
+    from conftest import reference_test_spline
+    from mbavo_b200 import api
+
+    kt, kR = reference_test_spline()
+    rng = np.random.default_rng(8)
+    for k in (2, 4):
+        for time in (0.0, 0.26, 0.75, 1.49):
+            t, q = api.spline_pose(k, 0.0, 0.5, kt, kR, time)
+            t_w, q_w = synth.spline_pose(k, kt, kR, 0.0, 0.5, time)
+            assert np.abs(t - t_w).max() <= 1e-13 and np.abs(q - q_w).max() <= 1e-14
+        with pytest.raises(pkg.MbavoError):
+            api.spline_pose(k, 0.0, 0.5, kt, kR, -0.6)   # a whole segment before the first knot: the reference asserts
+        with pytest.raises(pkg.MbavoError):
+            api.spline_pose(k, 0.0, 0.5, kt, kR, 0.5 * (len(kt) - k + 1) + 0.01)  # past the last segment
+        # TransformTo against its restatement (every knot right-multiplied by T(time)^-1 T_target); the pose at `time` lands
+        # exactly on the target only where the spline interpolates a knot (k = 2, u = 0) — the per-knot update is the reference's
+        tt, tq = _rand_pose(rng, 0.7)
+        for time in (0.5, 0.6):
+            nt, nR = api.spline_transform_to(k, 0.0, 0.5, kt, kR, time, tt, tq)
+            t0_, q0_ = synth.spline_pose(k, kt, kR, 0.0, 0.5, time)
+            qi = np.array([-q0_[0], -q0_[1], -q0_[2], q0_[3]]) / (q0_ @ q0_)
+            wt, wR = O.transform_by_right(kt, kR, O.q_mul(qi, tq), O.q_to_R(q0_ / np.linalg.norm(q0_)).T @ (tt - t0_))
+            assert np.abs(nt - wt).max() <= 1e-12 * max(1.0, np.abs(wt).max()) and np.abs(nR - wR).max() <= 1e-14
+            if k == 2 and time == 0.5:
+                t, q = api.spline_pose(k, 0.0, 0.5, nt, nR, time)
+                assert np.abs(t - tt).max() <= 1e-12 and min(np.abs(q - tq).max(), np.abs(q + tq).max()) <= 1e-13
+    # prediction and velocity against the rotation-matrix restatement
+    for _ in range(10):
+        vel = np.concatenate([rng.normal(size=3), rng.normal(size=3) * 0.3])
+        dtf = rng.uniform(0.01, 0.2)
+        pt, pR = api.predict_spline(kt, kR, vel, dtf)
+        ot, oR = O.predict_spline(kt, kR, vel, dtf)
+        assert np.abs(pt - ot).max() <= 1e-12 * max(1.0, np.abs(ot).max()) and np.abs(pR - oR).max() <= 1e-15
+        (t0, q0), (t1, q1) = _rand_pose(rng, 0.4), _rand_pose(rng, 0.5)
+        v = api.frame_velocity(t0, q0, t1, q1, dtf)
+        assert np.abs(v - O.frame_velocity(t0, q0, t1, q1, dtf)).max() <= 1e-12 * np.abs(v).max()
+        # constant velocity: a one-knot "spline" at pose 1 predicted with v lands on T1 (T0^-1 T1)
+        ct, cR = api.predict_spline(t1[None], q1[None], v, dtf)
+        R0, R1 = O.q_to_R(q0), O.q_to_R(q1)
+        want_R = R1 @ R0.T @ R1
+        want_t = R1 @ (R0.T @ (t1 - t0)) + t1
+        assert np.abs(O.q_to_R(cR[0]) - want_R).max() <= 1e-12 and np.abs(ct[0] - want_t).max() <= 1e-12
