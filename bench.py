@@ -178,6 +178,7 @@ def run_own(args, pkg):
     import torch
     import torch.distributed as dist
 
+    from mbavo_b200 import api
     from mbavo_b200.api import Limits
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -366,6 +367,20 @@ def run_own(args, pkg):
                                      "accepted": int(sum(s_["num_accepted"] for s_ in summ)),
                                      "final_cost_level0": float(summ[-1]["final_cost"]),
                                      "gn_iters_per_s": sum(s_["num_iterations"] for s_ in summ) / t_lm}
+    # New-keyframe set-up on the same keyframe (SURVEY §8f ranks 2 + 4, not part of the timed steps): level-0 image and depth map
+    # from pinned host memory -> pyramid, gradients, texels, semi-dense point selection, all on the GPU; wall clock
+    if world == 1:
+        lv0 = prob.levels[0]
+        depth = np.full((lv0.H, lv0.W), 7.5, dtype=np.float32)
+        with pkg.Context(api.limits_for(prob)) as kctx:
+            for it in range(13):
+                if it == 3:
+                    t_kf = time.perf_counter()
+                kctx.set_keyframe_pyramid(len(prob.levels), lv0.ref_I)
+                sel_counts = kctx.select_points(len(prob.levels), depth, lv0.fx, lv0.fy, lv0.cx, lv0.cy, lv0.pattern, lv0.N, 25.0, 30, 30)
+            t_kf = (time.perf_counter() - t_kf) / 10
+        line["keyframe_setup"] = {"ms": t_kf * 1e3, "points_selected": sel_counts,
+                                  "what": "mbavo_set_keyframe_pyramid + mbavo_select_points (threshold 25, cells 30 x 30), host image + depth in"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
 
@@ -386,6 +401,12 @@ def run_own(args, pkg):
         t_lm = time.perf_counter() - t_lm
         line["cpu_baseline"]["lm_to_convergence_ms"] = t_lm * 1e3
         line["cpu_baseline"]["lm_iterations"] = int(sum(len(tr.decisions) for tr in traces))
+        if O.RefSelect.available():  # the reference's own pyramid + gradient + detector loops on one host core
+            rs = O.RefSelect()
+            t_kf = time.perf_counter()
+            for _ in range(5):
+                rs.select_points(cprob.levels[0].ref_I, len(cprob.levels), 25.0, 30, 30, depth, max_points=4096)
+            line["cpu_baseline"]["keyframe_setup_ms"] = (time.perf_counter() - t_kf) / 5 * 1e3
     if rank == 0:
         print(json.dumps(line), flush=True)
     ctx.close()
