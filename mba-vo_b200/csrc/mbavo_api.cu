@@ -1165,6 +1165,8 @@ extern "C"
             {
                 const int base = n / ctx->shard.world, rem = n % ctx->shard.world, r = ctx->shard.rank;
                 lo = r * base + (r < rem ? r : rem), hi = lo + base + (r < rem ? 1 : 0);
+                if (n < ctx->shard.world)
+                    lo = hi = 0; // fewer points than ranks: the level is empty on EVERY rank (a collective needs them all)
                 ctx->points_global[l] = n;
             }
             const double scale = (double)(1 << l); // tracker.cpp:765-771

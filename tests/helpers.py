@@ -52,3 +52,26 @@ def delta_gate(O, H_ref, g_ref, base=1e-4, ulp=6e-8, trials=8, seed=0):
         gn = g_ref * (1 + ulp * rng.standard_normal(g_ref.shape))
         errs.append(rel(first_step(O, Hn, gn), d))
     return max(base, 3.0 * float(np.median(errs)))
+
+
+def run_ranks(fns):
+    """Run one callable per rank concurrently (ctypes releases the GIL while a rank spins inside a collective call)."""
+    import threading
+
+    out, err = [None] * len(fns), [None] * len(fns)
+
+    def body(i):
+        try:
+            out[i] = fns[i]()
+        except BaseException as e:  # noqa: BLE001
+            err[i] = e
+
+    th = [threading.Thread(target=body, args=(i,)) for i in range(len(fns))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    for e in err:
+        if e is not None:
+            raise e
+    return out

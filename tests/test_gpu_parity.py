@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 from helpers import delta_gate, first_step, golden, max_rel, problem_from_golden, rel
+from helpers import run_ranks as _run_ranks
 
 pytestmark = pytest.mark.gpu
 
@@ -449,29 +450,6 @@ def test_sharded_evaluator_single_rank(pkg, api, synth):
         c2, _, _ = ev.evaluate(0, prob.knots_t, prob.knots_R, False)
     assert c == want[0] and np.array_equal(H, want[1]) and np.array_equal(g, want[2])
     assert abs(c2 - c) <= 1e-6 * c  # the cost-only pass blends byte taps, the Hessian pass fp16 texels: same values, other FMA order
-
-
-def _run_ranks(fns):
-    """Run one callable per rank concurrently (ctypes releases the GIL while a rank spins inside a collective call)."""
-    import threading
-
-    out, err = [None] * len(fns), [None] * len(fns)
-
-    def body(i):
-        try:
-            out[i] = fns[i]()
-        except BaseException as e:  # noqa: BLE001
-            err[i] = e
-
-    th = [threading.Thread(target=body, args=(i,)) for i in range(len(fns))]
-    for t in th:
-        t.start()
-    for t in th:
-        t.join(timeout=120)
-    for e in err:
-        if e is not None:
-            raise e
-    return out
 
 
 @pytest.mark.parametrize("world", [2, 3])

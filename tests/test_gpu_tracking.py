@@ -5,6 +5,8 @@ recovered poses are compared with the trajectory that rendered the frames, befor
 import numpy as np
 import pytest
 
+from helpers import run_ranks
+
 pytestmark = pytest.mark.gpu
 
 H, W, LEVELS, D = 240, 320, 3, 7.5
@@ -74,3 +76,53 @@ def test_track_blurred_sequence(pkg, O, synth):
             print("after the keyframe change:", e_t, e_r, res["avg_flow"])
             assert e_t <= 2e-3 * D and e_r <= 1.5e-3, (e_t, e_r)  # observed: 5.4e-3, 5.6e-4
             assert res["avg_flow"] < 3.0 * (i - 3) + 8.0  # flow is measured from the NEW keyframe
+
+
+def test_track_blurred_sequence_point_sharded(pkg, O, synth):
+    """The same driver on a point-sharded tracker: two ranks (contexts on this GPU, one thread each) select the same points,
+    keep their contiguous block, and track collectively — identical poses on both ranks, equal to the single-context run up to
+    the summation order."""
+    from mbavo_b200 import api
+
+    key = synth.make_texture(H, W, seed=21)
+    pattern = synth.make_config("C1").levels[0].pattern
+    depth = np.full((H, W), D, np.float32)
+
+    def gt(t):
+        return np.concatenate(O.se3_exp(TWIST * t))
+
+    frames = []
+    for i in (1, 2):
+        cap = i * DT_FRAME
+        ts = [cap - 0.5 * EXPOSURE + j * EXPOSURE / 31 for j in range(32)]
+        frames.append((cap, api.synthesize_blurred(key, D, FX, FY, CX, CY, np.array([gt(t) for t in ts]))))
+    lim = api.Limits(max_num_keypoints=8192, max_num_virtual_poses_per_frame=16, max_patch_size=len(pattern))
+
+    def run(ctx):
+        counts = ctx.select_points(LEVELS, depth, FX, FY, CX, CY, pattern, 16, 4.0, 6, 6)
+        trk = api.FrameTracker(ctx, LEVELS, DT_FRAME, 0.0, huber_a=10.0, max_chi_square_error=3.0)
+        return counts, [trk.track(img, cap, EXPOSURE) for cap, img in frames], [ctx.get_points(l)[0].shape[0] for l in range(LEVELS)]
+
+    with pkg.Context(lim) as solo:
+        solo.set_keyframe_pyramid(LEVELS, key)
+        counts1, res1, held1 = run(solo)
+    assert held1 == counts1
+    ctxs = [pkg.Context(lim) for _ in range(2)]
+    try:
+        for c in ctxs:
+            c.set_keyframe_pyramid(LEVELS, key)
+        ptrs = [c.shard_export()[1] for c in ctxs]
+        for r, c in enumerate(ctxs):
+            c.shard_connect(2, r, mailbox_ptrs=ptrs)
+        out = run_ranks([lambda c=c: run(c) for c in ctxs])
+    finally:
+        for c in ctxs:
+            c.close()
+    (ca, ra, ha), (cb, rb, hb) = out
+    assert ca == counts1 and cb == counts1 and [x + y for x, y in zip(ha, hb)] == counts1  # the blocks partition the selection
+    for f in range(2):
+        for key_ in ("t_cur2key", "q_cur2key"):
+            assert np.array_equal(ra[f][key_], rb[f][key_])
+            assert np.abs(ra[f][key_] - res1[f][key_]).max() <= 1e-5
+        assert ra[f]["avg_flow"] == rb[f]["avg_flow"] and abs(ra[f]["avg_flow"] - res1[f]["avg_flow"]) <= 1e-4 * res1[f]["avg_flow"]
+        assert [lv["decisions"] for lv in ra[f]["levels"]] == [lv["decisions"] for lv in res1[f]["levels"]]
