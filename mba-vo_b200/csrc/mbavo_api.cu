@@ -1154,11 +1154,18 @@ extern "C"
         CUDA_TRY(cudaStreamSynchronize(s));
         for (int l = 0; l < n_levels; ++l)
         {
+            num_selected[l] = ctx->sel_count_host[l];
+            if (num_selected[l] > cap) // nothing is kept: the points of every level are void
+            {
+                for (int k = 0; k < n_levels; ++k)
+                    ctx->levels[k].has_pts = false, pyramid_level_ready(ctx->levels[k]);
+                return fail(MBAVO_ECAPACITY, "level %d: %d points selected, max_num_keypoints is %d", l, num_selected[l], cap);
+            }
+        }
+        for (int l = 0; l < n_levels; ++l)
+        {
             LevelStore &L = ctx->levels[l];
-            const int n = ctx->sel_count_host[l];
-            num_selected[l] = n;
-            if (n > cap)
-                return fail(MBAVO_ECAPACITY, "level %d: %d points selected, max_num_keypoints is %d", l, n, cap);
+            const int n = num_selected[l];
             // a sharded context keeps its contiguous block of the selection (every rank selects the same points)
             int lo = 0, hi = n;
             if (ctx->shard.world > 1)

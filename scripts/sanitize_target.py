@@ -1,6 +1,6 @@
 """Target for compute-sanitizer (memcheck / racecheck / initcheck / synccheck): every kernel of the library on small inputs —
 pack, pyramid, pose, tracking (Hessian + cost, texel and direct-gather variants, ragged shapes, borders, k = 4, multi-segment),
-outlier statistics, and a two-rank sharded evaluation on one device.   usage: python scripts/sanitize_target.py"""
+outlier and keyframe statistics, point selection, the per-frame driver, and a two-rank sharded evaluation on one device.   usage: python scripts/sanitize_target.py"""
 import os
 import sys
 import threading
@@ -55,6 +55,22 @@ del os.environ["MBAVO_PHASES"]
 img = api.synthesize_blurred(probs[0].levels[0].ref_I, 7.5, 48.0, 48.0, 48.0, 32.0,
                              np.array([[0.01 * i, 0.0, 0.0, 0.0, 0.0, 0.001 * i, 1.0] for i in range(6)]))
 print("synth ok", int(img.sum()), flush=True)
+
+# semi-dense point selection (odd image sizes: partial last cells, odd pyramid sizes) and the per-frame driver on the selection
+key = synth.make_texture(122, 162, seed=4)
+pat = probs[0].levels[0].pattern
+with pkg.Context(api.Limits(max_num_keypoints=4096, max_num_virtual_poses_per_frame=8, max_patch_size=len(pat))) as ctx:
+    ctx.set_keyframe_pyramid(3, key)
+    depth = np.full(key.shape, 7.5, np.float32)
+    depth[::7, ::5] = 0.0
+    for thr, ch, cw in ((4.0, 6, 6), (0.5, 17, 23), (25.0, 30, 30), (300.0, 6, 6)):
+        counts = ctx.select_points(3, depth, 81.0, 81.0, 81.0, 61.0, pat, 8, thr, ch, cw)
+        print("select ok", thr, counts, [ctx.get_points(l)[0].shape[0] for l in range(3)], flush=True)
+    ctx.select_points(3, depth, 81.0, 81.0, 81.0, 61.0, pat, 8, 2.0, 5, 5)
+    trk = api.FrameTracker(ctx, 3, 0.1, 0.0, huber_a=10.0, max_chi_square_error=3.0)
+    poses = np.array([[0.02 * i, -0.01 * i, 0.0, 0.0, 0.0, 0.0005 * i, 1.0] for i in range(8)])
+    res = trk.track(api.synthesize_blurred(key, 7.5, 81.0, 81.0, 81.0, 61.0, poses), 0.1, 0.05)
+    print("track ok", res["t_cur2key"], res["levels_run"], flush=True)
 
 # two ranks on one device
 prob = probs[0]
