@@ -18,7 +18,8 @@
 namespace mbavo
 {
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
-                                   double *mid, int *seg_end, cudaStream_t stream, GnState *gn, int knots_from, bool dependent);
+                                   double *mid, int *seg_end, cudaStream_t stream, GnState *gn, int knots_from, bool dependent,
+                                   int buf_select, int samples_stride, int mid_stride, int seg_end_stride);
     cudaError_t launch_track_kernel(int K, int NK, bool with_j, bool big, const TrackParams &prm, dim3 grid, size_t smem,
                                     cudaStream_t stream, int *query_occupancy, bool dependent);
     size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool big, int N, int S, int TP);
@@ -120,6 +121,7 @@ struct mbavo_ctx
     unsigned long long shard_seq = 0, aux_seq = 0;
     int points_global[MBAVO_MAX_LEVELS] = {};
     float *samples = nullptr;
+    int samples_stride = 0;  // floats from record buffer A to record buffer B
     double *mid = nullptr;
     int *seg_end = nullptr;
     double *block_partials = nullptr;
@@ -457,6 +459,9 @@ namespace
         GnParams gn{};          // gn.state == nullptr: plain evaluation
         int knots_from = 0;     // pose kernel: 0 launch parameter, 1 state->cur, 2 state->cand
         bool first = false;     // first launch of the sweep: its pose kernel is not launched programmatically
+        bool skip_pose = false; // the records this evaluation needs are already in a buffer (BufSelect below)
+        bool pose_with_j = false; // candidate records computed with Jacobians: the next level may stand on them
+        int buf_select = kBufA; // record buffer the pose kernel writes and the tracking kernel reads
     };
 
     int run_evaluation(mbavo_ctx *ctx, int level, const EvalPlan &pl, double *packed_dev_out, bool blocking, double inv_num_residuals,
@@ -474,14 +479,23 @@ namespace
             ctx->block_partials_cap = need;
         }
         L.last_eval_frames = pl.F;
-        ctx->launches += 2;
-        CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, pl.with_h ? 1 : 0, ctx->samples, ctx->mid, ctx->seg_end, s,
-                                    sweep ? sweep->gn.state : nullptr, sweep ? sweep->knots_from : 0, sweep && !sweep->first));
+        const int buf_select = sweep ? sweep->buf_select : (int)kBufA;
+        if (!(sweep && sweep->skip_pose))
+        {
+            ctx->launches += 1;
+            CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, (pl.with_h || (sweep && sweep->pose_with_j)) ? 1 : 0, ctx->samples,
+                                        ctx->mid, ctx->seg_end, s, sweep ? sweep->gn.state : nullptr, sweep ? sweep->knots_from : 0,
+                                        sweep && !sweep->first, buf_select, ctx->samples_stride, kMidDoubles * kMaxFrames,
+                                        kMaxSegments * kMaxFrames));
+        }
+        ctx->launches += 1;
         TrackParams prm{};
         prm.lv = L.dev;
         prm.samples = ctx->samples;
         prm.mid = ctx->mid;
         prm.seg_end = ctx->seg_end;
+        prm.buf_select = buf_select;
+        prm.samples_stride = ctx->samples_stride, prm.mid_stride = kMidDoubles * kMaxFrames, prm.seg_end_stride = kMaxSegments * kMaxFrames;
         prm.inv_num_residuals = inv_num_residuals;
         prm.huber_a = (float)huber_a;
         prm.TP = pl.TP;
@@ -585,9 +599,11 @@ extern "C"
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         ctx->stream = ctx->own_stream;
         const size_t nsamp = (size_t)lim->max_num_frames * lim->max_num_virtual_poses_per_frame;
-        CUDA_TRY(cudaMalloc(&ctx->samples, nsamp * sample_rec_floats(4) * sizeof(float)));
-        CUDA_TRY(cudaMalloc(&ctx->mid, sizeof(double) * kMidDoubles * kMaxFrames));
-        CUDA_TRY(cudaMalloc(&ctx->seg_end, sizeof(int) * kMaxSegments * kMaxFrames));
+        // two record buffers each (A, B): see BufSelect
+        ctx->samples_stride = (int)(nsamp * sample_rec_floats(4));
+        CUDA_TRY(cudaMalloc(&ctx->samples, 2 * nsamp * sample_rec_floats(4) * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&ctx->mid, 2 * sizeof(double) * kMidDoubles * kMaxFrames));
+        CUDA_TRY(cudaMalloc(&ctx->seg_end, 2 * sizeof(int) * kMaxSegments * kMaxFrames));
         CUDA_TRY(cudaMalloc(&ctx->counter, sizeof(unsigned int)));
         CUDA_TRY(cudaMemset(ctx->counter, 0, sizeof(unsigned int)));
         const int emax = packed_len(MBAVO_MAX_KNOT_WINDOW);
@@ -1387,6 +1403,13 @@ extern "C"
         }
         mbavo_spline sp{k, t0, dt, n, knots_t, knots_R};
         unsigned long long seq_of_level[MBAVO_MAX_LEVELS] = {};
+        // The sample records depend on the knots, the frame times and the number of exposure samples only — not on the level.
+        // When every level of the sweep uses the same sample count, a level after the first finds the records of its knots in
+        // one of the two buffers (the previous level's, or its committed candidate's) and runs no pose kernel of its own.
+        bool reuse = nlev > 1;
+        for (int li = 1; li < nlev && reuse; ++li)
+            reuse = ctx->levels[level_coarse - li].set && ctx->levels[level_coarse].set &&
+                    ctx->levels[level_coarse - li].dev.N == ctx->levels[level_coarse].dev.N;
         for (int li = 0; li < nlev; ++li)
         {
             const int level = level_coarse - li;
@@ -1409,6 +1432,15 @@ extern "C"
                 sw.gn.radius = radius;
                 sw.knots_from = pass == 1 ? 2 : (li == 0 ? 0 : 1);
                 sw.first = li == 0 && pass == 0;
+                if (reuse)
+                {
+                    sw.skip_pose = pass == 0 && li > 0;
+                    sw.pose_with_j = pass == 1 && li < nlev - 1;
+                    if (chain) // the buffer roles swap whenever a candidate is committed: read the state on the device
+                        sw.buf_select = pass == 0 ? (li == 0 ? kBufA : kBufCur) : kBufCand;
+                    else
+                        sw.buf_select = pass == 0 ? kBufA : kBufB;
+                }
                 rc = run_evaluation(ctx, level, pl, ctx->packed_dev, true, 1.0 / (double)nres, huber_a, &sw);
                 if (rc != MBAVO_OK)
                     return rc;

@@ -181,7 +181,17 @@ namespace mbavo
         double step[6 * 16];                   // first LM step of the level in flight, full ordering [dt(3n), dw(3n)]
         double cost, cand_cost, model;
         int status;                            // 0 ok, 1 normal equations not safely positive definite, 2 model decrease < 0
-        int pad_;
+        int cur_buf;                           // which of the two sample-record buffers holds the records of cur_t / cur_R
+    };
+    // Sample records of a sweep live in two buffers (A at the base pointers, B one stride further): one holds the records of
+    // the knots the sweep stands on, the other those of the candidate, so that a level whose knots did not change (or became
+    // the candidate) finds its records already there instead of running the pose kernel again.
+    enum BufSelect : int
+    {
+        kBufA = 0,        // static: buffer A (plain evaluations; sweeps that never commit keep their knots in A)
+        kBufCur = 1,      // dynamic: state->cur_buf
+        kBufCand = 2,     // dynamic: 1 - state->cur_buf
+        kBufB = 3         // static: buffer B
     };
     struct GnParams
     {
@@ -200,6 +210,8 @@ namespace mbavo
         const float *samples;     // [F * N * rec] sample records
         const double *mid;        // [F * kMidDoubles]
         const int *seg_end;       // [F * kMaxSegments]: one past the last sample index of every segment offset
+        int buf_select;           // BufSelect: which record buffer this launch reads
+        int samples_stride, mid_stride, seg_end_stride; // element offsets of buffer B
         double inv_num_residuals; // 1 / ((P - num_bad) F S)            spline_update_step.cpp:116-117
         float huber_a;
         int TP;                   // points per warp batch

@@ -351,7 +351,8 @@ namespace mbavo
         // initialised from it), 1 = gn->cur_*, 2 = gn->cand_* (device-resident Gauss-Newton sweep).
         template <int K>
         __global__ void pose_kernel(const __grid_constant__ EvalStage stage, int with_jacobian, float *__restrict__ samples,
-                                    double *__restrict__ mid, int *__restrict__ seg_end, GnState *gn, int knots_from)
+                                    double *__restrict__ mid, int *__restrict__ seg_end, GnState *gn, int knots_from, int buf_select,
+                                    int samples_stride, int mid_stride, int seg_end_stride)
         {
             cudaTriggerProgrammaticLaunchCompletion(); // the tracking kernel may start its prologue now
             const double *kt = stage.knots_t, *kR = stage.knots_R;
@@ -370,9 +371,13 @@ namespace mbavo
                     for (int e = threadIdx.x; e < 4 * stage.n_knots; e += blockDim.x)
                         gn->cur_R[e] = stage.knots_R[e];
                     if (threadIdx.x == 0)
-                        gn->status = 0;
+                        gn->status = 0, gn->cur_buf = 0;
                 }
             }
+            int buf = buf_select == kBufB ? 1 : 0;
+            if (buf_select == kBufCur || buf_select == kBufCand)
+                buf = buf_select == kBufCur ? gn->cur_buf : 1 - gn->cur_buf;
+            samples += (size_t)buf * samples_stride, mid += (size_t)buf * mid_stride, seg_end += (size_t)buf * seg_end_stride;
             const int g = blockIdx.x * blockDim.x + threadIdx.x;
             if (g < stage.N * stage.F)
                 pose_one<K>(&stage, kt, kR, g, with_jacobian, samples, mid, seg_end);
@@ -398,7 +403,8 @@ namespace mbavo
     // gn / knots_from: see pose_kernel.  dependent: launch programmatically behind the previous kernel of the stream (the
     // kernel then waits for it before it reads the sweep state).
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
-                                   double *mid, int *seg_end, cudaStream_t stream, GnState *gn, int knots_from, bool dependent)
+                                   double *mid, int *seg_end, cudaStream_t stream, GnState *gn, int knots_from, bool dependent,
+                                   int buf_select, int samples_stride, int mid_stride, int seg_end_stride)
     {
         const int threads = 64;
         const int blocks = (total_samples + threads - 1) / threads;
@@ -409,7 +415,9 @@ namespace mbavo
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr, cfg.numAttrs = (dependent && gn) ? 1 : 0;
         if (K == 2)
-            return cudaLaunchKernelEx(&cfg, pose_kernel<2>, stage, with_jacobian, samples, mid, seg_end, gn, knots_from);
-        return cudaLaunchKernelEx(&cfg, pose_kernel<4>, stage, with_jacobian, samples, mid, seg_end, gn, knots_from);
+            return cudaLaunchKernelEx(&cfg, pose_kernel<2>, stage, with_jacobian, samples, mid, seg_end, gn, knots_from, buf_select, samples_stride,
+                                      mid_stride, seg_end_stride);
+        return cudaLaunchKernelEx(&cfg, pose_kernel<4>, stage, with_jacobian, samples, mid, seg_end, gn, knots_from, buf_select, samples_stride,
+                                  mid_stride, seg_end_stride);
     }
 } // namespace mbavo

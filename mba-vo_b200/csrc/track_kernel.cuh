@@ -553,12 +553,21 @@ namespace mbavo
             MBAVO_STAMP(1);
             cudaGridDependencySynchronize();
             MBAVO_STAMP(2);
+            int buf = prm.buf_select == kBufB ? 1 : 0;
+            if (prm.buf_select == kBufCur || prm.buf_select == kBufCand)
+            {
+                const int cb = __ldcg(&prm.gn.state->cur_buf);
+                buf = prm.buf_select == kBufCur ? cb : 1 - cb;
+            }
+            const float *samples_g = prm.samples + (size_t)buf * prm.samples_stride;
+            const int *seg_end_g = prm.seg_end + (size_t)buf * prm.seg_end_stride;
+            const double *mid_g = prm.mid + (size_t)buf * prm.mid_stride;
             for (int e = threadIdx.x; e < N * REC; e += blockDim.x)
-                samples_s[e] = prm.samples[(size_t)f * N * REC + e];
+                samples_s[e] = samples_g[(size_t)f * N * REC + e];
             if (threadIdx.x < kMaxSegments)
-                seg_end_s[threadIdx.x] = prm.seg_end[f * kMaxSegments + threadIdx.x];
+                seg_end_s[threadIdx.x] = seg_end_g[f * kMaxSegments + threadIdx.x];
             if (threadIdx.x < kMidDoubles)
-                mid_s[threadIdx.x] = prm.mid[f * kMidDoubles + threadIdx.x];
+                mid_s[threadIdx.x] = mid_g[f * kMidDoubles + threadIdx.x];
             __syncthreads();
 
             MBAVO_STAMP(3);
@@ -893,6 +902,7 @@ namespace mbavo
                             st->cur_t[e] = st->cand_t[e];
                         for (int e = 0; e < 4 * gp.n_knots; ++e)
                             st->cur_R[e] = st->cand_R[e];
+                        st->cur_buf ^= 1; // the candidate's sample records are now those of the knots the sweep stands on
                     }
                     if (gp.last && prm.host_out)
                     {

@@ -564,6 +564,36 @@ def test_device_resident_sweep_matches_host_path(pkg, api, synth, monkeypatch, n
     assert dev[3] == 2 and host[3] == 0, (dev[3], dev[4])  # the device-resident path really ran
 
 
+@pytest.mark.parametrize("seed,mixed_n", [(2, False), (3, False), (3, True)])
+def test_device_sweep_rejected_levels_and_record_reuse(pkg, api, synth, monkeypatch, seed, mixed_n):
+    """A chained sweep in which some level's candidate is REJECTED (the sweep keeps standing on its knots) and others are
+    committed: the levels after the first find the sample records of their knots in one of the two record buffers instead of
+    running a pose kernel — whichever buffer that is after the commits so far.  With a different number of exposure samples on
+    one level the records cannot be shared and every level computes its own.  Both against the evaluation-by-evaluation form."""
+    prob = synth.make_problem("rej", W=160, H=120, levels=3, P0=600, N=8, n_knots=2, k=2, seed=100 + seed, margin=16)
+    kt = prob.knots_t + np.random.default_rng(seed).normal(size=prob.knots_t.shape) * 2e-2
+    if mixed_n:
+        prob.levels[1].N = 5
+
+    def sweep():
+        with pkg.Context(api.limits_for(prob)) as ctx:
+            api.upload_problem(ctx, prob)
+            l0 = ctx.kernel_launches()
+            out = ctx.gn_sweep(2, 0, prob.k, prob.t0, prob.dt, kt, prob.knots_R, prob.huber_a, 1e4, chain=True)
+            return out + (ctx.device_sweeps(), ctx.kernel_launches() - l0)
+
+    dev = sweep()
+    monkeypatch.setenv("MBAVO_NO_DEVICE_SWEEP", "1")
+    host = sweep()
+    assert dev[3] == 1 and host[3] == 0
+    assert dev[4] == (12 if mixed_n else 10) and host[4] == 12  # 6 tracking kernels + 6 pose kernels, or 4 with shared records
+    assert np.abs(dev[0] - host[0]).max() <= 1e-9 * np.abs(host[0]).max(), (dev[0], host[0])
+    assert np.abs(dev[1] - host[1]).max() <= 1e-9 and np.abs(dev[2] - host[2]).max() <= 1e-9
+    decisions = "".join("A" if cand < cost else "R" for cost, cand in dev[0])
+    if not mixed_n:
+        assert decisions == {2: "AAR", 3: "RAA"}[seed], decisions  # (predicted with the oracle on the CPU)
+
+
 def test_device_sweep_with_unobserved_knots(pkg, api, O, orc, synth, monkeypatch):
     """A spline with a control knot that no exposure sample touches: the normal equations are singular in that knot.  The
     host path solves them by the pseudo-inverse (zero step on the unobserved knot); the device-resident sweep solves the
