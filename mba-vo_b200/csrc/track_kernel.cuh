@@ -336,9 +336,90 @@ namespace mbavo
         // = knots [+] step.  Knots outside the window keep a zero step (what the pseudo-inverse of the full system gives).
         // A (2 D x D) and w (3 D) are shared-memory scratch.  Executed by ONE warp; right-looking factorisation so that every
         // step is a handful of parallel FMAs instead of long serial dot products.
-        template <int NK>
-        __device__ void gn_solve_step(const double *__restrict__ v, const GnParams &gp, double *__restrict__ A, double *__restrict__ w)
+        // fp64 reciprocal for the pivots: float seed (24 bits) + two Newton steps in FMA form (error at the fp64 rounding
+        // level); an IEEE division costs about twice the latency and the factorisation is a chain of D of them
+        __device__ __forceinline__ double rcp_newton(double d)
         {
+            double r = (double)(1.0f / (float)d);
+            r = fma(r, fma(-d, r, 1.0), r);
+            r = fma(r, fma(-d, r, 1.0), r);
+            return r;
+        }
+
+        // Register-resident LDL^T solve of the damped window system for D = 6 NK <= 32: lane i owns row i of the lower
+        // triangle, columns are exchanged by warp shuffles, every loop is unrolled at compile time.  On return y (shared)
+        // holds H^-1 g; *ok_out tells whether every pivot passed the host's test.  Executed by one warp.
+        template <int D>
+        __device__ __noinline__ void ldlt_solve_regs(const double *__restrict__ Hd, const double *__restrict__ g,
+                                                     double *__restrict__ Ls, double *__restrict__ y, bool *ok_out)
+        {
+            const int lane = threadIdx.x & 31;
+            const int row = lane < D ? lane : D - 1; // lanes >= D shadow the last row (their results are ignored)
+            double a[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c)
+                a[c] = Hd[row * D + c];
+            bool ok = true;
+            double dmax = 0.0, yi = g[row], idiag = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+            {
+                const double d = __shfl_sync(0xffffffffu, a[j], j);
+                dmax = d > dmax ? d : dmax;
+                if (!(d > 1e-9 * dmax))
+                    ok = false;
+                const double id = rcp_newton(d);
+                const double aj = a[j];           // A(row, j) before scaling
+                const double l = aj * id;         // L(row, j)
+#pragma unroll
+                for (int k = j + 1; k < D; ++k)
+                {
+                    const double akj = __shfl_sync(0xffffffffu, aj, k); // A(k, j) before scaling
+                    a[k] -= l * akj;              // A(row, k) -= L(row, j) d_j L(k, j)   (only row >= k is used later)
+                }
+                if (row > j)
+                    a[j] = l;
+                if (row == j)
+                    idiag = id;
+            }
+            // L to shared memory for the transposed sweep
+#pragma unroll
+            for (int c = 0; c < D; ++c)
+                if (lane < D)
+                    Ls[lane * D + c] = a[c];
+            // forward: L y = g
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+            {
+                const double yk = __shfl_sync(0xffffffffu, yi, k);
+                if (row > k)
+                    yi -= a[k] * yk;
+            }
+            yi *= idiag;
+            __syncwarp();
+            // backward: L^T x = y
+#pragma unroll
+            for (int k = D - 1; k >= 0; --k)
+            {
+                const double xk = __shfl_sync(0xffffffffu, yi, k);
+                if (row < k)
+                    yi -= Ls[k * D + row] * xk;
+            }
+            if (lane < D)
+                y[lane] = yi;
+            *ok_out = ok;
+            __syncwarp();
+        }
+
+        template <int NK>
+        __device__ void gn_solve_step(const double *__restrict__ v, const GnParams &gp, double *__restrict__ A, double *__restrict__ w,
+                                      unsigned long long *ts = nullptr)
+        {
+#ifdef MBAVO_PROFILE_PHASES
+#define MBAVO_TS(k) do { if (ts && (threadIdx.x & 31) == 0) ts[k] = global_timer_ns(); } while (0)
+#else
+#define MBAVO_TS(k) do { } while (0)
+#endif
             constexpr int D = 6 * NK, D1 = D + 1;
             const int lane = threadIdx.x & 31;
             GnState *st = gp.state;
@@ -356,49 +437,63 @@ namespace mbavo
             for (int e = lane; e < D; e += 32)
                 g[e] = v[1 + e], y[e] = v[1 + e];
             __syncwarp();
-            // right-looking LDL^T: after step j column j of A holds L(:, j) below the diagonal and d_j on it
+            MBAVO_TS(11);
             bool ok = true;
-            double dmax = 0.0;
-            for (int j = 0; j < D; ++j)
+#ifdef MBAVO_SMEM_SOLVE
+            constexpr int kRegSolveMaxD = 0;
+#else
+            constexpr int kRegSolveMaxD = 24;
+#endif
+            if constexpr (D <= kRegSolveMaxD)
             {
-                const double d = A[j * D + j];
-                dmax = d > dmax ? d : dmax;
-                if (!(d > 1e-9 * dmax))
-                    ok = false;
-                const double id = 1.0 / d;
-                __syncwarp();
-                const int m = D - j - 1; // trailing size
-                for (int e = lane; e < m * m; e += 32)
+                ldlt_solve_regs<D>(Hd, g, A, y, &ok);
+            }
+            else
+            {
+                // right-looking LDL^T: after step j column j of A holds L(:, j) below the diagonal and d_j on it
+                double dmax = 0.0;
+                for (int j = 0; j < D; ++j)
                 {
-                    const int i = j + 1 + e / m, k = j + 1 + e % m;
-                    if (k <= i) // lower triangle only
-                        A[i * D + k] -= A[i * D + j] * A[k * D + j] * id;
+                    const double d = A[j * D + j];
+                    dmax = d > dmax ? d : dmax;
+                    if (!(d > 1e-9 * dmax))
+                        ok = false;
+                    const double id = 1.0 / d;
+                    __syncwarp();
+                    const int m = D - j - 1; // trailing size
+                    for (int e = lane; e < m * m; e += 32)
+                    {
+                        const int i = j + 1 + e / m, k = j + 1 + e % m;
+                        if (k <= i) // lower triangle only
+                            A[i * D + k] -= A[i * D + j] * A[k * D + j] * id;
+                    }
+                    __syncwarp();
+                    for (int i = j + 1 + lane; i < D; i += 32)
+                        A[i * D + j] *= id; // L(i, j)
+                    __syncwarp();
                 }
+                // L y = g (column sweeps), y /= d, L^T x = y
+                for (int k = 0; k < D; ++k)
+                {
+                    const double yk = y[k];
+                    __syncwarp();
+                    for (int i = k + 1 + lane; i < D; i += 32)
+                        y[i] -= A[i * D + k] * yk;
+                    __syncwarp();
+                }
+                for (int e = lane; e < D; e += 32)
+                    y[e] /= A[e * D + e];
                 __syncwarp();
-                for (int i = j + 1 + lane; i < D; i += 32)
-                    A[i * D + j] *= id; // L(i, j)
-                __syncwarp();
+                for (int k = D - 1; k >= 0; --k)
+                {
+                    const double xk = y[k];
+                    __syncwarp();
+                    for (int i = lane; i < k; i += 32)
+                        y[i] -= A[k * D + i] * xk;
+                    __syncwarp();
+                }
             }
-            // L y = g (column sweeps), y /= d, L^T x = y
-            for (int k = 0; k < D; ++k)
-            {
-                const double yk = y[k];
-                __syncwarp();
-                for (int i = k + 1 + lane; i < D; i += 32)
-                    y[i] -= A[i * D + k] * yk;
-                __syncwarp();
-            }
-            for (int e = lane; e < D; e += 32)
-                y[e] /= A[e * D + e];
-            __syncwarp();
-            for (int k = D - 1; k >= 0; --k)
-            {
-                const double xk = y[k];
-                __syncwarp();
-                for (int i = lane; i < k; i += 32)
-                    y[i] -= A[k * D + i] * xk;
-                __syncwarp();
-            }
+            MBAVO_TS(12);
             for (int e = lane; e < D; e += 32)
                 sv[e] = -y[e]; // solve_normal_equation.h:33
             __syncwarp();
@@ -415,6 +510,7 @@ namespace mbavo
             for (int o = 16; o > 0; o >>= 1)
                 part += __shfl_xor_sync(0xffffffffu, part, o);
             const double model = -part;
+            MBAVO_TS(13);
             const int n = gp.n_knots;
             // full-ordering step and candidate knots
             for (int e = lane; e < 6 * n; e += 32)
@@ -463,6 +559,7 @@ namespace mbavo
                 o[2] = q[3] * dq[2] + q[2] * dq[3] + q[0] * dq[1] - q[1] * dq[0];
                 o[3] = q[3] * dq[3] - q[0] * dq[0] - q[1] * dq[1] - q[2] * dq[2];
             }
+            MBAVO_TS(14);
             if (lane == 0)
             {
                 st->cost = v[0];
@@ -883,7 +980,7 @@ namespace mbavo
                 {
                     double *A = fin_s + ((E + 1) & ~1), *w = A + 72 * NK * NK;
                     if (warp == 0)
-                        gn_solve_step<NK>(fin_s, gp, A, w);
+                        gn_solve_step<NK>(fin_s, gp, A, w, prm.phase_times ? prm.phase_times + 16 * (prm.trace_row & 63) : nullptr);
                 }
                 else if (threadIdx.x == 0)
                 {

@@ -48,4 +48,6 @@ for env in ("", "1"):
         for r in range(8):
             row = t[r]
             print(f"  kernel {r}: entry +{(row[0] - t0) / 1e3:7.1f}us  griddep done +{(row[2] - t0) / 1e3:7.1f}  batches done +{(row[6] - t0) / 1e3:7.1f}  "
-                  f"ticket +{(row[8] - t0) / 1e3:7.1f}  summed +{(row[9] - t0) / 1e3:7.1f}  end +{(row[10] - t0) / 1e3:7.1f}")
+                  f"ticket +{(row[8] - t0) / 1e3:7.1f}  summed +{(row[9] - t0) / 1e3:7.1f}  end +{(row[10] - t0) / 1e3:7.1f}"
+                  + (f"  | solve: system built +{(row[11] - row[9]) / 1e3:.1f}  factored+solved +{(row[12] - row[9]) / 1e3:.1f}  "
+                     f"model +{(row[13] - row[9]) / 1e3:.1f}  candidate +{(row[14] - row[9]) / 1e3:.1f}" if row[11] > row[9] > 0 else ""))
