@@ -442,7 +442,7 @@ namespace mbavo
 #ifdef MBAVO_SMEM_SOLVE
             constexpr int kRegSolveMaxD = 0;
 #else
-            constexpr int kRegSolveMaxD = 24;
+            constexpr int kRegSolveMaxD = 12; // two-knot window, the tracker's own mode; ~31 KB of unrolled shuffle code per instantiation
 #endif
             if constexpr (D <= kRegSolveMaxD)
             {
