@@ -347,7 +347,7 @@ int mbavo_keyframe_stats(mbavo_ctx *ctx, int level, const double *poses_tq, doub
  *                               The context must hold the keyframe pyramid and the points (mbavo_set_keyframe_pyramid +
  *                               mbavo_select_points or mbavo_set_points_pyramid).
  *   mbavo_tracker_new_keyframe  the re-anchoring the reference does when the frame became the keyframe (:186-199); the
- *                               caller applies the thresholds (:250-262) and uploads the new keyframe + points. */
+ *                               caller (mbavo_is_keyframe decides) uploads the new keyframe + points. */
 #define MBAVO_MAX_TRACKER_KNOTS 16
 typedef struct mbavo_tracker
 {
@@ -373,6 +373,10 @@ int mbavo_tracker_init(mbavo_tracker *tracker, int spline_deg_k, double sample_d
 int mbavo_track_frame(mbavo_ctx *ctx, mbavo_tracker *tracker, int n_levels, int mem, const unsigned char *cur_I0,
                       double capture_time, double exposure_time, const mbavo_lm_options *opt, mbavo_frame_result *result);
 int mbavo_tracker_new_keyframe(mbavo_tracker *tracker, double capture_time);
+/* the decision of isKeyframe (blur_aware_direct_tracker.cpp:251-262) on the statistics mbavo_track_frame returned, with the
+ * options keyframe_max_flow_mag0 / _mag1 / keyframe_max_blur_kernel_mag (blur_aware_direct_tracker.h): 1 = new keyframe */
+int mbavo_is_keyframe(double avg_flow, double avg_kernel_len, double max_flow_mag0, double max_flow_mag1,
+                      double max_blur_kernel_mag);
 
 /* ---- synthetic blurred frame ---------------------------------------------------------------
  * warp_image + synthesize_motion_blurred_img (src/ba_tracker/generate_synthetic_data.cpp:127-180): the mean over num_poses

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points", "mbavo_synthesize_blurred",
     "mbavo_keyframe_stats", "mbavo_select_points", "mbavo_get_points", "mbavo_se3_exp", "mbavo_se3_log",
     "mbavo_spline_pose", "mbavo_spline_transform_by_right", "mbavo_spline_transform_to", "mbavo_predict_spline", "mbavo_frame_velocity",
-    "mbavo_tracker_init", "mbavo_track_frame", "mbavo_tracker_new_keyframe",
+    "mbavo_tracker_init", "mbavo_track_frame", "mbavo_tracker_new_keyframe", "mbavo_is_keyframe",
 ]
 IPC_HANDLE_BYTES = 64
 

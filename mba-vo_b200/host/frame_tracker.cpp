@@ -8,7 +8,8 @@
 //   isKeyframe statistics                   :205-248   mbavo_keyframe_stats
 //   velocity from the neighbouring frames   :155-162   mbavo_frame_velocity
 //   re-anchoring on a new keyframe          :186-199   mbavo_tracker_new_keyframe
-// The keyframe decision itself (thresholds :250-262) and the new keyframe's image / depth / point selection
+//   keyframe decision                       :251-262   mbavo_is_keyframe
+// The new keyframe's image / depth / point selection
 // (mbavo_set_keyframe_pyramid, mbavo_select_points) stay with the caller, as in tmpProcessKeyframe.
 #include "../../include/mbavo.h"
 
@@ -109,6 +110,16 @@ extern "C"
         std::memcpy(res->q_cur2key, poses + 3, sizeof(double) * 4);
         compose(tr->keyframe_t, tr->keyframe_q, poses, poses + 3, res->t_cur2world, res->q_cur2world); // :203
         return MBAVO_OK;
+    }
+
+    int mbavo_is_keyframe(double avg_flow, double avg_kernel_len, double max_flow_mag0, double max_flow_mag1, double max_blur_kernel_mag)
+    {
+        // blur_aware_direct_tracker.cpp:251-262: far enough from the keyframe and sharp enough, or simply too far
+        if (avg_flow > max_flow_mag0 && avg_kernel_len < max_blur_kernel_mag)
+            return 1;
+        if (avg_flow > max_flow_mag1)
+            return 1;
+        return 0;
     }
 
     int mbavo_tracker_new_keyframe(mbavo_tracker *tr, double capture_time)

@@ -216,3 +216,56 @@ def test_spline_pose_and_transforms(pkg, cuda_lib, O, synth):
         want_R = R1 @ R0.T @ R1
         want_t = R1 @ (R0.T @ (t1 - t0)) + t1
         assert np.abs(O.q_to_R(cR[0]) - want_R).max() <= 1e-12 and np.abs(ct[0] - want_t).max() <= 1e-12
+
+
+def test_tracker_state_and_keyframe_decision(pkg, cuda_lib, O, synth):
+    """The host-only parts of the per-frame driver: mbavo_tracker_init (tracker.cpp:91-109), mbavo_tracker_new_keyframe
+    (:186-199: mTKeyframe *= T(capture), the spline re-anchored so that its pose at the capture time is the identity, mTprevB2W
+    reset) and mbavo_is_keyframe (:251-262)."""
+    import ctypes as C
+
+    from mbavo_b200 import api
+
+    trk = api._Tracker()
+    assert cuda_lib.mbavo_tracker_init(C.byref(trk), C.c_int(4), C.c_double(0.1), C.c_double(2.0)) != 0  # two knots: k = 2 only
+    assert cuda_lib.mbavo_tracker_init(C.byref(trk), C.c_int(2), C.c_double(0.1), C.c_double(2.0)) == 0
+    assert trk.num_ctrl_knots == 2 and trk.start_time == 2.0 and trk.prev_timestamp == 2.0
+    assert list(trk.knots_R[:8]) == [0, 0, 0, 1, 0, 0, 0, 1] and list(trk.knots_t[:6]) == [0] * 6
+    assert list(trk.keyframe_q) == [0, 0, 0, 1] and list(trk.velocity) == [0] * 6
+    # put the tracker somewhere: two knots of a moving spline, a keyframe pose, then re-anchor at a time inside the segment
+    rng = np.random.default_rng(2)
+    kt = rng.normal(size=(2, 3))
+    kR = np.array([np.concatenate([np.sin(a / 2) * ax / np.linalg.norm(ax), [np.cos(a / 2)]])
+                   for a, ax in ((0.3, rng.normal(size=3)), (0.5, rng.normal(size=3)))])
+    key_t, key_q = rng.normal(size=3), np.array([0.0, np.sin(0.2), 0.0, np.cos(0.2)])
+    for i in range(6):
+        trk.knots_t[i] = kt.reshape(-1)[i]
+    for i in range(8):
+        trk.knots_R[i] = kR.reshape(-1)[i]
+    for i in range(3):
+        trk.keyframe_t[i] = key_t[i]
+    for i in range(4):
+        trk.keyframe_q[i] = key_q[i]
+    trk.prev_t[0] = 5.0
+    cap = 2.04
+    t_c, q_c = synth.spline_pose(2, kt, kR, 2.0, 0.1, cap)
+    assert cuda_lib.mbavo_tracker_new_keyframe(C.byref(trk), C.c_double(cap)) == 0
+    want_t = O.q_to_R(key_q) @ t_c + key_t
+    want_q = O.q_mul(key_q, q_c)
+    assert np.abs(np.array(trk.keyframe_t) - want_t).max() <= 1e-14 and np.abs(np.array(trk.keyframe_q) - want_q).max() <= 1e-15
+    nt, nR = np.array(trk.knots_t[:6]).reshape(2, 3), np.array(trk.knots_R[:8]).reshape(2, 4)
+    t_n, q_n = synth.spline_pose(2, nt, nR, 2.0, 0.1, cap)
+    # exactly the identity in rotation; in translation up to the reference's per-knot update (Spline.h:196-200)
+    assert np.abs(q_n - [0, 0, 0, 1]).max() <= 1e-14 and np.abs(t_n).max() <= 0.05 * np.abs(kt).max()
+    assert list(trk.prev_t) == [0, 0, 0] and list(trk.prev_q) == [0, 0, 0, 1]
+    # the relative motion along the spline is what it was, seen from the new body frame (conjugated by the re-anchoring transform)
+    before = O.frame_velocity(*synth.spline_pose(2, kt, kR, 2.0, 0.1, 2.0), *synth.spline_pose(2, kt, kR, 2.0, 0.1, 2.1), 1.0)
+    after = O.frame_velocity(*synth.spline_pose(2, nt, nR, 2.0, 0.1, 2.0), *synth.spline_pose(2, nt, nR, 2.0, 0.1, 2.1), 1.0)
+    assert abs(np.linalg.norm(before[3:]) - np.linalg.norm(after[3:])) <= 1e-12
+    # keyframe decision
+    f = cuda_lib.mbavo_is_keyframe
+    f.argtypes = [C.c_double] * 5
+    assert f(12.0, 3.0, 10.0, 30.0, 5.0) == 1      # far enough and sharp enough
+    assert f(12.0, 6.0, 10.0, 30.0, 5.0) == 0      # far enough but too blurred
+    assert f(31.0, 6.0, 10.0, 30.0, 5.0) == 1      # too far, whatever the blur
+    assert f(9.0, 1.0, 10.0, 30.0, 5.0) == 0
