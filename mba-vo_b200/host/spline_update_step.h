@@ -96,34 +96,22 @@ namespace SLAM
             int mbavo_max_num_ctrl_knots = 0;
         };
 
-        void initialize_shared_cuda_storages(const int max_num_frames,
-                                             const int max_num_virtual_poses_per_frame,
-                                             const int max_num_keypoints,
-                                             const int max_patch_size,
-                                             const int max_num_ctrl_knots,
-                                             const int spline_deg_k,
+        // spline_update_step.h:60-68 of the reference: sizes the context once from the tracker's maxima
+        void initialize_shared_cuda_storages(const int max_num_frames, const int max_num_virtual_poses_per_frame, const int max_num_keypoints,
+                                             const int max_patch_size, const int max_num_ctrl_knots, const int spline_deg_k,
                                              CudaSharedStorages &storages);
 
         void free_shared_cuda_storages(CudaSharedStorages &storages);
 
-        void evaluate_cost_hessian_gradient(const int n_vir_poses_per_frame,
-                                            const int n_frames,
-                                            const unsigned char *cuda_ref_img,
-                                            const float *cuda_dIxy_ref,
-                                            const int num_keypoints,
-                                            const int patch_size,
-                                            const Core::VectorX<double, 4> &intrinsics,
-                                            const Core::VectorX<int, 2> &im_size_HW,
-                                            const int spline_deg_k,
-                                            const double spline_start_time,
-                                            const double spline_sample_dt,
-                                            const int *cpu_ctrl_knot_start_indices,
-                                            const int num_ctrl_knots,
-                                            const CudaSharedStorages &storages,
-                                            const double huber_a,
-                                            double *total_costs,
-                                            double *cpu_hessian_tR,
-                                            double *cpu_gradient_tR);
+        // spline_update_step.h:70-87 of the reference.  cpu_hessian_tR == nullptr selects the cost-only branch (.cpp:242-348);
+        // H is 6n x 6n symmetric, g is 6n ordered [t-block, omega-block] (merge_hessian_gradient_cost.cpp:41-85)
+        void evaluate_cost_hessian_gradient(const int n_vir_poses_per_frame, const int n_frames, const unsigned char *cuda_ref_img,
+                                            const float *cuda_dIxy_ref, const int num_keypoints, const int patch_size,
+                                            const Core::VectorX<double, 4> &intrinsics, const Core::VectorX<int, 2> &im_size_HW,
+                                            const int spline_deg_k, const double spline_start_time, const double spline_sample_dt,
+                                            const int *cpu_ctrl_knot_start_indices, const int num_ctrl_knots,
+                                            const CudaSharedStorages &storages, const double huber_a, double *total_costs,
+                                            double *cpu_hessian_tR, double *cpu_gradient_tR);
     } // namespace VO
 } // namespace SLAM
 
