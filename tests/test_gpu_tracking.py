@@ -2,6 +2,9 @@
 blur_aware_direct_tracker.cpp:88-203): a synthetic sequence of motion-blurred frames of a textured plane, rendered by
 mbavo_synthesize_blurred along a constant-twist trajectory, is tracked with the points the GPU selected on the keyframe; the
 recovered poses are compared with the trajectory that rendered the frames, before and after a keyframe change."""
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
@@ -126,3 +129,18 @@ def test_track_blurred_sequence_point_sharded(pkg, O, synth):
             assert np.abs(ra[f][key_] - res1[f][key_]).max() <= 1e-5
         assert ra[f]["avg_flow"] == rb[f]["avg_flow"] and abs(ra[f]["avg_flow"] - res1[f]["avg_flow"]) <= 1e-4 * res1[f]["avg_flow"]
         assert [lv["decisions"] for lv in ra[f]["levels"]] == [lv["decisions"] for lv in res1[f]["levels"]]
+
+
+def test_plain_c_tracker_loop(tmp_path):
+    """examples/track_sequence.c — keyframe set-up, point selection, mbavo_track_frame per frame, the keyframe decision and a
+    keyframe change, all through include/mbavo.h from plain C: builds with gcc -std=c99 and tracks its sequence within its own
+    tolerances (exit code 0)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "mba-vo_b200", "lib")
+    exe = os.path.join(str(tmp_path), "track_sequence")
+    subprocess.run(["/usr/bin/gcc", "-O2", "-std=c99", os.path.join(root, "examples", "track_sequence.c"), "-I" + os.path.join(root, "include"),
+                    "-L" + libdir, "-lmbavo_b200", "-lm", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe],
+                   check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "-> new keyframe" in r.stdout and r.stdout.count("frame ") >= 6

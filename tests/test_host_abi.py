@@ -269,3 +269,18 @@ def test_tracker_state_and_keyframe_decision(pkg, cuda_lib, O, synth):
     assert f(12.0, 6.0, 10.0, 30.0, 5.0) == 0      # far enough but too blurred
     assert f(31.0, 6.0, 10.0, 30.0, 5.0) == 1      # too far, whatever the blur
     assert f(9.0, 1.0, 10.0, 30.0, 5.0) == 0
+
+
+def test_header_is_plain_c_and_example_links(pkg, cuda_lib, tmp_path):
+    """include/mbavo.h is a C header (no C++ in the signatures): the plain-C example compiles with gcc -std=c99 -Wall -Werror and
+    links against the product library (running it needs a GPU: tests/test_gpu_tracking.py)."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "mba-vo_b200", "lib")
+    exe = os.path.join(str(tmp_path), "track_sequence")
+    r = subprocess.run(["/usr/bin/gcc", "-O2", "-std=c99", "-Wall", "-Werror", os.path.join(root, "examples", "track_sequence.c"),
+                        "-I" + os.path.join(root, "include"), "-L" + libdir, "-lmbavo_b200", "-lm", "-Wl,-rpath," + libdir,
+                        "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
