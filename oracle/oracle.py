@@ -433,6 +433,21 @@ class RefSelect:
         res = [(xy[l, :cnt[l]].copy(), z[l, :cnt[l]].copy()) for l in range(n_levels)]
         return (res, mag) if want_mag else res
 
+    def pyramid(self, I0, n_levels):
+        """The reference's own computePyramid + compute_image_gradients -> [(image u8 (H, W), gradient float32 (H, W, 2))] per level."""
+        H0, W0 = I0.shape
+        sizes = [(H0 // (1 << l), W0 // (1 << l)) for l in range(n_levels)]
+        total = sum(h * w for h, w in sizes)
+        levels = np.zeros(total, np.uint8)
+        grads = np.zeros(2 * total, np.float32)
+        self.lib.mbavo_refselect_pyramid(_ptr(np.ascontiguousarray(I0, dtype=np.uint8), _u8p), C.c_int(H0), C.c_int(W0), C.c_int(n_levels),
+                                         _ptr(levels, _u8p), _ptr(grads, _fp))
+        out, off = [], 0
+        for h, w in sizes:
+            out.append((levels[off:off + h * w].reshape(h, w).copy(), grads[2 * off:2 * (off + h * w)].reshape(h, w, 2).copy()))
+            off += h * w
+        return out
+
 
 def best_cpu_lib() -> _Lib:
     """oracle/_ref when present (kind 'reference'), else the C port (kind 'port')."""

@@ -19,6 +19,34 @@ using namespace SLAM::Core;
 
 extern "C"
 {
+    // The reference's own pyramid and gradient loops (ImagePyramid<T>::computePyramid, ImagePyramid.h:59-99;
+    // compute_image_gradients, Gradient.h:17-75): levels[] receives the n_levels images back to back (H0*W0, then
+    // (H0/2)*(W0/2), ...), grads[] the interleaved (dx, dy) float images in the same order.
+    int mbavo_refselect_pyramid(const unsigned char *I0, int H0, int W0, int n_levels, unsigned char *levels, float *grads)
+    {
+        Image<unsigned char> img(H0, W0, 1);
+        img.copyFrom(const_cast<unsigned char *>(I0), H0, W0, 1);
+        ImagePyramid<unsigned char> pyr;
+        pyr.setNumOfPyramidLevels(n_levels);
+        pyr.computePyramid(&img);
+        size_t off = 0;
+        for (int lv = 0; lv < n_levels; ++lv)
+        {
+            Image<unsigned char> *im = pyr.getImagePtr(lv);
+            const int H = im->nHeight(), W = im->nWidth();
+            Image<float> grad(H, W, 2);
+            compute_image_gradients<unsigned char, float>(im, &grad);
+            for (int i = 0; i < H * W; ++i)
+            {
+                levels[off + i] = im->getData()[i];
+                grads[2 * (off + i)] = grad.getData()[2 * i];
+                grads[2 * (off + i) + 1] = grad.getData()[2 * i + 1];
+            }
+            off += (size_t)H * W;
+        }
+        return 0;
+    }
+
     // xy: n_levels x max_points x 2 doubles, z: n_levels x max_points doubles, count: n_levels ints (the number selected,
     // even where it exceeds max_points; only the first max_points are stored)
     int mbavo_refselect_points(const unsigned char *I0, int H0, int W0, int n_levels, float score_threshold, int cell_H, int cell_W,

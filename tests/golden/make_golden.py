@@ -96,6 +96,12 @@ def main():
         cases[name + "_xy"] = np.concatenate([xy for xy, _ in res])
         cases[name + "_z"] = np.concatenate([z for _, z in res])
     np.savez_compressed(os.path.join(HERE, "point_selection.npz"), **cases)
+
+    # 6. the reference's own pyramid and gradient loops (ImagePyramid.h:59-99, Gradient.h:17-75) on an odd-sized image
+    img = np.random.default_rng(12).integers(0, 256, (47, 61)).astype(np.uint8)
+    pyr = sel.pyramid(img, 3)
+    np.savez_compressed(os.path.join(HERE, "pyramid.npz"), **{f"I{l}": im for l, (im, _) in enumerate(pyr)},
+                        **{f"g{l}": g for l, (_, g) in enumerate(pyr)})
     print("golden vectors written to", HERE)
 
 

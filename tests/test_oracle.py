@@ -66,6 +66,23 @@ def test_golden_blurred(orc):
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3  # a float-rounding tie may move a pixel by one grey level
 
 
+def test_golden_pyramid_and_gradients(orc, O, synth):
+    """The 2 x 2 box pyramid and the central-difference gradients as the reference's own loops produced them
+    (tests/golden/make_golden.py, section 6): the numpy restatements (package synth, oracle) and the oracle's C
+    restatement reproduce every level bit for bit — these are the loops the GPU pyramid path is compared with."""
+    z = golden("pyramid.npz")
+    cur = np.ascontiguousarray(z["I0"])
+    levels = O.pyramid_numpy(cur, 3)
+    for l in range(3):
+        if l > 0:
+            assert np.array_equal(np.asarray(orc.pyramid_down(cur)), z[f"I{l}"])
+            cur = synth.pyramid_down(cur)
+        assert np.array_equal(cur, z[f"I{l}"]) and np.array_equal(levels[l], z[f"I{l}"])
+        g = z[f"g{l}"]
+        assert np.array_equal(synth.image_gradient(cur).reshape(g.shape), g)
+        assert np.array_equal(np.asarray(orc.image_gradient(cur)).reshape(g.shape), g)
+
+
 def _selection_cases():
     z = golden("point_selection.npz")
     for name in ("tex", "ramp"):
@@ -327,3 +344,21 @@ def test_oracle_matches_reference_point_selection(O, synth, thr, cell):
         assert np.array_equal(mag, O.gradient_magnitude(I))
         for (xy, zz), (xy_w, zz_w) in zip(got, want):
             assert np.array_equal(xy, xy_w) and np.array_equal(zz, zz_w)
+
+
+def test_oracle_matches_reference_pyramid(orc, O, synth):
+    """Directly against the reference's ImagePyramid<T>::computePyramid and compute_image_gradients (oracle/_ref)."""
+    if not O.RefSelect.available():
+        pytest.skip("oracle/_ref/libmbavo_refselect.so not built (no /root/reference here)")
+    rs = O.RefSelect()
+    rng = np.random.default_rng(1)
+    for H, W, L in ((123, 161, 4), (480, 640, 4), (47, 33, 3)):
+        I = rng.integers(0, 256, (H, W)).astype(np.uint8)
+        cur = I
+        for l, (im, g) in enumerate(rs.pyramid(I, L)):
+            if l > 0:
+                assert np.array_equal(np.asarray(orc.pyramid_down(cur)), im)
+                cur = synth.pyramid_down(cur)
+            assert np.array_equal(cur, im)
+            assert np.array_equal(synth.image_gradient(cur).reshape(g.shape), g)
+            assert np.array_equal(np.asarray(orc.image_gradient(cur)).reshape(g.shape), g)
