@@ -1406,7 +1406,8 @@ extern "C"
         // The sample records depend on the knots, the frame times and the number of exposure samples only — not on the level.
         // When every level of the sweep uses the same sample count, a level after the first finds the records of its knots in
         // one of the two buffers (the previous level's, or its committed candidate's) and runs no pose kernel of its own.
-        bool reuse = nlev > 1;
+        // (point-sharded contexts keep one pose kernel per evaluation: the shared-record form has only been measured on one GPU)
+        bool reuse = nlev > 1 && ctx->shard.world <= 1;
         for (int li = 1; li < nlev && reuse; ++li)
             reuse = ctx->levels[level_coarse - li].set && ctx->levels[level_coarse].set &&
                     ctx->levels[level_coarse - li].dev.N == ctx->levels[level_coarse].dev.N;
