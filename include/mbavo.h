@@ -332,7 +332,7 @@ int mbavo_get_points(mbavo_ctx *ctx, int level, int capacity, double *xy, double
  * pi(T+^-1 P)|^2), P the point un-projected with its depth, T the live-camera-to-keyframe pose at the capture time (T0)
  * and at -/+ half the exposure (T-, T+), pi the pinhole projection.  poses_tq: 3 x 7 doubles (tx ty tz qx qy qz qw) in
  * the order T0, T-, T+ — SplineSE3::GetPose at those times.  Collective in a sharded context (means over all ranks).
- * The caller applies its thresholds (keyframe_max_flow_mag0 / _mag1, keyframe_max_blur_kernel_mag, :250-262). */
+ * mbavo_is_keyframe applies the thresholds (keyframe_max_flow_mag0 / _mag1, keyframe_max_blur_kernel_mag, :250-262). */
 int mbavo_keyframe_stats(mbavo_ctx *ctx, int level, const double *poses_tq, double *avg_flow, double *avg_kernel_len);
 
 /* ---- BlurAwareDirectTracker::trackFrame ------------------------------------------------------------
