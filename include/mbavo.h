@@ -138,6 +138,17 @@ int mbavo_set_live_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned
 int mbavo_set_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *points);
 /* the points of levels 0 .. n_levels-1 in one call (one synchronisation): points[l] describes level l */
 int mbavo_set_points_pyramid(mbavo_ctx *ctx, int n_levels, const mbavo_level_points *points);
+/* Everything a new frame brings, in ONE call with ONE synchronisation: the level-0 keyframe (ref_I0, may be NULL: the
+ * keyframe pyramid already in the context stays) and live images (cur_I0, may be NULL likewise) go up on the context's
+ * stream, followed by the pyramid / gradient / texel kernels, while the points of all levels go up on a second stream
+ * underneath them.  Replaces the sequence mbavo_set_keyframe_pyramid + mbavo_set_live_pyramid + mbavo_set_points_pyramid
+ * (three synchronisations) — what the tracker does per keyframe / frame in tmpProcessKeyframe + uploadDataToGpu
+ * (blur_aware_direct_tracker.cpp:346-409, 701-751).  flags: MBAVO_UPLOAD_ASYNC returns without synchronising; the host
+ * buffers must then stay valid and unchanged until the next blocking call on this context (any evaluation, sweep,
+ * LM or statistics entry point) has returned. */
+#define MBAVO_UPLOAD_ASYNC 1
+int mbavo_set_frame(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0,
+                    const unsigned char *const *cur_I0, int n_frames, const mbavo_level_points *points, int flags);
 
 /* A new live (blurred) frame for an already set level — what BlurAwareDirectTracker::trackFrame uploads per frame
  * (blur_aware_direct_tracker.cpp:112-116) while keyframe image, gradient, texels and host-map points stay resident.
@@ -199,11 +210,17 @@ int mbavo_unpack(const double *packed_host, int kmin, int knot_window, int num_c
  * all-reduce fused into the kernel, no NCCL call, no extra launch.  The reference has no multi-GPU path; this replaces
  * what a ported version would do with ncclAllReduce after kernel_compute_frame_cost_gradient_hessian.
  *
- *   mbavo_shard_export   creates this context's mailbox; handle_out (MBAVO_IPC_HANDLE_BYTES, may be NULL) receives its CUDA
- *                        IPC handle for ranks in OTHER processes, mailbox_ptr_out (may be NULL) its device pointer for
- *                        ranks in the SAME process.
+ *   mbavo_shard_export   creates (first call) and ZEROES this context's mailbox; handle_out (MBAVO_IPC_HANDLE_BYTES, may be
+ *                        NULL) receives its CUDA IPC handle for ranks in OTHER processes, mailbox_ptr_out (may be NULL) its
+ *                        device pointer for ranks in the SAME process.  The mailbox is zeroed here — before its handle can
+ *                        reach a peer — and never by mbavo_shard_connect, so no barrier is needed between the ranks'
+ *                        connects and the first collective call: a rank that connects first may already deposit its first
+ *                        vector in a slower peer's mailbox.  Call it after the last collective of an earlier connection
+ *                        has returned.
  *   mbavo_shard_connect  handles: world x MBAVO_IPC_HANDLE_BYTES in rank order (other processes), or mailbox_ptrs: world
- *                        device pointers in rank order (same process); the entry of `rank` itself is ignored.
+ *                        device pointers in rank order (same process); the entry of `rank` itself is ignored.  The
+ *                        sequence numbers of the exchange restart at 0, so every connect needs a fresh mbavo_shard_export
+ *                        of this context (MBAVO_ENOTREADY otherwise) and all ranks of a group (re)connect together.
  *   mbavo_shard_set_global_points   total number of host-map points of `level` over all ranks (the normaliser
  *                        1 / ((P - num_bad) F S) of spline_update_step.cpp:116-117 is global; num_bad_keypoints given to
  *                        mbavo_set_outliers / mbavo_set_num_bad is the global count too).

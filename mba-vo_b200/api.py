@@ -19,6 +19,7 @@ SOLVER_SVD_JACOBI, SOLVER_LDLT = 0, 1
 EXPORTED_SYMBOLS = [
     "mbavo_last_error", "mbavo_version", "mbavo_create", "mbavo_destroy", "mbavo_set_stream", "mbavo_set_frame_times",
     "mbavo_set_level", "mbavo_set_keyframe_pyramid", "mbavo_set_live_pyramid", "mbavo_set_level_points", "mbavo_set_points_pyramid",
+    "mbavo_set_frame",
     "mbavo_set_live_images", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
@@ -223,6 +224,23 @@ class Context:
             arr[l] = _LevelPoints(MEM_HOST, lv.fx, lv.fy, lv.cx, lv.cy, lv.xy.ctypes.data, 16, 0, lv.z.ctypes.data, lv.xy.shape[0],
                                   lv.pattern.ctypes.data, lv.S, lv.N)
         self._check(self.lib.mbavo_set_points_pyramid(self._h, C.c_int(len(levels)), arr))
+
+    def set_frame(self, n_levels: int, ref_I0: Optional[np.ndarray], cur_I0: Optional[Sequence[np.ndarray]], levels: Sequence,
+                  async_upload: bool = False):
+        """mbavo_set_frame: level-0 keyframe + live images (either may be None) and the points of every level (synth.Level list,
+        level 0 first) in one call.  async_upload: no synchronisation — the arrays must stay alive and unchanged until the next
+        blocking call on this context returns (they are kept referenced here)."""
+        arr = (_LevelPoints * len(levels))()
+        for l, lv in enumerate(levels):
+            arr[l] = _LevelPoints(MEM_HOST, lv.fx, lv.fy, lv.cx, lv.cy, lv.xy.ctypes.data, 16, 0, lv.z.ctypes.data, lv.xy.shape[0],
+                                  lv.pattern.ctypes.data, lv.S, lv.N)
+        H0, W0 = ref_I0.shape if ref_I0 is not None else (0, 0)
+        F = len(cur_I0) if cur_I0 is not None else 0
+        cur = (C.c_void_p * F)(*[c.ctypes.data for c in cur_I0]) if F else None
+        self._keep["frame"] = (ref_I0, cur_I0, levels, arr, cur)
+        self._check(self.lib.mbavo_set_frame(self._h, C.c_int(n_levels), C.c_int(MEM_HOST),
+                                             C.c_void_p(ref_I0.ctypes.data if ref_I0 is not None else 0), C.c_int(H0), C.c_int(W0), cur,
+                                             C.c_int(F), arr, C.c_int(1 if async_upload else 0)))
 
     def set_live_images(self, level: int, cur_I: Sequence[np.ndarray]):
         """mbavo_set_live_images with host images: a new blurred frame for a level whose keyframe stays resident."""

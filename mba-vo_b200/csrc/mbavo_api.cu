@@ -92,6 +92,8 @@ struct mbavo_ctx
     int device = 0;
     mbavo_limits lim{};
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // second stream of mbavo_set_frame (point uploads under the pyramid build)
+    cudaEvent_t copy_done = nullptr;
     int num_sms = 148;
 
     double cap[kMaxFrames] = {}, exp_time[kMaxFrames] = {};
@@ -116,6 +118,7 @@ struct mbavo_ctx
 
     // point sharding (mbavo_shard_*): this rank's mailbox, the mapped mailboxes of all ranks, exchange counters
     Mailbox *mailbox = nullptr;
+    bool mailbox_fresh = false;             // zeroed by mbavo_shard_export and not yet consumed by a connect
     ShardParams shard{};                    // world <= 1: not sharded
     bool peer_is_ipc[kMaxShards] = {};      // opened with cudaIpcOpenMemHandle (to be closed)
     unsigned long long shard_seq = 0, aux_seq = 0;
@@ -529,38 +532,37 @@ namespace
         return MBAVO_OK;
     }
 
-    // Spin until every (value, sequence) pair of the result shows sequence number ctx->seq (a microsecond after the
-    // tracking kernel's last block stores them), then compact the values into ctx->result_vals.  The stream is polled now
-    // and then so that a failed launch cannot hang the caller.
-    int wait_result(mbavo_ctx *ctx)
+    // Spin until both self-validating words of every element of the result carry the tag of ctx->seq (a microsecond after
+    // the tracking kernel's last block stores them; see TrackParams::host_out), collecting the values into
+    // ctx->result_vals.  The stream is polled now and then so that a failed launch cannot hang the caller.
+    int wait_published(mbavo_ctx *ctx, int first, int count, unsigned long long seq, double *vals, const char *what)
     {
-        const volatile unsigned long long *pairs = reinterpret_cast<const volatile unsigned long long *>(ctx->result_host);
-        const int E = ctx->result_len;
-        int done = 0; // elements [0, done) have been seen with the right sequence number
-        for (unsigned long long spins = 1; done < E; ++spins)
+        const volatile unsigned long long *words = reinterpret_cast<const volatile unsigned long long *>(ctx->result_host);
+        int done = 0; // elements [first, first + done) have been seen with the right tag
+        for (unsigned long long spins = 1; done < count; ++spins)
         {
-            while (done < E && pairs[2 * done + 1] == ctx->seq)
+            while (done < count && read_published(words + 2 * (first + done), seq, vals ? vals + done : nullptr))
                 ++done;
-            if (done < E && (spins & 0xfff) == 0)
+            if (done < count && (spins & 0xfff) == 0)
             {
                 cudaError_t e = cudaStreamQuery(ctx->stream);
                 if (e != cudaSuccess && e != cudaErrorNotReady)
-                    return fail(MBAVO_ECUDA, "evaluation failed: %s", cudaGetErrorString(e));
+                    return fail(MBAVO_ECUDA, "%s failed: %s", what, cudaGetErrorString(e));
                 if (e == cudaSuccess)
                 {
-                    bool all = true;
-                    for (int i = done; i < E; ++i)
-                        all = all && pairs[2 * i + 1] == ctx->seq;
-                    if (!all)
-                        return fail(MBAVO_ECUDA, "tracking kernel finished without publishing its result");
+                    // the stream is idle: every store of the kernel is visible by now
+                    std::atomic_thread_fence(std::memory_order_acquire);
+                    for (; done < count; ++done)
+                        if (!read_published(words + 2 * (first + done), seq, vals ? vals + done : nullptr))
+                            return fail(MBAVO_ECUDA, "%s finished without publishing its result", what);
                 }
             }
         }
         std::atomic_thread_fence(std::memory_order_acquire);
-        for (int i = 0; i < E; ++i)
-            ctx->result_vals[i] = ctx->result_host[2 * i];
         return MBAVO_OK;
     }
+
+    int wait_result(mbavo_ctx *ctx) { return wait_published(ctx, 0, ctx->result_len, ctx->seq, ctx->result_vals.data(), "evaluation"); }
 } // namespace
 
 extern "C"
@@ -591,6 +593,16 @@ extern "C"
         DeviceGuard guard(dev);
 
         mbavo_ctx *ctx = new mbavo_ctx();
+        // any failure below releases what has been allocated so far (mbavo_destroy copes with a half-built context)
+        struct Guard
+        {
+            mbavo_ctx *c;
+            ~Guard()
+            {
+                if (c)
+                    mbavo_destroy(c);
+            }
+        } undo{ctx};
         ctx->device = dev;
         ctx->lim = *lim;
         cudaDeviceProp prop;
@@ -636,6 +648,7 @@ extern "C"
             if (ph == 1 || ph == 2 || ph == 4 || ph == 8 || ph == 16 || ph == 32)
                 ctx->force_phases = ph;
         }
+        undo.c = nullptr;
         *out = ctx;
         return MBAVO_OK;
     }
@@ -645,7 +658,8 @@ extern "C"
         if (!ctx)
             return MBAVO_OK;
         DeviceGuard guard(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
+        if (ctx->stream)
+            cudaStreamSynchronize(ctx->stream);
         for (auto &L : ctx->levels)
         {
             free_level(L);
@@ -682,9 +696,17 @@ extern "C"
         cudaFreeHost(ctx->result_host);
         cudaFree(ctx->outlier_result_dev);
         cudaFreeHost(ctx->outlier_result_host);
-        cudaEventDestroy(ctx->ev0);
-        cudaEventDestroy(ctx->ev1);
-        cudaStreamDestroy(ctx->own_stream);
+        if (ctx->ev0)
+            cudaEventDestroy(ctx->ev0);
+        if (ctx->ev1)
+            cudaEventDestroy(ctx->ev1);
+        if (ctx->own_stream)
+            cudaStreamDestroy(ctx->own_stream);
+        if (ctx->copy_stream)
+            cudaStreamDestroy(ctx->copy_stream);
+        if (ctx->copy_done)
+            cudaEventDestroy(ctx->copy_done);
+        cudaGetLastError();
         delete ctx;
         return MBAVO_OK;
     }
@@ -856,16 +878,13 @@ extern "C"
         L.set = L.has_key && L.has_live && L.has_pts;
     }
 
-    int mbavo_set_keyframe_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0)
+    // validation, allocation and the enqueue of the upload + pyramid / gradient / texel kernels on `s` (no synchronisation)
+    static int enqueue_keyframe_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0, cudaStream_t s)
     {
         if (!ctx || !ref_I0 || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS || (mem != MBAVO_MEM_HOST && mem != MBAVO_MEM_DEVICE))
             return fail(MBAVO_EINVAL, "bad arguments");
         if ((H0 >> (n_levels - 1)) < 2 || (W0 >> (n_levels - 1)) < 2)
             return fail(MBAVO_EINVAL, "%d levels of a %d x %d image leave less than 2 x 2 pixels", n_levels, H0, W0);
-        DeviceGuard guard(ctx->device);
-        cudaStream_t s = ctx->stream;
-        if (cudaStreamQuery(s) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(s));
         for (int l = 0; l < n_levels; ++l)
         {
             LevelStore &L = ctx->levels[l];
@@ -916,11 +935,25 @@ extern "C"
             L.has_key = true;
             pyramid_level_ready(L);
         }
-        CUDA_TRY(cudaStreamSynchronize(s)); // the host image is only borrowed for the call
         return MBAVO_OK;
     }
 
-    int mbavo_set_live_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *const *cur_I0, int n_frames)
+    int mbavo_set_keyframe_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0)
+    {
+        if (!ctx)
+            return fail(MBAVO_EINVAL, "null context");
+        DeviceGuard guard(ctx->device);
+        cudaStream_t s = ctx->stream;
+        if (cudaStreamQuery(s) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(s));
+        int rc = enqueue_keyframe_pyramid(ctx, n_levels, mem, ref_I0, H0, W0, s);
+        cudaError_t e = cudaStreamSynchronize(s); // the host image is only borrowed for the call
+        if (rc == MBAVO_OK && e != cudaSuccess)
+            return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e));
+        return rc;
+    }
+
+    static int enqueue_live_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *const *cur_I0, int n_frames, cudaStream_t s)
     {
         if (!ctx || !cur_I0 || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS || (mem != MBAVO_MEM_HOST && mem != MBAVO_MEM_DEVICE))
             return fail(MBAVO_EINVAL, "bad arguments");
@@ -929,10 +962,6 @@ extern "C"
         for (int l = 0; l < n_levels; ++l)
             if (!ctx->levels[l].has_key)
                 return fail(MBAVO_ENOTREADY, "mbavo_set_keyframe_pyramid has not set level %d", l);
-        DeviceGuard guard(ctx->device);
-        cudaStream_t s = ctx->stream;
-        if (cudaStreamQuery(s) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(s));
         for (int l = 0; l < n_levels; ++l)
         {
             LevelStore &L = ctx->levels[l];
@@ -973,12 +1002,27 @@ extern "C"
             L.has_live = true;
             pyramid_level_ready(L);
         }
-        CUDA_TRY(cudaStreamSynchronize(s));
         return MBAVO_OK;
     }
 
+    int mbavo_set_live_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *const *cur_I0, int n_frames)
+    {
+        if (!ctx)
+            return fail(MBAVO_EINVAL, "null context");
+        DeviceGuard guard(ctx->device);
+        cudaStream_t s = ctx->stream;
+        if (cudaStreamQuery(s) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(s));
+        int rc = enqueue_live_pyramid(ctx, n_levels, mem, cur_I0, n_frames, s);
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (rc == MBAVO_OK && e != cudaSuccess)
+            return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e));
+        return rc;
+    }
+
+
     // enqueue the uploads of one level's points on the context's stream (no synchronisation)
-    static int enqueue_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d)
+    static int enqueue_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d, cudaStream_t s)
     {
         if (!ctx || !d || level < 0 || level >= MBAVO_MAX_LEVELS)
             return fail(MBAVO_EINVAL, "bad context / level");
@@ -1001,7 +1045,6 @@ extern "C"
         LevelStore &L = ctx->levels[level];
         if (L.set && !L.has_key)
             return fail(MBAVO_EINVAL, "level %d was set by mbavo_set_level; points of such a level are replaced by mbavo_set_level", level);
-        cudaStream_t s = ctx->stream;
         int rc = ensure_level_scratch(ctx, L);
         if (rc != MBAVO_OK)
             return rc;
@@ -1054,7 +1097,7 @@ extern "C"
         DeviceGuard guard(ctx->device);
         if (cudaStreamQuery(ctx->stream) != cudaSuccess)
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        int rc = enqueue_level_points(ctx, level, d);
+        int rc = enqueue_level_points(ctx, level, d, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream); // host buffers are only borrowed for the call
         if (rc == MBAVO_OK && e != cudaSuccess)
             return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -1070,10 +1113,63 @@ extern "C"
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         int rc = MBAVO_OK;
         for (int l = 0; l < n_levels && rc == MBAVO_OK; ++l)
-            rc = enqueue_level_points(ctx, l, points + l);
+            rc = enqueue_level_points(ctx, l, points + l, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream); // one synchronisation for all levels
         if (rc == MBAVO_OK && e != cudaSuccess)
             return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e));
+        return rc;
+    }
+
+    // Keyframe + live frame + points of every level in ONE call: the level-0 images go up on the context's stream, followed by the
+    // pyramid / gradient / texel kernels; the points of all levels go up on a second stream at the same time (the two copies share
+    // the PCIe link, but the pyramid kernels run under the point copies); the context's stream then waits for the second one.
+    // One synchronisation — or none with MBAVO_UPLOAD_ASYNC, in which case the host buffers must stay valid and unchanged until
+    // the next blocking call on this context has returned (every evaluation / sweep entry point is one).
+    int mbavo_set_frame(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0,
+                        const unsigned char *const *cur_I0, int n_frames, const mbavo_level_points *points, int flags)
+    {
+        if (!ctx || !points || (!ref_I0 && !cur_I0))
+            return fail(MBAVO_EINVAL, "bad arguments");
+        DeviceGuard guard(ctx->device);
+        cudaStream_t s = ctx->stream;
+        if (cudaStreamQuery(s) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(s));
+        if (!ctx->copy_stream)
+        {
+            CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+        }
+        int rc = MBAVO_OK;
+        // points first: their copies are the bulk of the bytes and depend on nothing
+        for (int l = 0; l < n_levels && rc == MBAVO_OK; ++l)
+        {
+            if (!ref_I0 && !ctx->levels[l].has_key)
+                rc = fail(MBAVO_ENOTREADY, "level %d has no keyframe pyramid", l);
+            else
+                rc = enqueue_level_points(ctx, l, points + l, ctx->copy_stream);
+        }
+        if (rc == MBAVO_OK)
+        {
+            cudaError_t e = cudaEventRecord(ctx->copy_done, ctx->copy_stream);
+            if (e != cudaSuccess)
+                rc = fail(MBAVO_ECUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
+        }
+        if (rc == MBAVO_OK && ref_I0)
+            rc = enqueue_keyframe_pyramid(ctx, n_levels, mem, ref_I0, H0, W0, s);
+        if (rc == MBAVO_OK && cur_I0)
+            rc = enqueue_live_pyramid(ctx, n_levels, mem, cur_I0, n_frames, s);
+        if (rc == MBAVO_OK)
+        {
+            cudaError_t e = cudaStreamWaitEvent(s, ctx->copy_done, 0);
+            if (e != cudaSuccess)
+                rc = fail(MBAVO_ECUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));
+        }
+        if (rc != MBAVO_OK || !(flags & MBAVO_UPLOAD_ASYNC))
+        {
+            cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(s);
+            if (rc == MBAVO_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
+                return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        }
         return rc;
     }
 
@@ -1342,6 +1438,8 @@ extern "C"
         if (ctx->shard.world > 1 && pts < pl.P)
             return fail(MBAVO_ENOTREADY, "mbavo_shard_set_global_points has not been called for level %d", level);
         const long long nres = (pts - L.num_bad) * pl.F * pl.S;
+        if (nres <= 0)
+            return fail(MBAVO_EINVAL, "level %d: no residuals left (%lld points, %d flagged as outliers)", level, pts, L.num_bad);
         rc = run_evaluation(ctx, level, pl, ctx->packed_dev, true, 1.0 / (double)nres, huber_a);
         if (rc != MBAVO_OK)
             return rc;
@@ -1370,6 +1468,8 @@ extern "C"
             return rc;
         LevelStore &L = ctx->levels[level];
         const long long nres = num_residuals_global > 0 ? num_residuals_global : (long long)(pl.P - L.num_bad) * pl.F * pl.S;
+        if (nres <= 0)
+            return fail(MBAVO_EINVAL, "level %d: no residuals left (%d points, %d flagged as outliers)", level, pl.P, L.num_bad);
         if (kmin)
             *kmin = pl.kmin;
         if (knot_window)
@@ -1425,6 +1525,8 @@ extern "C"
                 if (ctx->shard.world > 1 && pts < pl.P)
                     return fail(MBAVO_ENOTREADY, "mbavo_shard_set_global_points has not been called for level %d", level);
                 const long long nres = (pts - L.num_bad) * pl.F * pl.S;
+                if (nres <= 0)
+                    return fail(MBAVO_EINVAL, "level %d: no residuals left (%lld points, %d flagged as outliers)", level, pts, L.num_bad);
                 SweepLaunch sw;
                 sw.gn.state = ctx->gn_state;
                 sw.gn.mode = pass == 0 ? 1 : 2;
@@ -1449,35 +1551,22 @@ extern "C"
                     seq_of_level[li] = ctx->seq;
             }
         }
-        // wait for the last level's scalars and the final knots, then check the earlier levels' tags
-        const volatile unsigned long long *pairs = reinterpret_cast<const volatile unsigned long long *>(ctx->result_host);
-        const int first_pair[2] = {4 * (nlev - 1), 4 * MBAVO_MAX_LEVELS}, num_pairs[2] = {4, 7 * n};
-        for (int part = 0; part < 2; ++part)
-        {
-            int done = 0;
-            for (unsigned long long spins = 1; done < num_pairs[part]; ++spins)
-            {
-                while (done < num_pairs[part] && pairs[2 * (first_pair[part] + done) + 1] == ctx->seq)
-                    ++done;
-                if (done < num_pairs[part] && (spins & 0xfff) == 0)
-                {
-                    cudaError_t e = cudaStreamQuery(ctx->stream);
-                    if (e != cudaSuccess && e != cudaErrorNotReady)
-                        return fail(MBAVO_ECUDA, "sweep failed: %s", cudaGetErrorString(e));
-                    if (e == cudaSuccess && pairs[2 * (first_pair[part] + done) + 1] != ctx->seq)
-                        return fail(MBAVO_ECUDA, "sweep finished without publishing its result");
-                }
-            }
-        }
-        std::atomic_thread_fence(std::memory_order_acquire);
+        // wait for the last level's scalars and the final knots, then read the earlier levels' (published before them)
+        double scal[4 * MBAVO_MAX_LEVELS], knots_out[7 * 16];
+        int rcw = wait_published(ctx, 4 * (nlev - 1), 4, ctx->seq, scal + 4 * (nlev - 1), "sweep");
+        if (rcw == MBAVO_OK)
+            rcw = wait_published(ctx, 4 * MBAVO_MAX_LEVELS, 7 * n, ctx->seq, knots_out, "sweep");
+        if (rcw != MBAVO_OK)
+            return rcw;
         bool fallback = false, peer_lost = false;
+        const volatile unsigned long long *words = reinterpret_cast<const volatile unsigned long long *>(ctx->result_host);
         for (int li = 0; li < nlev; ++li)
         {
             for (int e = 0; e < 4; ++e)
-                if (pairs[2 * (4 * li + e) + 1] != seq_of_level[li])
+                if (!read_published(words + 2 * (4 * li + e), seq_of_level[li], scal + 4 * li + e))
                     return fail(MBAVO_ECUDA, "sweep: level %d did not publish", level_coarse - li);
-            const double c = ctx->result_host[2 * (4 * li)], cc = ctx->result_host[2 * (4 * li + 1)];
-            if (ctx->result_host[2 * (4 * li + 2)] != 0.0)
+            const double c = scal[4 * li], cc = scal[4 * li + 1];
+            if (scal[4 * li + 2] != 0.0)
                 fallback = true;
             if (ctx->shard.world > 1 && (c != c || cc != cc))
                 peer_lost = true;
@@ -1488,17 +1577,17 @@ extern "C"
             return fail(MBAVO_ENCCL, "sharded sweep: a peer rank did not arrive within 4 s");
         if (fallback)
         {
-            fail(1, "device sweep declined: solve status %g %g %g %g ...", ctx->result_host[2 * 2], ctx->result_host[2 * 6],
-                 ctx->result_host[2 * 10], ctx->result_host[2 * 14]);
+            fail(1, "device sweep declined: solve status %g %g %g %g ...", scal[2], nlev > 1 ? scal[6] : 0.0, nlev > 2 ? scal[10] : 0.0,
+                 nlev > 3 ? scal[14] : 0.0);
             return 1;
         }
         ++ctx->device_sweeps;
         if (chain)
         {
             for (int e = 0; e < 3 * n; ++e)
-                knots_t[e] = ctx->result_host[2 * (4 * MBAVO_MAX_LEVELS + e)];
+                knots_t[e] = knots_out[e];
             for (int e = 0; e < 4 * n; ++e)
-                knots_R[e] = ctx->result_host[2 * (4 * MBAVO_MAX_LEVELS + 3 * n + e)];
+                knots_R[e] = knots_out[3 * n + e];
         }
         return MBAVO_OK;
     }
@@ -1577,13 +1666,18 @@ extern "C"
     }
 
     // ---- point sharding over the GPUs of one node ------------------------------------------------------------------
+    // The mailbox is zeroed HERE, by mbavo_shard_export, i.e. before its address / IPC handle can reach a peer — never in
+    // mbavo_shard_connect: a peer that connects first may already have written its first vector into this rank's mailbox
+    // by the time this rank connects, and a later memset would wipe it.  The sequence numbers restart at 0 with every
+    // export + connect round, so a connect requires a fresh export (mailbox_fresh).
     static int ensure_mailbox(mbavo_ctx *ctx)
     {
-        if (ctx->mailbox)
-            return MBAVO_OK;
-        CUDA_TRY(cudaMalloc(&ctx->mailbox, sizeof(Mailbox)));
+        if (!ctx->mailbox)
+            CUDA_TRY(cudaMalloc(&ctx->mailbox, sizeof(Mailbox)));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         CUDA_TRY(cudaMemset(ctx->mailbox, 0, sizeof(Mailbox)));
         CUDA_TRY(cudaDeviceSynchronize());
+        ctx->mailbox_fresh = true;
         return MBAVO_OK;
     }
 
@@ -1612,9 +1706,10 @@ extern "C"
         if (!ctx || world < 1 || world > kMaxShards || rank < 0 || rank >= world || (world > 1 && !handles && !mailbox_ptrs))
             return fail(MBAVO_EINVAL, "bad sharding arguments (world %d, rank %d, at most %d ranks)", world, rank, kMaxShards);
         DeviceGuard guard(ctx->device);
-        int rc = ensure_mailbox(ctx);
-        if (rc != MBAVO_OK)
-            return rc;
+        if (!ctx->mailbox || !ctx->mailbox_fresh)
+            return fail(MBAVO_ENOTREADY, "mbavo_shard_connect needs a fresh mbavo_shard_export of this context (it zeroes the mailbox "
+                                         "before the handle is shared; sequence numbers restart with every connection)");
+        ctx->mailbox_fresh = false;
         mbavo_shard_disconnect(ctx);
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         ShardParams sh{};
@@ -1648,10 +1743,7 @@ extern "C"
             }
         }
         ctx->shard = sh;
-        ctx->shard_seq = ctx->aux_seq = 0;
-        // the mailbox sequence numbers restart with the connection
-        CUDA_TRY(cudaMemsetAsync(ctx->mailbox, 0, sizeof(Mailbox), ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->shard_seq = ctx->aux_seq = 0; // the sequence numbers restart with the connection (mailbox zeroed by the export)
         return MBAVO_OK;
     }
 

@@ -222,10 +222,12 @@ namespace mbavo
         unsigned int *counter;    // last-block-done ticket
         double *packed_out;       // [E] device memory
         // Blocking evaluations: the last block also stores the packed vector straight into mapped pinned host memory, every
-        // element as ONE 16-byte store of (value, sequence number).  A 16-byte aligned store reaches host memory as a
-        // whole, so each element validates itself: the host spins until all E sequence fields show `seq` — no system-scope
-        // fence, no separate flag, no D2H copy, no stream synchronisation.
-        double2 *host_out;                    // [E] (value, seq as bits) in mapped pinned host memory, or nullptr
+        // element as two 8-byte words (tag | low half of the value bits) (tag | high half), tag = publish_tag(seq): EACH
+        // 8-byte word validates itself (an aligned 8-byte access is single-copy atomic in the PTX memory model; a 16-byte
+        // vector store is not guaranteed to be), so the host spins until both tags of all E elements show the evaluation's
+        // tag — no system-scope fence, no separate flag, no D2H copy, no stream synchronisation, and no reliance on how
+        // the 16-byte store crosses PCIe / C2C.
+        double2 *host_out;                    // [E] word pairs in mapped pinned host memory, or nullptr
         unsigned long long seq;
         ShardParams shard;                    // point sharding: the vector published is the sum over all ranks
         GnParams gn;                          // device-resident Gauss-Newton sweep
@@ -258,6 +260,29 @@ namespace mbavo
     };
 
     __host__ __device__ constexpr int packed_len(int NK) { return (6 * NK + 1) * (6 * NK + 2) / 2; }
+
+    // ---- self-validating result words (TrackParams::host_out) ------------------------------------------------------------
+    // 32-bit tag of a sequence number; never 0 (the buffer starts zeroed)
+    __host__ __device__ inline unsigned long long publish_tag(unsigned long long seq) { return seq % 0xffffffffull + 1ull; }
+#ifdef __CUDACC__
+    __device__ __forceinline__ void publish_host(double2 *slot, double v, unsigned long long seq)
+    {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v), tag = publish_tag(seq) << 32;
+        // one 16-byte store instruction; correctness only needs each aligned 8-byte half to arrive whole
+        *reinterpret_cast<ulonglong2 *>(slot) = make_ulonglong2(tag | (b & 0xffffffffull), tag | (b >> 32));
+    }
+#endif
+    // host side: true when both words of `slot` carry the tag of `seq`; *v receives the value
+    inline bool read_published(const volatile unsigned long long *slot, unsigned long long seq, double *v)
+    {
+        const unsigned long long w0 = slot[0], w1 = slot[1], tag = publish_tag(seq);
+        if ((w0 >> 32) != tag || (w1 >> 32) != tag)
+            return false;
+        const unsigned long long b = (w0 & 0xffffffffull) | (w1 << 32);
+        if (v)
+            __builtin_memcpy(v, &b, sizeof b);
+        return true;
+    }
 } // namespace mbavo
 
 #endif

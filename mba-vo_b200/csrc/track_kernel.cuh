@@ -44,12 +44,26 @@
 #ifndef MBAVO_UNROLL
 #define MBAVO_UNROLL 2
 #endif
+// cost-only pass: branch-free sample step (an invalid sample runs with zero weights and a safe tap) so that the unrolled
+// loop keeps several texel loads in flight per lane; MBAVO_COST_BRANCHLESS=0 restores the early exit
+#ifndef MBAVO_COST_BRANCHLESS
+#define MBAVO_COST_BRANCHLESS 1
+#endif
+#ifndef MBAVO_UNROLL_C
+#define MBAVO_UNROLL_C 4
+#endif
+// floor + float->int of the blur-sized tap offset by the 1.5 * 2^23 trick (full-rate FADD.RM / IADD) instead of
+// FRND + F2I (quarter-rate XU pipe)
+#ifndef MBAVO_MAGIC_FLOOR
+#define MBAVO_MAGIC_FLOOR 1
+#endif
 
 namespace mbavo
 {
     namespace
     {
         constexpr int kSampleUnroll = MBAVO_UNROLL;
+        constexpr int kCostUnroll = MBAVO_UNROLL_C;
         constexpr int MBAVO_MAX_LEVELS_DEV = 8; // host_out layout of a sweep: 4 scalars per level, then the final knots
 
 #ifdef MBAVO_PROFILE_PHASES
@@ -87,6 +101,21 @@ namespace mbavo
         __device__ __forceinline__ float2 halves(unsigned int v)
         {
             return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+        }
+        // floor(x) as float, and as int in `i`, for |x| < 2^22 (tap offsets are bounded by the image size): adding 1.5 * 2^23
+        // with round-down leaves the integer part in the mantissa — two full-rate FADDs and one IADD where floorf + (int)
+        // cost an FRND and an F2I on the quarter-rate XU pipe.  Out-of-range / NaN inputs give garbage that callers discard.
+        __device__ __forceinline__ float floor_to_int(float x, int &i)
+        {
+#if MBAVO_MAGIC_FLOOR
+            const float t = __fadd_rd(x, 12582912.0f);
+            i = __float_as_int(t) - 0x4B400000;
+            return t - 12582912.0f;
+#else
+            const float f = floorf(x);
+            i = (int)f;
+            return f;
+#endif
         }
         __device__ __forceinline__ float rcp_approx(float x)
         {
@@ -197,17 +226,18 @@ namespace mbavo
             // divisor stays N (…cost.cu:107-110).  NaN / inf coordinates fail the comparisons.
             float il, w00, w01, w10, w11;
             int idx, rowoff, xi;
-            if constexpr (WITH_J && MBAVO_BRANCHLESS)
+            if constexpr (WITH_J ? MBAVO_BRANCHLESS : MBAVO_COST_BRANCHLESS)
             {
             // Branch-free form: an invalid sample keeps going with zero weights, a safe tap address and il = 0 (so that
             // nothing non-finite reaches the sums).  Straight-line code lets the compiler overlap the loads of one sample
             // with the arithmetic of the previous one when the sample loop is unrolled.
                 const bool ok = duv.x >= ps.lox && duv.x <= ps.hix && duv.y >= ps.loy && duv.y <= ps.hiy;
                 il = ok ? il_raw : 0.f;
-                const float xf = floorf(duv.x), yf = floorf(duv.y);
+                int xo, yo;
+                const float xf = floor_to_int(duv.x, xo), yf = floor_to_int(duv.y, yo);
                 const float dx = duv.x - xf, dy = duv.y - yf; // exact
-                const int yi = ps.Y + (int)yf;
-                xi = ok ? ps.X + (int)xf : 0;
+                const int yi = ps.Y + yo;
+                xi = ok ? ps.X + xo : 0;
                 const float dxdy = dx * dy;
                 w00 = ok ? 1.0f - dx - dy + dxdy : 0.f, w01 = ok ? dx - dxdy : 0.f, w10 = ok ? dy - dxdy : 0.f, w11 = ok ? dxdy : 0.f;
                 idx = ok ? yi * lv.W + xi : 0;
@@ -218,10 +248,11 @@ namespace mbavo
                 if (!(duv.x >= ps.lox && duv.x <= ps.hix && duv.y >= ps.loy && duv.y <= ps.hiy))
                     return;
                 il = il_raw;
-                const float xf = floorf(duv.x), yf = floorf(duv.y);
+                int xo, yo;
+                const float xf = floor_to_int(duv.x, xo), yf = floor_to_int(duv.y, yo);
                 const float dx = duv.x - xf, dy = duv.y - yf; // exact
-                const int yi = ps.Y + (int)yf;
-                xi = ps.X + (int)xf;
+                const int yi = ps.Y + yo;
+                xi = ps.X + xo;
                 // bilinear_interpolation, compute_pixel_intensity.h:40-68
                 const float dxdy = dx * dy;
                 w00 = 1.0f - dx - dy + dxdy, w01 = dx - dxdy, w10 = dy - dxdy, w11 = dxdy;
@@ -730,6 +761,7 @@ namespace mbavo
                             }
                             else
                             {
+#pragma unroll kCostUnroll
                                 for (int i = phase; i < N; i += PH) // cost only: the segment of a sample is irrelevant
                                     sample_step<K, NK, false, PACKED, 0>(SmemRec{samples_s + i * REC}, ps, lv, fxy, sumI, J);
                             }
@@ -988,10 +1020,9 @@ namespace mbavo
                     st->cand_cost = cc;
                     if (prm.host_out)
                     {
-                        const double tag = __longlong_as_double((long long)prm.seq);
                         double2 *o = prm.host_out + 4 * gp.slot;
-                        o[0] = make_double2(st->cost, tag), o[1] = make_double2(cc, tag);
-                        o[2] = make_double2((double)st->status, tag), o[3] = make_double2(st->model, tag);
+                        publish_host(o + 0, st->cost, prm.seq), publish_host(o + 1, cc, prm.seq);
+                        publish_host(o + 2, (double)st->status, prm.seq), publish_host(o + 3, st->model, prm.seq);
                     }
                     if (gp.chain && st->status == 0 && cc < st->cost) // the finer level starts from the candidate
                     {
@@ -1003,12 +1034,11 @@ namespace mbavo
                     }
                     if (gp.last && prm.host_out)
                     {
-                        const double tag = __longlong_as_double((long long)prm.seq);
                         double2 *o = prm.host_out + 4 * MBAVO_MAX_LEVELS_DEV;
                         for (int e = 0; e < 3 * gp.n_knots; ++e)
-                            o[e] = make_double2(st->cur_t[e], tag);
+                            publish_host(o + e, st->cur_t[e], prm.seq);
                         for (int e = 0; e < 4 * gp.n_knots; ++e)
-                            o[3 * gp.n_knots + e] = make_double2(st->cur_R[e], tag);
+                            publish_host(o + 3 * gp.n_knots + e, st->cur_R[e], prm.seq);
                     }
                 }
                 __syncthreads();
@@ -1018,7 +1048,7 @@ namespace mbavo
                 const double s = fin_s[e];
                 prm.packed_out[e] = s;
                 if (prm.host_out && !gp.state)
-                    prm.host_out[e] = make_double2(s, __longlong_as_double((long long)prm.seq)); // one 16-byte store
+                    publish_host(prm.host_out + e, s, prm.seq);
             }
             MBAVO_STAMP(10);
             if (threadIdx.x == 0)

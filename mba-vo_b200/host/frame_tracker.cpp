@@ -62,31 +62,37 @@ extern "C"
         if (!ctx || !tr || !cur_I0 || !opt || !res || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS)
             return MBAVO_EINVAL;
         std::memset(res, 0, sizeof(*res));
+        const double dt_frame = capture_time - tr->prev_timestamp; // :120
+        if (!(dt_frame > 0) || !(exposure_time > 0))
+            return MBAVO_EINVAL;
+        // Everything fallible runs on a COPY of the tracker state; *tr is committed only when the whole frame has succeeded, so a
+        // failed call (time-out of a peer rank, exposure outside the spline, a CUDA error) can be retried without the
+        // constant-velocity prediction being applied twice.
+        mbavo_tracker w = *tr;
         const unsigned char *frames[1] = {cur_I0};
         int rc = mbavo_set_live_pyramid(ctx, n_levels, mem, frames, 1); // :112-117
         if (rc != MBAVO_OK)
             return rc;
-        const double dt_frame = capture_time - tr->prev_timestamp; // :120
-        if (!(dt_frame > 0))
-            return MBAVO_EINVAL;
-        tr->start_time = capture_time - 0.5 * exposure_time;       // :144
-        rc = mbavo_predict_spline(tr->num_ctrl_knots, tr->knots_t, tr->knots_R, tr->velocity, dt_frame); // :122-145
+        w.start_time = capture_time - 0.5 * exposure_time;       // :144
+        rc = mbavo_predict_spline(w.num_ctrl_knots, w.knots_t, w.knots_R, w.velocity, dt_frame); // :122-145
         if (rc != MBAVO_OK)
             return rc;
         rc = mbavo_set_frame_times(ctx, 1, &capture_time, &exposure_time); // uploadDataToGpu, :701-719
         if (rc != MBAVO_OK)
             return rc;
+        mbavo_frame_result out;
+        std::memset(&out, 0, sizeof out);
         for (int level = n_levels - 1; level >= 0; --level) // optimizeTrajectory, :571-575
         {
-            rc = mbavo_optimize_level(ctx, level, tr->spline_deg_k, tr->start_time, tr->sample_dt, tr->num_ctrl_knots, tr->knots_t,
-                                      tr->knots_R, opt, &res->levels[level]);
+            rc = mbavo_optimize_level(ctx, level, w.spline_deg_k, w.start_time, w.sample_dt, w.num_ctrl_knots, w.knots_t, w.knots_R, opt,
+                                      &out.levels[level]);
             if (rc == MBAVO_ENOTREADY && level > 0)
                 continue; // a coarse level the selection left without points
             if (rc != MBAVO_OK)
                 return rc;
-            res->levels_run |= 1 << level;
+            out.levels_run |= 1 << level;
         }
-        const mbavo_spline sp = spline_of(tr);
+        const mbavo_spline sp = spline_of(&w);
         // isKeyframe statistics (:205-248): poses at the capture time and at -/+ half the exposure
         double poses[21];
         const double times[3] = {capture_time, capture_time - 0.5 * exposure_time, capture_time + 0.5 * exposure_time};
@@ -96,19 +102,21 @@ extern "C"
             if (rc != MBAVO_OK)
                 return rc;
         }
-        rc = mbavo_keyframe_stats(ctx, 0, poses, &res->avg_flow, &res->avg_kernel_len);
+        rc = mbavo_keyframe_stats(ctx, 0, poses, &out.avg_flow, &out.avg_kernel_len);
         if (rc != MBAVO_OK)
             return rc;
         // velocity from the neighbouring frames (:155-162); poses[0..6] is the pose at the capture time
-        rc = mbavo_frame_velocity(tr->prev_t, tr->prev_q, poses, poses + 3, dt_frame, tr->velocity);
+        rc = mbavo_frame_velocity(w.prev_t, w.prev_q, poses, poses + 3, dt_frame, w.velocity);
         if (rc != MBAVO_OK)
             return rc;
-        std::memcpy(tr->prev_t, poses, sizeof(double) * 3);
-        std::memcpy(tr->prev_q, poses + 3, sizeof(double) * 4);
-        tr->prev_timestamp = capture_time; // :200
-        std::memcpy(res->t_cur2key, poses, sizeof(double) * 3);
-        std::memcpy(res->q_cur2key, poses + 3, sizeof(double) * 4);
-        compose(tr->keyframe_t, tr->keyframe_q, poses, poses + 3, res->t_cur2world, res->q_cur2world); // :203
+        std::memcpy(w.prev_t, poses, sizeof(double) * 3);
+        std::memcpy(w.prev_q, poses + 3, sizeof(double) * 4);
+        w.prev_timestamp = capture_time; // :200
+        std::memcpy(out.t_cur2key, poses, sizeof(double) * 3);
+        std::memcpy(out.q_cur2key, poses + 3, sizeof(double) * 4);
+        compose(w.keyframe_t, w.keyframe_q, poses, poses + 3, out.t_cur2world, out.q_cur2world); // :203
+        *tr = w;
+        *res = out;
         return MBAVO_OK;
     }
 

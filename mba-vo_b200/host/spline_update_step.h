@@ -94,6 +94,17 @@ namespace SLAM
             mbavo_ctx *mbavo = nullptr;
             int mbavo_max_num_frames = 0;
             int mbavo_max_num_ctrl_knots = 0;
+            // new: the small arrays above (capture / exposure times, live-image pointers, control knots) live in ONE device
+            // slab so that an evaluation reads back what the tracker uploaded with a single copy
+            unsigned char *mbavo_slab = nullptr;
+            int mbavo_slab_bytes = 0;
+            // new, opt-in: 1 = keep the level of the previous evaluation (keyframe texels included) while the image /
+            // keypoint / pattern pointers, the sizes and mbavo_keyframe_epoch are unchanged, instead of re-deriving it on
+            // every call.  A caller that rewrites the keyframe image or its gradient behind an unchanged pointer must bump
+            // mbavo_keyframe_epoch (tmpProcessKeyframe is the one place, tracker.cpp:346-409).  0 (default) re-derives always.
+            int mbavo_texel_cache = 0;
+            int mbavo_keyframe_epoch = 0;
+            struct LevelKey *mbavo_level_key = nullptr; // state of that cache (owned by the storages)
         };
 
         // spline_update_step.h:60-68 of the reference: sizes the context once from the tracker's maxima
