@@ -412,6 +412,11 @@ long long mbavo_kernel_launches(const mbavo_ctx *ctx);
 /* Number of mbavo_gn_sweep calls that ran on the device-resident path (solve, candidate and commit inside the kernels,
  * one host wait) rather than evaluation by evaluation. */
 long long mbavo_device_sweeps(const mbavo_ctx *ctx);
+/* ... of which as ONE persistent launch: the pose kernel for the starting knots + sweep_kernel, which runs the Hessian pass,
+ * the solve, the candidate's sample records and the cost pass of every level inside one resident grid of one block per SM
+ * (passes separated by a ticket + flag barrier).  Taken when all levels share the exposure-sample count and the patch size,
+ * track one frame, have keyframe texels, and the knot window is one of {k=2: 2..5, k=4: 4}; MBAVO_NO_PERSISTENT=1 disables it. */
+long long mbavo_persistent_sweeps(const mbavo_ctx *ctx);
 
 /* 1 if the kernels of `level` read the keyframe through the packed fp16 texels built by mbavo_set_level (every
  * gradient value exactly representable in fp16 — always the case for Gradient.h's central differences of an 8-bit

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "mbavo_set_live_images", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
-    "mbavo_device_sweeps", "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
+    "mbavo_device_sweeps", "mbavo_persistent_sweeps", "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
     "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points", "mbavo_synthesize_blurred",
     "mbavo_keyframe_stats", "mbavo_select_points", "mbavo_get_points", "mbavo_se3_exp", "mbavo_se3_log",
     "mbavo_spline_pose", "mbavo_spline_transform_by_right", "mbavo_spline_transform_to", "mbavo_predict_spline", "mbavo_frame_velocity",
@@ -125,6 +125,7 @@ def load_library() -> C.CDLL:
     lib.mbavo_last_error.restype = C.c_char_p
     lib.mbavo_kernel_launches.restype = C.c_longlong
     lib.mbavo_device_sweeps.restype = C.c_longlong
+    lib.mbavo_persistent_sweeps.restype = C.c_longlong
     lib.mbavo_last_kernel_ms.restype = C.c_float
     for name in EXPORTED_SYMBOLS:
         getattr(lib, name)
@@ -433,6 +434,9 @@ class Context:
 
     def device_sweeps(self) -> int:
         return int(self.lib.mbavo_device_sweeps(self._h))
+
+    def persistent_sweeps(self) -> int:
+        return int(self.lib.mbavo_persistent_sweeps(self._h))
 
     def level_uses_texels(self, level: int) -> int:
         return int(self.lib.mbavo_level_uses_texels(self._h, C.c_int(level)))

@@ -23,6 +23,9 @@ namespace mbavo
     cudaError_t launch_track_kernel(int K, int NK, bool with_j, bool big, const TrackParams &prm, dim3 grid, size_t smem,
                                     cudaStream_t stream, int *query_occupancy, bool dependent);
     size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool big, int N, int S, int TP);
+    size_t sweep_kernel_smem_bytes(int K, int NK, int N, int S, int TP);
+    cudaError_t launch_sweep_kernel(int K, int NK, const SweepParams &sp, const EvalStage &stage, int num_sms, size_t smem,
+                                    cudaStream_t stream, bool dependent, int *query_occupancy);
     cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,
                                    int *inexact, cudaStream_t stream);
     cudaError_t launch_pyr_down_kernel(const unsigned char *src, int Ws, unsigned char *dst, int Hd, int Wd, cudaStream_t stream);
@@ -112,6 +115,11 @@ struct mbavo_ctx
     size_t sel_cells_cap = 0, sel_depth_cap = 0;
     int *sel_count_dev = nullptr, *sel_count_host = nullptr;
     long long device_sweeps = 0;                   // sweeps completed on the device-resident path
+    long long persistent_sweeps = 0;               // ... of which inside ONE launch (sweep_kernel)
+    bool use_persistent = true;                    // MBAVO_NO_PERSISTENT=1: one launch per pass
+    SweepCtl *sweep_ctl = nullptr;                 // pass barrier of the persistent sweep kernel
+    unsigned int sweep_base = 0;                   // value of sweep_ctl->done after the sweeps issued so far
+    bool shard_shares_device = false;              // a peer rank lives on this GPU: persistent grids could not be co-resident
     bool use_device_sweep = true;                  // MBAVO_NO_DEVICE_SWEEP=1: every evaluation returns to the host
     long long big_block_batches = 2000; // MBAVO_BIG_BLOCK_BATCHES: Hessian pass uses the big block shape from this many batches
     bool use_pdl = true;     // MBAVO_NO_PDL=1: tracking kernel fully serialised behind the pose kernel
@@ -467,37 +475,32 @@ namespace
         int buf_select = kBufA; // record buffer the pose kernel writes and the tracking kernel reads
     };
 
-    int run_evaluation(mbavo_ctx *ctx, int level, const EvalPlan &pl, double *packed_dev_out, bool blocking, double inv_num_residuals,
-                       double huber_a, const SweepLaunch *sweep = nullptr)
+    // per-block partials of `blocks` blocks with E elements each
+    int ensure_block_partials(mbavo_ctx *ctx, size_t need)
     {
-        LevelStore &L = ctx->levels[level];
-        cudaStream_t s = ctx->stream;
-        size_t need = (size_t)pl.grid.x * pl.grid.y * pl.E;
         if (need > ctx->block_partials_cap)
         {
-            CUDA_TRY(cudaStreamSynchronize(s));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             cudaFree(ctx->block_partials);
             ctx->block_partials = nullptr;
             CUDA_TRY(cudaMalloc(&ctx->block_partials, need * sizeof(double)));
             ctx->block_partials_cap = need;
         }
-        L.last_eval_frames = pl.F;
-        const int buf_select = sweep ? sweep->buf_select : (int)kBufA;
-        if (!(sweep && sweep->skip_pose))
-        {
-            ctx->launches += 1;
-            CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, (pl.with_h || (sweep && sweep->pose_with_j)) ? 1 : 0, ctx->samples,
-                                        ctx->mid, ctx->seg_end, s, sweep ? sweep->gn.state : nullptr, sweep ? sweep->knots_from : 0,
-                                        sweep && !sweep->first, buf_select, ctx->samples_stride, kMidDoubles * kMaxFrames,
-                                        kMaxSegments * kMaxFrames));
-        }
-        ctx->launches += 1;
-        TrackParams prm{};
+        return MBAVO_OK;
+    }
+
+    // the launch parameter of one pass (one tracking-kernel launch, or one pass of the persistent sweep kernel); consumes one
+    // result sequence number when blocking and one exchange sequence number when sharded
+    void fill_track_params(mbavo_ctx *ctx, int level, const EvalPlan &pl, double *packed_dev_out, bool blocking, double inv_num_residuals,
+                           double huber_a, const SweepLaunch *sweep, TrackParams &prm)
+    {
+        LevelStore &L = ctx->levels[level];
+        prm = TrackParams{};
         prm.lv = L.dev;
         prm.samples = ctx->samples;
         prm.mid = ctx->mid;
         prm.seg_end = ctx->seg_end;
-        prm.buf_select = buf_select;
+        prm.buf_select = sweep ? sweep->buf_select : (int)kBufA;
         prm.samples_stride = ctx->samples_stride, prm.mid_stride = kMidDoubles * kMaxFrames, prm.seg_end_stride = kMaxSegments * kMaxFrames;
         prm.inv_num_residuals = inv_num_residuals;
         prm.huber_a = (float)huber_a;
@@ -523,6 +526,29 @@ namespace
             prm.seq = ++ctx->seq;
             ctx->result_len = pl.E;
         }
+    }
+
+    int run_evaluation(mbavo_ctx *ctx, int level, const EvalPlan &pl, double *packed_dev_out, bool blocking, double inv_num_residuals,
+                       double huber_a, const SweepLaunch *sweep = nullptr)
+    {
+        LevelStore &L = ctx->levels[level];
+        cudaStream_t s = ctx->stream;
+        int rc = ensure_block_partials(ctx, (size_t)pl.grid.x * pl.grid.y * pl.E);
+        if (rc != MBAVO_OK)
+            return rc;
+        L.last_eval_frames = pl.F;
+        const int buf_select = sweep ? sweep->buf_select : (int)kBufA;
+        if (!(sweep && sweep->skip_pose))
+        {
+            ctx->launches += 1;
+            CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, (pl.with_h || (sweep && sweep->pose_with_j)) ? 1 : 0, ctx->samples,
+                                        ctx->mid, ctx->seg_end, s, sweep ? sweep->gn.state : nullptr, sweep ? sweep->knots_from : 0,
+                                        sweep && !sweep->first, buf_select, ctx->samples_stride, kMidDoubles * kMaxFrames,
+                                        kMaxSegments * kMaxFrames));
+        }
+        ctx->launches += 1;
+        TrackParams prm;
+        fill_track_params(ctx, level, pl, packed_dev_out, blocking, inv_num_residuals, huber_a, sweep, prm);
         if (ctx->timing)
             CUDA_TRY(cudaEventRecord(ctx->ev0, s));
         // event timing brackets the tracking kernel alone, so it is then launched fully serialised
@@ -563,6 +589,88 @@ namespace
     }
 
     int wait_result(mbavo_ctx *ctx) { return wait_published(ctx, 0, ctx->result_len, ctx->seq, ctx->result_vals.data(), "evaluation"); }
+
+    // The coarse-to-fine sweep as TWO launches: the pose kernel for the knots the sweep starts from, then sweep_kernel, which runs
+    // the Hessian pass and the cost pass of every level inside one resident grid (mbavo_device.h, SweepCtl).  Returns 1 when there
+    // is no instantiation for this window (the caller runs the sweep pass by pass), < 0 on errors.
+    int run_persistent_sweep(mbavo_ctx *ctx, int level_coarse, int nlev, int chain, const mbavo_spline *sp, double radius, double huber_a,
+                             unsigned long long *seq_of_level)
+    {
+        cudaStream_t s = ctx->stream;
+        EvalPlan plans[2 * MBAVO_MAX_LEVELS];
+        size_t smem = 0, partials = 0;
+        for (int li = 0; li < nlev; ++li)
+            for (int pass = 0; pass < 2; ++pass)
+            {
+                EvalPlan &pl = plans[2 * li + pass];
+                int rc = plan_evaluation(ctx, level_coarse - li, sp, pass == 0, pl);
+                if (rc != MBAVO_OK)
+                    return rc;
+                if (pl.K != plans[0].K || pl.NK != plans[0].NK || pl.kmin != plans[0].kmin || pl.N != plans[0].N || pl.F != 1)
+                    return 1;
+                const size_t need = sweep_kernel_smem_bytes(pl.K, plans[0].NK, pl.N, pl.S, pl.TP);
+                smem = need > smem ? need : smem;
+                partials = (size_t)ctx->num_sms * pl.E > partials ? (size_t)ctx->num_sms * pl.E : partials;
+            }
+        if (smem > 200 * 1024)
+            return 1;
+        int occ = 0;
+        cudaError_t e = launch_sweep_kernel(plans[0].K, plans[0].NK, SweepParams{}, ctx->stage, ctx->num_sms, smem, s, false, &occ);
+        if (e == cudaErrorNotSupported || (e == cudaSuccess && occ < 1))
+        {
+            cudaGetLastError();
+            return 1;
+        }
+        if (e != cudaSuccess)
+            return fail(MBAVO_ECUDA, "sweep kernel: %s", cudaGetErrorString(e));
+        if (!ctx->sweep_ctl)
+        {
+            CUDA_TRY(cudaMalloc(&ctx->sweep_ctl, sizeof(SweepCtl)));
+            CUDA_TRY(cudaMemset(ctx->sweep_ctl, 0, sizeof(SweepCtl)));
+            ctx->sweep_base = 0;
+        }
+        int rc = ensure_block_partials(ctx, partials);
+        if (rc != MBAVO_OK)
+            return rc;
+        static thread_local SweepParams prm; // ~10 KB: kept off the stack of the caller's thread
+        prm.n_levels = nlev, prm.ctl = ctx->sweep_ctl, prm.base = ctx->sweep_base;
+        for (int li = 0; li < nlev; ++li)
+        {
+            const int level = level_coarse - li;
+            LevelStore &L = ctx->levels[level];
+            L.last_eval_frames = 1;
+            for (int pass = 0; pass < 2; ++pass)
+            {
+                const EvalPlan &pl = plans[2 * li + pass];
+                const long long pts = ctx->shard.world > 1 ? ctx->points_global[level] : pl.P;
+                if (ctx->shard.world > 1 && pts < pl.P)
+                    return fail(MBAVO_ENOTREADY, "mbavo_shard_set_global_points has not been called for level %d", level);
+                const long long nres = (pts - L.num_bad) * pl.F * pl.S;
+                if (nres <= 0)
+                    return fail(MBAVO_EINVAL, "level %d: no residuals left (%lld points, %d flagged as outliers)", level, pts, L.num_bad);
+                SweepLaunch sw;
+                sw.gn.state = ctx->gn_state;
+                sw.gn.mode = pass == 0 ? 1 : 2;
+                sw.gn.n_knots = sp->num_ctrl_knots, sw.gn.kmin = pl.kmin;
+                sw.gn.chain = chain, sw.gn.slot = li, sw.gn.last = (li == nlev - 1) ? 1 : 0;
+                sw.gn.radius = radius;
+                // record buffers: the knots the sweep stands on / the candidate; the roles swap on the device at every commit
+                sw.buf_select = pass == 0 ? (li == 0 ? kBufA : kBufCur) : kBufCand;
+                fill_track_params(ctx, level, pl, ctx->packed_dev, true, 1.0 / (double)nres, huber_a, &sw, prm.pass[2 * li + pass]);
+                if (pass == 1)
+                    seq_of_level[li] = ctx->seq;
+            }
+        }
+        // records of the starting knots (with Jacobians) into buffer A; initialises the sweep state (cur knots, status, cur_buf = 0)
+        ctx->launches += 2;
+        CUDA_TRY(launch_pose_kernel(plans[0].K, ctx->stage, plans[0].N, 1, ctx->samples, ctx->mid, ctx->seg_end, s, ctx->gn_state, 0, false, kBufA,
+                                    ctx->samples_stride, kMidDoubles * kMaxFrames, kMaxSegments * kMaxFrames));
+        e = launch_sweep_kernel(plans[0].K, plans[0].NK, prm, ctx->stage, ctx->num_sms, smem, s, ctx->use_pdl, nullptr);
+        if (e != cudaSuccess)
+            return fail(MBAVO_ECUDA, "sweep kernel launch: %s", cudaGetErrorString(e));
+        ctx->sweep_base += 2u * (unsigned int)nlev;
+        return MBAVO_OK;
+    }
 } // namespace
 
 extern "C"
@@ -634,6 +742,8 @@ extern "C"
         ctx->use_pdl = !(g && g[0] == '1');
         g = getenv("MBAVO_NO_DEVICE_SWEEP");
         ctx->use_device_sweep = !(g && g[0] == '1');
+        g = getenv("MBAVO_NO_PERSISTENT");
+        ctx->use_persistent = !(g && g[0] == '1');
         g = getenv("MBAVO_BIG_BLOCK_BATCHES");
         if (g)
             ctx->big_block_batches = atoll(g);
@@ -681,6 +791,7 @@ extern "C"
         cudaFree(ctx->mailbox);
         cudaFree(ctx->phase_times_dev);
         cudaFree(ctx->gn_state);
+        cudaFree(ctx->sweep_ctl);
         cudaFree(ctx->kf_dev);
         cudaFreeHost(ctx->kf_host);
         cudaFree(ctx->sel_cells);
@@ -1511,7 +1622,30 @@ extern "C"
         for (int li = 1; li < nlev && reuse; ++li)
             reuse = ctx->levels[level_coarse - li].set && ctx->levels[level_coarse].set &&
                     ctx->levels[level_coarse - li].dev.N == ctx->levels[level_coarse].dev.N;
-        for (int li = 0; li < nlev; ++li)
+        // ---- the whole sweep inside ONE launch (sweep_kernel) when every level shares one exposure-sample count, one frame, the
+        // texel path and a knot window the kernel is instantiated for; else pass by pass below
+        bool persistent = reuse || (nlev == 1 && ctx->shard.world <= 1);
+        if (ctx->shard.world > 1)
+        {
+            persistent = !ctx->shard_shares_device; // every rank needs its whole GPU
+            for (int li = 1; li < nlev && persistent; ++li)
+                persistent = ctx->levels[level_coarse - li].set && ctx->levels[level_coarse].set &&
+                             ctx->levels[level_coarse - li].dev.N == ctx->levels[level_coarse].dev.N;
+        }
+        persistent = persistent && ctx->use_persistent;
+        for (int li = 0; li < nlev && persistent; ++li)
+        {
+            const LevelStore &L = ctx->levels[level_coarse - li];
+            persistent = L.set && L.dev.F == 1 && L.dev.ref_pair != nullptr && L.dev.S == ctx->levels[level_coarse].dev.S;
+        }
+        if (persistent)
+        {
+            const int rcp = run_persistent_sweep(ctx, level_coarse, nlev, chain, &sp, radius, huber_a, seq_of_level);
+            if (rcp < 0)
+                return rcp;
+            persistent = rcp == MBAVO_OK; // 1: no instantiation for this window, fall through
+        }
+        for (int li = 0; li < nlev && !persistent; ++li)
         {
             const int level = level_coarse - li;
             LevelStore &L = ctx->levels[level];
@@ -1557,7 +1691,18 @@ extern "C"
         if (rcw == MBAVO_OK)
             rcw = wait_published(ctx, 4 * MBAVO_MAX_LEVELS, 7 * n, ctx->seq, knots_out, "sweep");
         if (rcw != MBAVO_OK)
+        {
+            if (persistent && ctx->sweep_ctl)
+            {
+                // a block gave up (SweepCtl::abort) or the launch failed: drain the stream and re-arm the pass barrier
+                cudaStreamSynchronize(ctx->stream);
+                cudaMemset(ctx->sweep_ctl, 0, sizeof(SweepCtl));
+                cudaMemset(ctx->counter, 0, sizeof(unsigned int));
+                cudaGetLastError();
+                ctx->sweep_base = 0;
+            }
             return rcw;
+        }
         bool fallback = false, peer_lost = false;
         const volatile unsigned long long *words = reinterpret_cast<const volatile unsigned long long *>(ctx->result_host);
         for (int li = 0; li < nlev; ++li)
@@ -1582,6 +1727,8 @@ extern "C"
             return 1;
         }
         ++ctx->device_sweeps;
+        if (persistent)
+            ++ctx->persistent_sweeps;
         if (chain)
         {
             for (int e = 0; e < 3 * n; ++e)
@@ -1723,6 +1870,8 @@ extern "C"
                 // same process: plain peer access (a no-op on the same device)
                 cudaPointerAttributes at{};
                 CUDA_TRY(cudaPointerGetAttributes(&at, mailbox_ptrs[r]));
+                if (at.device == ctx->device)
+                    ctx->shard_shares_device = true;
                 if (at.device != ctx->device)
                 {
                     cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
@@ -1760,6 +1909,7 @@ extern "C"
             ctx->peer_is_ipc[r] = false;
         }
         ctx->shard = ShardParams{};
+        ctx->shard_shares_device = false;
         return MBAVO_OK;
     }
 
@@ -1793,6 +1943,7 @@ extern "C"
 
     long long mbavo_kernel_launches(const mbavo_ctx *ctx) { return ctx ? ctx->launches : 0; }
     long long mbavo_device_sweeps(const mbavo_ctx *ctx) { return ctx ? ctx->device_sweeps : 0; }
+    long long mbavo_persistent_sweeps(const mbavo_ctx *ctx) { return ctx ? ctx->persistent_sweeps : 0; }
 
     int mbavo_level_uses_texels(const mbavo_ctx *ctx, int level)
     {

@@ -118,6 +118,16 @@ namespace mbavo
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
         return v;
     }
+    __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p)
+    {
+        unsigned int v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v)
+    {
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    }
     __device__ __forceinline__ unsigned long long global_timer_ns()
     {
         unsigned long long t;
@@ -233,6 +243,27 @@ namespace mbavo
         GnParams gn;                          // device-resident Gauss-Newton sweep
         unsigned long long *phase_times;      // development: globaltimer stamps of kernel phases (MBAVO_PROFILE_PHASES builds),
         int trace_row;                        // 16 stamps per row; row = ordinal of the launch since the trace was armed
+    };
+
+    // ---- persistent sweep (one launch for the whole coarse-to-fine Gauss-Newton sweep) ---------------------------------------
+    // sweep_kernel runs every pass of mbavo_gn_sweep — Hessian pass and cost pass of every level — inside ONE grid of one
+    // block per SM.  The passes are separated by a ticket + flag barrier: every block announces its per-block partials with
+    // the ticket of TrackParams::counter, the LAST block to arrive finishes the pass (sum of the partials, exchange, solve,
+    // candidate knots AND the candidate's sample records; or record / commit) and then releases SweepCtl::done, which the
+    // other blocks acquire before they read the records of the next pass.  `done` counts passes monotonically over the
+    // life of the context, so nothing has to be reset between sweeps.
+    struct SweepCtl
+    {
+        unsigned int done;  // passes completed so far
+        int abort;          // a block gave up waiting (4 s): every block leaves the kernel
+    };
+    constexpr int kMaxSweepLevels = 8; // MBAVO_MAX_LEVELS of include/mbavo.h
+    struct SweepParams
+    {
+        TrackParams pass[2 * kMaxSweepLevels]; // [2 li]: Hessian pass of level li (coarse first), [2 li + 1]: its cost pass
+        int n_levels;
+        SweepCtl *ctl;
+        unsigned int base;                     // value of ctl->done when this sweep starts
     };
 
     // ---- semi-dense point selection (select_kernel.cu) -------------------------------------------------------------------

@@ -107,14 +107,48 @@ namespace mbavo
         return cudaGetLastError();
     }
 
+    cudaError_t sweep_dispatch_k2(int NK, const SweepParams &sp, const EvalStage &stage, int num_sms, size_t smem, cudaStream_t stream,
+                                  bool dependent, int *query_occupancy);
+    cudaError_t sweep_dispatch_k2_hi(int NK, const SweepParams &sp, const EvalStage &stage, int num_sms, size_t smem, cudaStream_t stream,
+                                     bool dependent, int *query_occupancy);
+    cudaError_t sweep_dispatch_k4(int NK, const SweepParams &sp, const EvalStage &stage, int num_sms, size_t smem, cudaStream_t stream,
+                                  bool dependent, int *query_occupancy);
+
+    // persistent sweep kernel: instantiated for the texel path and the windows listed here; cudaErrorNotSupported otherwise
+    // (the caller then runs the sweep pass by pass)
+    cudaError_t launch_sweep_kernel(int K, int NK, const SweepParams &sp, const EvalStage &stage, int num_sms, size_t smem,
+                                    cudaStream_t stream, bool dependent, int *query_occupancy)
+    {
+        if (K == 2 && NK <= 3)
+            return sweep_dispatch_k2(NK, sp, stage, num_sms, smem, stream, dependent, query_occupancy);
+        if (K == 2)
+            return sweep_dispatch_k2_hi(NK, sp, stage, num_sms, smem, stream, dependent, query_occupancy);
+        if (K == 4)
+            return sweep_dispatch_k4(NK, sp, stage, num_sms, smem, stream, dependent, query_occupancy);
+        return cudaErrorNotSupported;
+    }
+
+    size_t track_pass_smem_bytes(int K, int NK, bool with_j, int kWarpsPerBlock, int N, int S, int TP);
     size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool big, int N, int S, int TP)
+    {
+        return track_pass_smem_bytes(K, NK, with_j, track_warps(with_j, NK, big), N, S, TP);
+    }
+    // both passes of a level inside the persistent sweep kernel (block shape of the big Hessian pass)
+    size_t sweep_kernel_smem_bytes(int K, int NK, int N, int S, int TP)
+    {
+        const int w = track_warps(true, NK, true);
+        const size_t a = track_pass_smem_bytes(K, NK, true, w, N, S, TP), b = track_pass_smem_bytes(K, NK, false, w, N, S, TP);
+        return a > b ? a : b;
+    }
+
+    size_t track_pass_smem_bytes(int K, int NK, bool with_j, int kWarpsPerBlock, int N, int S, int TP)
     {
         const int REC = sample_rec_floats(K);
         const int D1 = with_j ? 6 * NK + 1 : 1, D1E = (D1 + 1) & ~1;
         const int PITCH = (D1E / 2) % 2 == 1 ? D1E : D1E + 2, T = D1E / 2, NT = T * (T + 1) / 2;
         const int E = with_j ? packed_len(NK) : 1;
         const int rho_per_warp = max(32, TP * S);
-        const int kWarpsPerBlock = track_warps(with_j, NK, big), kThreads = kWarpsPerBlock * 32;
+        const int kThreads = kWarpsPerBlock * 32;
         size_t main_bytes = (size_t)N * REC * 4 + 8 * 4 + kMidDoubles * 8 + (size_t)kWarpsPerBlock * 32 * 32 /* PixelRec */ +
                             (size_t)S * 8 +
                             (size_t)kWarpsPerBlock * rho_per_warp * 4 + (size_t)((NT + 7) & ~7) * 2 +

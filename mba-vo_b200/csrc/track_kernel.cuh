@@ -30,6 +30,7 @@
 #ifndef MBAVO_TRACK_KERNEL_CUH_
 #define MBAVO_TRACK_KERNEL_CUH_
 #include "mbavo_device.h"
+#include "pose_device.cuh"
 
 #include <cuda_fp16.h>
 
@@ -473,7 +474,8 @@ namespace mbavo
 #ifdef MBAVO_SMEM_SOLVE
             constexpr int kRegSolveMaxD = 0;
 #else
-            constexpr int kRegSolveMaxD = 12; // two-knot window, the tracker's own mode; ~31 KB of unrolled shuffle code per instantiation
+            constexpr int kRegSolveMaxD = 24; // windows of up to 4 knots: 2 D registers per lane for the row; the shared-memory form
+                                              // below takes 10.5 us for D = 18 (12 steps x 3 warp barriers + runtime-index updates)
 #endif
             if constexpr (D <= kRegSolveMaxD)
             {
@@ -627,21 +629,76 @@ namespace mbavo
             static constexpr int E = WITH_J ? packed_len(NK) : 1;        // packed upper triangle
         };
 
-        // K: knots per segment, NK: knots in the window (NK - K + 1 segments touched), WITH_J: Hessian pass or cost only,
-        // PACKED: keyframe texels available.
-        template <int K, int NK, bool WITH_J, bool PACKED, bool BIG>
-        __global__ void __launch_bounds__(track_warps(WITH_J, NK, BIG) * 32, WITH_J ? ((!BIG && NK <= 3) ? 2 : 1) : MBAVO_MINB_C)
-            track_kernel(const __grid_constant__ TrackParams prm)
+        // Persistent sweep: what a pass needs beyond its TrackParams (see SweepCtl)
+        struct PersistArgs
+        {
+            SweepCtl *ctl;
+            unsigned int target;     // ctl->done value that makes the records of this pass valid
+            const EvalStage *stage;  // frame times / segment table for the candidate's sample records
+        };
+
+        // spin (thread 0) until ctl->done reaches target; false: aborted or timed out (the caller leaves the kernel)
+        __device__ __forceinline__ bool wait_pass(SweepCtl *ctl, unsigned int target)
+        {
+            __shared__ int go_s;
+            if (threadIdx.x == 0)
+            {
+                int go = 1;
+                const unsigned long long t0 = global_timer_ns();
+                while ((int)(ld_acquire_gpu(&ctl->done) - target) < 0)
+                {
+                    if (*reinterpret_cast<volatile int *>(&ctl->abort) != 0)
+                    {
+                        go = 0;
+                        break;
+                    }
+                    if (global_timer_ns() - t0 > 4000000000ull)
+                    {
+                        *reinterpret_cast<volatile int *>(&ctl->abort) = 1;
+                        go = 0;
+                        break;
+                    }
+                    __nanosleep(32);
+                }
+                go_s = go;
+            }
+            __syncthreads();
+            const bool go = go_s != 0;
+            __syncthreads();
+            return go;
+        }
+
+        // the candidate's sample records, computed by the threads of ONE block (the pass's last block) right after the solve:
+        // same arithmetic as pose_kernel, one thread per (frame, sample)
+        template <int K>
+        __device__ __noinline__ void pose_records_block(const EvalStage *st, const double *kt, const double *kR, int with_jacobian,
+                                                        float *samples, double *mid, int *seg_end)
+        {
+            const int total = st->N * st->F;
+            for (int g = threadIdx.x; g < total; g += blockDim.x)
+                pose_one<K>(st, kt, kR, g, with_jacobian, samples, mid, seg_end);
+        }
+
+        // One pass over one pyramid level.  K: knots per segment, NK: knots in the window (NK - K + 1 segments touched),
+        // WITH_J: Hessian pass or cost only, PACKED: keyframe texels available, WARPS: warps per block.
+        // PERSIST = false: the body of track_kernel (one launch per pass).  PERSIST = true: one pass of sweep_kernel — all
+        // blocks stay resident, the pass starts when SweepCtl::done reaches pa.target and its last block releases done =
+        // target + 1.  Returns false when the sweep was aborted.
+        template <int K, int NK, bool WITH_J, bool PACKED, int WARPS, bool PERSIST>
+        __device__ __forceinline__ bool track_pass(const TrackParams &prm, unsigned char *smem_raw, const PersistArgs pa)
         {
             using G = RowGeom<NK, WITH_J>;
-            constexpr int kWarpsPerBlock = track_warps(WITH_J, NK, BIG), kThreads = kWarpsPerBlock * 32;
+            constexpr int kWarpsPerBlock = WARPS, kThreads = kWarpsPerBlock * 32;
             constexpr int REC = sample_rec_floats(K);
             constexpr int NJ = WITH_J ? NK : 1;
             constexpr int D1 = G::D1, PITCH = G::PITCH, NT = G::NT, MT = G::MT, E = G::E;
 
             MBAVO_STAMP(0);
-            if (prm.gn.state)
-                cudaTriggerProgrammaticLaunchCompletion(); // the next pose kernel of the sweep may queue up behind this grid
+            if constexpr (!PERSIST)
+            {
+                if (prm.gn.state)
+                    cudaTriggerProgrammaticLaunchCompletion(); // the next pose kernel of the sweep may queue up behind this grid
+            }
             const LevelDev &lv = prm.lv;
             const int f = blockIdx.y;
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -653,7 +710,6 @@ namespace mbavo
             const int slot = pf ? lane / PH : lane & (Q - 1), phase = pf ? lane & (PH - 1) : lane / Q;
             const int bfly_lo = pf ? 1 : Q, bfly_hi = pf ? PH : 32;
 
-            extern __shared__ __align__(16) unsigned char smem_raw[];
             float *samples_s = reinterpret_cast<float *>(smem_raw);                  // N * REC
             int *seg_end_s = reinterpret_cast<int *>(samples_s + N * REC);          // kMaxSegments (+1 pad)
             double *mid_s = reinterpret_cast<double *>(seg_end_s + 8);              // kMidDoubles
@@ -679,7 +735,13 @@ namespace mbavo
             // everything above is independent of the pose kernel; what follows reads its output (programmatic dependent
             // launch: this grid may have started before the pose kernel finished)
             MBAVO_STAMP(1);
-            cudaGridDependencySynchronize();
+            if constexpr (PERSIST)
+            {
+                if (!wait_pass(pa.ctl, pa.target))
+                    return false;
+            }
+            else
+                cudaGridDependencySynchronize();
             MBAVO_STAMP(2);
             int buf = prm.buf_select == kBufB ? 1 : 0;
             if (prm.buf_select == kBufCur || prm.buf_select == kBufCand)
@@ -690,15 +752,26 @@ namespace mbavo
             const float *samples_g = prm.samples + (size_t)buf * prm.samples_stride;
             const int *seg_end_g = prm.seg_end + (size_t)buf * prm.seg_end_stride;
             const double *mid_g = prm.mid + (size_t)buf * prm.mid_stride;
+            // (__ldcg: inside a persistent sweep the records were written by another SM during this very kernel)
             for (int e = threadIdx.x; e < N * REC; e += blockDim.x)
-                samples_s[e] = samples_g[(size_t)f * N * REC + e];
+                samples_s[e] = __ldcg(samples_g + (size_t)f * N * REC + e);
             if (threadIdx.x < kMaxSegments)
-                seg_end_s[threadIdx.x] = seg_end_g[f * kMaxSegments + threadIdx.x];
+                seg_end_s[threadIdx.x] = __ldcg(seg_end_g + f * kMaxSegments + threadIdx.x);
             if (threadIdx.x < kMidDoubles)
-                mid_s[threadIdx.x] = mid_g[f * kMidDoubles + threadIdx.x];
+                mid_s[threadIdx.x] = __ldcg(mid_g + f * kMidDoubles + threadIdx.x);
             __syncthreads();
 
             MBAVO_STAMP(3);
+            // Persistent sweep, cost pass: the last block of the grid takes no batches; it completes the candidate's sample
+            // records with their Jacobian part (the Hessian pass's last block wrote the pose part only, to release this pass
+            // sooner) — off the critical path, and finished before this block takes its ticket, i.e. before the next pass starts.
+            const bool service_pass = PERSIST && !WITH_J && gridDim.x > 1 && prm.gn.state != nullptr;
+            const bool service_block = service_pass && blockIdx.x == gridDim.x - 1;
+            if (service_block && !prm.gn.last && prm.gn.chain)
+            {
+                pose_records_block<K>(pa.stage, prm.gn.state->cand_t, prm.gn.state->cand_R, kPoseJacobianOnly,
+                                      const_cast<float *>(samples_g), nullptr, nullptr);
+            }
             const double *mid = mid_s;
             const float2 fxy = f2((float)lv.fx, (float)lv.fy);
             const float inv_N = 1.0f / (float)N;
@@ -718,7 +791,12 @@ namespace mbavo
             double cost_acc = 0.0;
 
             const int items = TP * S;
-            for (int wb = blockIdx.x * kWarpsPerBlock + warp; wb < prm.batches_per_frame; wb += gridDim.x * kWarpsPerBlock)
+            // batch -> warp: one launch per pass sizes its grid to the batches, block-major; the resident grid of a persistent
+            // sweep is the whole GPU whatever the level, so batches go block-fastest (a coarse level still reaches every SM)
+            const int nblk = (int)gridDim.x - (service_pass ? 1 : 0); // blocks that take batches
+            const int wb_first = service_block ? prm.batches_per_frame
+                                               : (PERSIST ? warp * nblk + (int)blockIdx.x : (int)blockIdx.x * kWarpsPerBlock + warp);
+            for (int wb = wb_first; wb < prm.batches_per_frame; wb += nblk * kWarpsPerBlock)
             {
                 const int p0 = wb * TP;
                 for (int base = 0; base < items; base += 32)
@@ -922,7 +1000,7 @@ namespace mbavo
                 ticket_s = atomicAdd(prm.counter, 1u);
             __syncthreads();
             if (ticket_s != (unsigned int)(num_blocks - 1))
-                return;
+                return true;
             MBAVO_STAMP(8);
             // last block: sum the partials of all blocks in a fixed order.  GRP adjacent lanes share one element: lane `part`
             // sums the blocks b = part, part + GRP, ... (32 loads in flight), the GRP partial sums are combined by a fixed
@@ -1013,46 +1091,145 @@ namespace mbavo
                     double *A = fin_s + ((E + 1) & ~1), *w = A + 72 * NK * NK;
                     if (warp == 0)
                         gn_solve_step<NK>(fin_s, gp, A, w, prm.phase_times ? prm.phase_times + 16 * (prm.trace_row & 63) : nullptr);
+                    if constexpr (PERSIST)
+                    {
+                        // the candidate's sample records (what the stand-alone pose kernel computes between the two passes of a
+                        // level when every pass is its own launch), with Jacobians: the next level may stand on them
+                        __syncthreads();
+                        // into the record buffer the sweep does NOT stand on (a sweep that never commits keeps cur_buf = 0)
+                        const int cb = 1 - *reinterpret_cast<volatile int *>(&st->cur_buf);
+                        // pose part only: all the cost pass needs.  The Jacobian part, which only a finer level standing on the
+                        // committed candidate reads, is computed by the service block WHILE the cost pass runs (below).
+                        pose_records_block<K>(pa.stage, st->cand_t, st->cand_R, gridDim.x > 1 ? 0 : 1,
+                                              const_cast<float *>(prm.samples) + (size_t)cb * prm.samples_stride,
+                                              const_cast<double *>(prm.mid) + (size_t)cb * prm.mid_stride,
+                                              const_cast<int *>(prm.seg_end) + (size_t)cb * prm.seg_end_stride);
+                        MBAVO_STAMP(15);
+                    }
                 }
-                else if (threadIdx.x == 0)
+                else if (threadIdx.x < 32)
                 {
-                    const double cc = fin_s[0];
-                    st->cand_cost = cc;
+                    // record the candidate's cost, commit the candidate when it lowered the cost (the finer level then starts from
+                    // it), publish the level's scalars (and, after the last level, the knots) to the host.  One warp: the knots are
+                    // copied / published a lane per element.  Inside a persistent sweep the pass is released to the other blocks
+                    // BEFORE anything is stored to host memory (a fence behind PCIe stores costs microseconds).
+                    const int lane32 = threadIdx.x;
+                    const double cc = fin_s[0], cost0 = st->cost, model0 = st->model;
+                    const int status0 = st->status;
+                    const bool commit = gp.chain && status0 == 0 && cc < cost0;
+                    const int nk7 = 7 * gp.n_knots; // cur_t (3n) and cur_R (4n) are adjacent in GnState
+                    double *cur = st->cur_t;
+                    const double *cand = st->cand_t;
+                    static_assert(offsetof(GnState, cur_R) == offsetof(GnState, cur_t) + sizeof(double) * 3 * 16 &&
+                                      offsetof(GnState, cand_R) == offsetof(GnState, cand_t) + sizeof(double) * 3 * 16,
+                                  "GnState: rotations follow translations");
+                    double keep[4]; // the knots the sweep stands on after this level, 4 elements per lane (7 * 16 <= 128)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                    {
+                        const int e = lane32 + 32 * u;
+                        const int idx = e < 3 * gp.n_knots ? e : 48 + (e - 3 * gp.n_knots); // element of the padded [t(48) | R(64)] layout
+                        keep[u] = 0.0;
+                        if (e < nk7)
+                        {
+                            keep[u] = commit ? cand[idx] : cur[idx];
+                            if (commit)
+                                cur[idx] = keep[u];
+                        }
+                    }
+                    if (lane32 == 0)
+                    {
+                        st->cand_cost = cc;
+                        if (commit)
+                            st->cur_buf ^= 1; // the candidate's sample records are now those of the knots the sweep stands on
+                    }
+                    if constexpr (PERSIST)
+                    {
+                        __threadfence();
+                        __syncwarp();
+                        if (lane32 == 0)
+                        {
+                            *prm.counter = 0u;
+                            st_release_gpu(&pa.ctl->done, pa.target + 1u);
+                        }
+                    }
                     if (prm.host_out)
                     {
                         double2 *o = prm.host_out + 4 * gp.slot;
-                        publish_host(o + 0, st->cost, prm.seq), publish_host(o + 1, cc, prm.seq);
-                        publish_host(o + 2, (double)st->status, prm.seq), publish_host(o + 3, st->model, prm.seq);
-                    }
-                    if (gp.chain && st->status == 0 && cc < st->cost) // the finer level starts from the candidate
-                    {
-                        for (int e = 0; e < 3 * gp.n_knots; ++e)
-                            st->cur_t[e] = st->cand_t[e];
-                        for (int e = 0; e < 4 * gp.n_knots; ++e)
-                            st->cur_R[e] = st->cand_R[e];
-                        st->cur_buf ^= 1; // the candidate's sample records are now those of the knots the sweep stands on
-                    }
-                    if (gp.last && prm.host_out)
-                    {
-                        double2 *o = prm.host_out + 4 * MBAVO_MAX_LEVELS_DEV;
-                        for (int e = 0; e < 3 * gp.n_knots; ++e)
-                            publish_host(o + e, st->cur_t[e], prm.seq);
-                        for (int e = 0; e < 4 * gp.n_knots; ++e)
-                            publish_host(o + 3 * gp.n_knots + e, st->cur_R[e], prm.seq);
+                        if (lane32 == 0)
+                        {
+                            publish_host(o + 0, cost0, prm.seq), publish_host(o + 1, cc, prm.seq);
+                            publish_host(o + 2, (double)status0, prm.seq), publish_host(o + 3, model0, prm.seq);
+                        }
+                        if (gp.last)
+                        {
+                            double2 *ok = prm.host_out + 4 * MBAVO_MAX_LEVELS_DEV;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (lane32 + 32 * u < nk7)
+                                    publish_host(ok + lane32 + 32 * u, keep[u], prm.seq);
+                        }
                     }
                 }
                 __syncthreads();
             }
-            for (int e = threadIdx.x; e < E; e += blockDim.x)
+            if constexpr (!PERSIST) // (a sweep publishes scalars and knots, never the packed vector)
             {
-                const double s = fin_s[e];
-                prm.packed_out[e] = s;
-                if (prm.host_out && !gp.state)
-                    publish_host(prm.host_out + e, s, prm.seq);
+                for (int e = threadIdx.x; e < E; e += blockDim.x)
+                {
+                    const double s = fin_s[e];
+                    prm.packed_out[e] = s;
+                    if (prm.host_out && !gp.state)
+                        publish_host(prm.host_out + e, s, prm.seq);
+                }
             }
             MBAVO_STAMP(10);
-            if (threadIdx.x == 0)
-                *prm.counter = 0u; // re-arm for the next launch
+            if constexpr (PERSIST && WITH_J)
+            {
+                // everything this block wrote (records, sweep state, counter) becomes visible to the blocks that acquire `done`
+                // (the cost pass released the sweep above, before its host stores)
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0)
+                {
+                    *prm.counter = 0u;
+                    st_release_gpu(&pa.ctl->done, pa.target + 1u);
+                }
+            }
+            else if constexpr (!PERSIST)
+            {
+                if (threadIdx.x == 0)
+                    *prm.counter = 0u; // re-arm for the next launch
+            }
+            return true;
+        }
+
+        template <int K, int NK, bool WITH_J, bool PACKED, bool BIG>
+        __global__ void __launch_bounds__(track_warps(WITH_J, NK, BIG) * 32, WITH_J ? ((!BIG && NK <= 3) ? 2 : 1) : MBAVO_MINB_C)
+            track_kernel(const __grid_constant__ TrackParams prm)
+        {
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            track_pass<K, NK, WITH_J, PACKED, track_warps(WITH_J, NK, BIG), false>(prm, smem_raw, PersistArgs{});
+        }
+
+        // The whole coarse-to-fine sweep in one launch: one block per SM, all passes inside (see SweepCtl).  The sample records
+        // of the knots the sweep starts from come from the pose kernel launched right before it.
+        template <int K, int NK, bool PACKED>
+        __global__ void __launch_bounds__(track_warps(true, NK, true) * 32, 1)
+            sweep_kernel(const __grid_constant__ SweepParams sp, const __grid_constant__ EvalStage stage)
+        {
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            constexpr int WARPS = track_warps(true, NK, true);
+            cudaGridDependencySynchronize(); // the pose kernel's records (and the sweep state it initialised)
+            for (int li = 0; li < sp.n_levels; ++li)
+            {
+                const PersistArgs ph{sp.ctl, sp.base + 2u * (unsigned int)li, &stage};
+                if (!track_pass<K, NK, true, PACKED, WARPS, true>(sp.pass[2 * li], smem_raw, ph))
+                    return;
+                const PersistArgs pc{sp.ctl, sp.base + 2u * (unsigned int)li + 1u, &stage};
+                if (!track_pass<K, NK, false, PACKED, WARPS, true>(sp.pass[2 * li + 1], smem_raw, pc))
+                    return;
+            }
         }
 
         template <int K, int NK, bool WITH_J, bool PACKED, bool BIG>
@@ -1078,6 +1255,52 @@ namespace mbavo
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr, cfg.numAttrs = dependent ? 1 : 0;
             return cudaLaunchKernelEx(&cfg, track_kernel<K, NK, WITH_J, PACKED, BIG>, prm);
+        }
+
+        // sweep_kernel: one block per SM, cooperative (all blocks co-resident: they wait for each other between the passes),
+        // programmatically chained behind the pose kernel when the driver accepts both attributes together
+        template <int K, int NK, bool PACKED>
+        cudaError_t launch_sweep_one(const SweepParams &sp, const EvalStage &stage, int num_sms, size_t smem, cudaStream_t stream, bool dependent,
+                                     int *query_occupancy)
+        {
+            static unsigned long long configured = 0;
+            static int pdl_ok = 1; // cooperative + programmatic serialisation accepted together
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!(configured >> dev & 1ull))
+            {
+                cudaError_t e = cudaFuncSetAttribute(sweep_kernel<K, NK, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                if (e != cudaSuccess)
+                    return e;
+                configured |= 1ull << dev;
+            }
+            constexpr int threads = track_warps(true, NK, true) * 32;
+            if (query_occupancy)
+            {
+                int n = 0;
+                cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sweep_kernel<K, NK, PACKED>, threads, smem);
+                *query_occupancy = n;
+                return e;
+            }
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(num_sms, 1, 1), cfg.blockDim = dim3(threads, 1, 1), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeCooperative;
+            attr[0].val.cooperative = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            if (dependent && pdl_ok)
+            {
+                cfg.numAttrs = 2;
+                cudaError_t e = cudaLaunchKernelEx(&cfg, sweep_kernel<K, NK, PACKED>, sp, stage);
+                if (e == cudaSuccess)
+                    return e;
+                cudaGetLastError();
+                pdl_ok = 0;
+            }
+            cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, sweep_kernel<K, NK, PACKED>, sp, stage);
         }
 
         // Occupancy-derived grid width for one instantiation

@@ -567,27 +567,38 @@ def test_shard_peer_timeout_is_an_error(pkg, api, synth):
 
 @pytest.mark.parametrize("name,chain", [("tiny", False), ("C2", True), ("C2", False), ("C5cubic", True)])
 def test_device_resident_sweep_matches_host_path(pkg, api, synth, monkeypatch, name, chain):
-    """mbavo_gn_sweep: the device-resident form (solve, candidate and commit in the kernels' last blocks, one host wait)
-    against the evaluation-by-evaluation form (MBAVO_NO_DEVICE_SWEEP=1)."""
+    """mbavo_gn_sweep in its three forms: ONE persistent launch (sweep_kernel: every pass of every level inside one resident
+    grid, the candidate's sample records computed by the pass's last block), the per-pass device-resident form
+    (MBAVO_NO_PERSISTENT=1: solve, candidate and commit in the kernels' last blocks, one host wait) and the
+    evaluation-by-evaluation form (MBAVO_NO_DEVICE_SWEEP=1)."""
     prob = synth.make_config(name)
     top = len(prob.levels) - 1
 
     def sweep():
         with pkg.Context(api.limits_for(prob)) as ctx:
             api.upload_problem(ctx, prob)
+            l0 = ctx.kernel_launches()
             out = [ctx.gn_sweep(top, 0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, 1e4, chain=chain)
-                   for _ in range(2)]
-            assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])  # deterministic
-            return out[0] + (ctx.device_sweeps(), ctx.lib.mbavo_last_error().decode())
+                   for _ in range(3)]
+            for o in out[1:]:
+                assert np.array_equal(out[0][0], o[0]) and np.array_equal(out[0][1], o[1])  # deterministic
+            return out[0] + (ctx.device_sweeps(), ctx.persistent_sweeps(), ctx.kernel_launches() - l0, ctx.lib.mbavo_last_error().decode())
 
+    pers = sweep()
+    monkeypatch.setenv("MBAVO_NO_PERSISTENT", "1")
     dev = sweep()
     monkeypatch.setenv("MBAVO_NO_DEVICE_SWEEP", "1")
     host = sweep()
-    assert np.abs(dev[0] - host[0]).max() <= 1e-9 * np.abs(host[0]).max(), (dev[0], host[0])
-    assert np.abs(dev[1] - host[1]).max() <= 1e-9 and np.abs(dev[2] - host[2]).max() <= 1e-9
+    for got in (pers, dev):
+        assert np.abs(got[0] - host[0]).max() <= 1e-9 * np.abs(host[0]).max(), (got[0], host[0])
+        assert np.abs(got[1] - host[1]).max() <= 1e-9 and np.abs(got[2] - host[2]).max() <= 1e-9
     if chain:
         assert np.abs(dev[1] - prob.knots_t).max() > 0  # a candidate was committed
-    assert dev[3] == 2 and host[3] == 0, (dev[3], dev[4])  # the device-resident path really ran
+    if name == "C5cubic":  # a 7-knot window has no persistent instantiation: that sweep runs pass by pass
+        assert pers[3] == 3 and pers[4] == 0, pers[3:]
+    else:
+        assert pers[3] == 3 and pers[4] == 3 and pers[5] == 6, pers[3:]  # two launches per sweep: pose kernel + sweep kernel
+    assert dev[3] == 3 and dev[4] == 0 and host[3] == 0, (dev[3:], host[3:])  # the device-resident paths really ran
 
 
 @pytest.mark.parametrize("seed,mixed_n", [(2, False), (3, False), (3, True)])
@@ -595,7 +606,8 @@ def test_device_sweep_rejected_levels_and_record_reuse(pkg, api, synth, monkeypa
     """A chained sweep in which some level's candidate is REJECTED (the sweep keeps standing on its knots) and others are
     committed: the levels after the first find the sample records of their knots in one of the two record buffers instead of
     running a pose kernel — whichever buffer that is after the commits so far.  With a different number of exposure samples on
-    one level the records cannot be shared and every level computes its own.  Both against the evaluation-by-evaluation form."""
+    one level the records cannot be shared: every level computes its own, one launch per pass.  The persistent launch, the
+    per-pass form and the evaluation-by-evaluation form against each other."""
     prob = synth.make_problem("rej", W=160, H=120, levels=3, P0=600, N=8, n_knots=2, k=2, seed=100 + seed, margin=16)
     kt = prob.knots_t + np.random.default_rng(seed).normal(size=prob.knots_t.shape) * 2e-2
     if mixed_n:
@@ -606,18 +618,22 @@ def test_device_sweep_rejected_levels_and_record_reuse(pkg, api, synth, monkeypa
             api.upload_problem(ctx, prob)
             l0 = ctx.kernel_launches()
             out = ctx.gn_sweep(2, 0, prob.k, prob.t0, prob.dt, kt, prob.knots_R, prob.huber_a, 1e4, chain=True)
-            return out + (ctx.device_sweeps(), ctx.kernel_launches() - l0)
+            return out + (ctx.device_sweeps(), ctx.kernel_launches() - l0, ctx.persistent_sweeps())
 
+    pers = sweep()
+    monkeypatch.setenv("MBAVO_NO_PERSISTENT", "1")
     dev = sweep()
     monkeypatch.setenv("MBAVO_NO_DEVICE_SWEEP", "1")
     host = sweep()
-    assert dev[3] == 1 and host[3] == 0
+    assert dev[3] == 1 and host[3] == 0 and pers[3] == 1 and pers[5] == (0 if mixed_n else 1)
     assert dev[4] == (12 if mixed_n else 10) and host[4] == 12  # 6 tracking kernels + 6 pose kernels, or 4 with shared records
-    assert np.abs(dev[0] - host[0]).max() <= 1e-9 * np.abs(host[0]).max(), (dev[0], host[0])
-    assert np.abs(dev[1] - host[1]).max() <= 1e-9 and np.abs(dev[2] - host[2]).max() <= 1e-9
-    decisions = "".join("A" if cand < cost else "R" for cost, cand in dev[0])
-    if not mixed_n:
-        assert decisions == {2: "AAR", 3: "RAA"}[seed], decisions  # (predicted with the oracle on the CPU)
+    assert pers[4] == (12 if mixed_n else 2)
+    for got in (pers, dev):
+        assert np.abs(got[0] - host[0]).max() <= 1e-9 * np.abs(host[0]).max(), (got[0], host[0])
+        assert np.abs(got[1] - host[1]).max() <= 1e-9 and np.abs(got[2] - host[2]).max() <= 1e-9
+        decisions = "".join("A" if cand < cost else "R" for cost, cand in got[0])
+        if not mixed_n:
+            assert decisions == {2: "AAR", 3: "RAA"}[seed], decisions  # (predicted with the oracle on the CPU)
 
 
 def test_device_sweep_with_unobserved_knots(pkg, api, O, orc, synth, monkeypatch):
