@@ -404,6 +404,33 @@ int mbavo_is_keyframe(double avg_flow, double avg_kernel_len, double max_flow_ma
 int mbavo_synthesize_blurred(int device, int mem, const unsigned char *ref_I, int H, int W, double plane_depth, double fx,
                              double fy, double cx, double cy, const double *poses_tq, int num_poses, unsigned char *out);
 
+/* ---- per-stage intermediates of one Hessian-pass evaluation (SURVEY.md §8d stage gates) ---------------------------------
+ * What the reference's module test prints stage by stage (test/test_blur_aware_tracker_modules.cpp:183-342 virtual poses and
+ * their Jacobians, :344-500 local patches, :502-895 pixel residuals and Jacobians), produced by the PRODUCT kernels with their
+ * debug stores switched on.  All pointers are host memory, each may be NULL.  F frames, N exposure samples, P points, S patch
+ * pixels, k = spline_deg_k, NK = knot_window:
+ *   poses_tq        [F N 7]     pose of every exposure sample, t then q (x, y, z, w), fp64 — before the rounding into the fp32
+ *                               sample record (compute_virtual_camera_poses.cu:26-109)
+ *   blend_weights   [F N k]     translation blend weight of the k knots of the sample's segment (J_t = w_j I, SplineFunctor.h:30-40, 74-91)
+ *   theta           [F N k 9]   Theta_j (3 x 3 row-major) = d theta / d w_j, theta the right perturbation of the pose rotation; the
+ *                               reference's 4 x 3 block is dq / dw_j = L(q) [I / 2; 0] Theta_j (SplineFunctor.h:178-213, 274-361)
+ *   segment_start_knot [F N]    first control knot of the sample's segment
+ *   patch_centres   [F P 2]     compute_local_patches_xy.cu:26-49, fp64
+ *   residuals       [F P S]     raw residual of every pixel, (1/N) sum_i I_i - I_cur (…cost.cu:115-121); 0 for invalid pixels
+ *   jacobians       [F P S 6NK] raw Jacobian row of every pixel w.r.t. the knots [kmin, kmin + NK), ordered [t-block | w-block]
+ *                               (…cost.cu:123-151 scattered per sample segment)
+ * Available for k = 2 with windows of 2 or 3 knots and k = 4 with 4 (MBAVO_ECAPACITY otherwise); unsharded contexts. */
+typedef struct mbavo_debug_out
+{
+    double *poses_tq, *blend_weights, *theta;
+    int *segment_start_knot;
+    double *patch_centres;
+    float *residuals, *jacobians;
+    int kmin, knot_window, spline_deg_k; /* out */
+    double cost;                         /* out: total cost of the evaluation */
+} mbavo_debug_out;
+int mbavo_debug_dump(mbavo_ctx *ctx, int level, const mbavo_spline *spline, double huber_a, mbavo_debug_out *out);
+
 /* ---- introspection for benchmarks ---------------------------------------------------------------------------- */
 
 /* Number of kernels this library has launched on behalf of ctx since creation */
@@ -417,6 +444,11 @@ long long mbavo_device_sweeps(const mbavo_ctx *ctx);
  * (passes separated by a ticket + flag barrier).  Taken when all levels share the exposure-sample count and the patch size,
  * track one frame, have keyframe texels, and the knot window is one of {k=2: 2..5, k=4: 4}; MBAVO_NO_PERSISTENT=1 disables it. */
 long long mbavo_persistent_sweeps(const mbavo_ctx *ctx);
+/* Durations (microseconds, device globaltimer) of the passes of the last persistent sweep, coarse level first: [2 li] the
+ * Hessian pass of level li — from the release of the previous pass to its own release, i.e. record load, batches, reduction,
+ * solve, candidate and the candidate's pose records included — and [2 li + 1] its cost pass.  The stamps are two stores per
+ * pass by one thread; they are always taken. */
+int mbavo_sweep_pass_times(mbavo_ctx *ctx, double *us_out, int capacity, int *num_passes);
 
 /* 1 if the kernels of `level` read the keyframe through the packed fp16 texels built by mbavo_set_level (every
  * gradient value exactly representable in fp16 — always the case for Gradient.h's central differences of an 8-bit

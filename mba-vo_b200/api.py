@@ -19,11 +19,11 @@ SOLVER_SVD_JACOBI, SOLVER_LDLT = 0, 1
 EXPORTED_SYMBOLS = [
     "mbavo_last_error", "mbavo_version", "mbavo_create", "mbavo_destroy", "mbavo_set_stream", "mbavo_set_frame_times",
     "mbavo_set_level", "mbavo_set_keyframe_pyramid", "mbavo_set_live_pyramid", "mbavo_set_level_points", "mbavo_set_points_pyramid",
-    "mbavo_set_frame",
+    "mbavo_set_frame", "mbavo_debug_dump",
     "mbavo_set_live_images", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
-    "mbavo_device_sweeps", "mbavo_persistent_sweeps", "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
+    "mbavo_device_sweeps", "mbavo_persistent_sweeps", "mbavo_sweep_pass_times", "mbavo_enable_kernel_timing", "mbavo_last_kernel_ms", "mbavo_level_uses_texels", "mbavo_shard_export",
     "mbavo_shard_connect", "mbavo_shard_disconnect", "mbavo_shard_set_global_points", "mbavo_synthesize_blurred",
     "mbavo_keyframe_stats", "mbavo_select_points", "mbavo_get_points", "mbavo_se3_exp", "mbavo_se3_log",
     "mbavo_spline_pose", "mbavo_spline_transform_by_right", "mbavo_spline_transform_to", "mbavo_predict_spline", "mbavo_frame_velocity",
@@ -67,6 +67,12 @@ class _LevelPoints(C.Structure):
 class _Spline(C.Structure):
     _fields_ = [("spline_deg_k", C.c_int), ("start_time", C.c_double), ("sample_dt", C.c_double),
                 ("num_ctrl_knots", C.c_int), ("knots_t", C.POINTER(C.c_double)), ("knots_R", C.POINTER(C.c_double))]
+
+
+class _DebugOut(C.Structure):
+    _fields_ = [("poses_tq", C.c_void_p), ("blend_weights", C.c_void_p), ("theta", C.c_void_p), ("segment_start_knot", C.c_void_p),
+                ("patch_centres", C.c_void_p), ("residuals", C.c_void_p), ("jacobians", C.c_void_p), ("kmin", C.c_int),
+                ("knot_window", C.c_int), ("spline_deg_k", C.c_int), ("cost", C.c_double)]
 
 
 class _LmOptions(C.Structure):
@@ -293,6 +299,21 @@ class Context:
                                                   C.c_void_p(packed_dev_ptr), C.byref(kmin), C.byref(nk)))
         return kmin.value, nk.value
 
+    def debug_dump(self, level: int, k: int, t0: float, dt: float, knots_t, knots_R, huber_a: float, F: int, N: int, P: int, S: int):
+        """mbavo_debug_dump -> dict of the per-stage intermediates of one Hessian-pass evaluation (see include/mbavo.h)."""
+        sp, kt, kR, n = self._spline(k, t0, dt, knots_t, knots_R)
+        poses, wts, theta = np.zeros((F, N, 7)), np.zeros((F, N, k)), np.zeros((F, N, k, 3, 3))
+        seg = np.zeros((F, N), dtype=np.int32)
+        centres = np.zeros((F, P, 2))
+        r = np.zeros((F, P, S), dtype=np.float32)
+        J = np.zeros(F * P * S * 6 * 8, dtype=np.float32)  # worst-case window
+        out = _DebugOut(poses.ctypes.data, wts.ctypes.data, theta.ctypes.data, seg.ctypes.data, centres.ctypes.data, r.ctypes.data,
+                        J.ctypes.data, 0, 0, 0, 0.0)
+        self._check(self.lib.mbavo_debug_dump(self._h, C.c_int(level), C.byref(sp), C.c_double(huber_a), C.byref(out)))
+        d = 6 * out.knot_window
+        return dict(poses_tq=poses, blend_weights=wts, theta=theta, segment_start_knot=seg, patch_centres=centres, residuals=r,
+                    jacobians=J[: F * P * S * d].reshape(F, P, S, d).copy(), kmin=out.kmin, knot_window=out.knot_window, cost=out.cost)
+
     def packed_len(self, knot_window: int) -> int:
         return int(self.lib.mbavo_packed_len(C.c_int(knot_window)))
 
@@ -437,6 +458,13 @@ class Context:
 
     def persistent_sweeps(self) -> int:
         return int(self.lib.mbavo_persistent_sweeps(self._h))
+
+    def sweep_pass_times(self) -> np.ndarray:
+        """mbavo_sweep_pass_times -> microseconds per pass of the last persistent sweep, shape (levels, 2): [Hessian pass, cost pass]."""
+        out = np.zeros(2 * MAX_LEVELS)
+        n = C.c_int(0)
+        self._check(self.lib.mbavo_sweep_pass_times(self._h, _dp(out), C.c_int(out.shape[0]), C.byref(n)))
+        return out[: n.value].reshape(-1, 2).copy()
 
     def level_uses_texels(self, level: int) -> int:
         return int(self.lib.mbavo_level_uses_texels(self._h, C.c_int(level)))

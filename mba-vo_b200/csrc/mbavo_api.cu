@@ -19,7 +19,8 @@ namespace mbavo
 {
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
                                    double *mid, int *seg_end, cudaStream_t stream, GnState *gn, int knots_from, bool dependent,
-                                   int buf_select, int samples_stride, int mid_stride, int seg_end_stride);
+                                   int buf_select, int samples_stride, int mid_stride, int seg_end_stride, double *dbg = nullptr);
+    cudaError_t launch_track_debug_kernel(int K, int NK, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream);
     cudaError_t launch_track_kernel(int K, int NK, bool with_j, bool big, const TrackParams &prm, dim3 grid, size_t smem,
                                     cudaStream_t stream, int *query_occupancy, bool dependent);
     size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool big, int N, int S, int TP);
@@ -95,8 +96,16 @@ struct mbavo_ctx
     int device = 0;
     mbavo_limits lim{};
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaStream_t copy_stream = nullptr;   // second stream of mbavo_set_frame (point uploads under the pyramid build)
-    cudaEvent_t copy_done = nullptr;
+    cudaStream_t copy_stream = nullptr;   // second stream of mbavo_set_frame (point uploads under the pyramid build / the sweep)
+    cudaEvent_t copy_done = nullptr, images_done = nullptr;
+    // MBAVO_UPLOAD_ASYNC: the context's stream has NOT yet been made to wait for the point copies of the last mbavo_set_frame.
+    // A persistent sweep does not need that wait — every Hessian pass spins on its level's ready flag, which the copy stream
+    // sets right behind the level's points — everything else joins the streams first (join_uploads).
+    bool join_pending = false;
+    int upload_levels = 0;
+    unsigned int upload_epoch = 0;
+    unsigned int *ready_dev = nullptr;    // [MBAVO_MAX_LEVELS] epoch of the points resident in each level
+    unsigned int *ready_src = nullptr;    // pinned: the value the flag copies carry
     int num_sms = 148;
 
     double cap[kMaxFrames] = {}, exp_time[kMaxFrames] = {};
@@ -118,6 +127,8 @@ struct mbavo_ctx
     long long persistent_sweeps = 0;               // ... of which inside ONE launch (sweep_kernel)
     bool use_persistent = true;                    // MBAVO_NO_PERSISTENT=1: one launch per pass
     SweepCtl *sweep_ctl = nullptr;                 // pass barrier of the persistent sweep kernel
+    unsigned long long *sweep_pass_times = nullptr; // globaltimer stamps of the last persistent sweep (SweepParams::pass_times)
+    int sweep_last_levels = 0;
     unsigned int sweep_base = 0;                   // value of sweep_ctl->done after the sweeps issued so far
     bool shard_shares_device = false;              // a peer rank lives on this GPU: persistent grids could not be co-resident
     bool use_device_sweep = true;                  // MBAVO_NO_DEVICE_SWEEP=1: every evaluation returns to the host
@@ -475,6 +486,30 @@ namespace
         int buf_select = kBufA; // record buffer the pose kernel writes and the tracking kernel reads
     };
 
+    // make the context's stream wait for the point copies of an asynchronous mbavo_set_frame (see mbavo_ctx::join_pending)
+    int join_uploads(mbavo_ctx *ctx)
+    {
+        if (ctx->join_pending)
+        {
+            CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+            ctx->join_pending = false;
+        }
+        return MBAVO_OK;
+    }
+
+    // before buffers of the context are replaced: nothing may be in flight on either stream
+    int quiesce(mbavo_ctx *ctx)
+    {
+        if (ctx->join_pending)
+        {
+            CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+            ctx->join_pending = false;
+        }
+        if (cudaStreamQuery(ctx->stream) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return MBAVO_OK;
+    }
+
     // per-block partials of `blocks` blocks with E elements each
     int ensure_block_partials(mbavo_ctx *ctx, size_t need)
     {
@@ -533,7 +568,10 @@ namespace
     {
         LevelStore &L = ctx->levels[level];
         cudaStream_t s = ctx->stream;
-        int rc = ensure_block_partials(ctx, (size_t)pl.grid.x * pl.grid.y * pl.E);
+        int rc = join_uploads(ctx);
+        if (rc != MBAVO_OK)
+            return rc;
+        rc = ensure_block_partials(ctx, (size_t)pl.grid.x * pl.grid.y * pl.E);
         if (rc != MBAVO_OK)
             return rc;
         L.last_eval_frames = pl.F;
@@ -627,13 +665,16 @@ namespace
         {
             CUDA_TRY(cudaMalloc(&ctx->sweep_ctl, sizeof(SweepCtl)));
             CUDA_TRY(cudaMemset(ctx->sweep_ctl, 0, sizeof(SweepCtl)));
+            CUDA_TRY(cudaMalloc(&ctx->sweep_pass_times, sizeof(unsigned long long) * (1 + 2 * kMaxSweepLevels)));
+            CUDA_TRY(cudaMemset(ctx->sweep_pass_times, 0, sizeof(unsigned long long) * (1 + 2 * kMaxSweepLevels)));
             ctx->sweep_base = 0;
         }
         int rc = ensure_block_partials(ctx, partials);
         if (rc != MBAVO_OK)
             return rc;
         static thread_local SweepParams prm; // ~10 KB: kept off the stack of the caller's thread
-        prm.n_levels = nlev, prm.ctl = ctx->sweep_ctl, prm.base = ctx->sweep_base;
+        prm.n_levels = nlev, prm.ctl = ctx->sweep_ctl, prm.base = ctx->sweep_base, prm.pass_times = ctx->sweep_pass_times;
+        ctx->sweep_last_levels = nlev;
         for (int li = 0; li < nlev; ++li)
         {
             const int level = level_coarse - li;
@@ -657,6 +698,12 @@ namespace
                 // record buffers: the knots the sweep stands on / the candidate; the roles swap on the device at every commit
                 sw.buf_select = pass == 0 ? (li == 0 ? kBufA : kBufCur) : kBufCand;
                 fill_track_params(ctx, level, pl, ctx->packed_dev, true, 1.0 / (double)nres, huber_a, &sw, prm.pass[2 * li + pass]);
+                if (pass == 0 && ctx->join_pending && level < ctx->upload_levels)
+                {
+                    // the level's points may still be on their way: the pass waits for the flag the copy stream sets behind them
+                    prm.pass[2 * li].ready_flag = ctx->ready_dev + level;
+                    prm.pass[2 * li].ready_epoch = ctx->upload_epoch;
+                }
                 if (pass == 1)
                     seq_of_level[li] = ctx->seq;
             }
@@ -665,10 +712,17 @@ namespace
         ctx->launches += 2;
         CUDA_TRY(launch_pose_kernel(plans[0].K, ctx->stage, plans[0].N, 1, ctx->samples, ctx->mid, ctx->seg_end, s, ctx->gn_state, 0, false, kBufA,
                                     ctx->samples_stride, kMidDoubles * kMaxFrames, kMaxSegments * kMaxFrames));
-        e = launch_sweep_kernel(plans[0].K, plans[0].NK, prm, ctx->stage, ctx->num_sms, smem, s, ctx->use_pdl, nullptr);
+        if (ctx->timing)
+            CUDA_TRY(cudaEventRecord(ctx->ev0, s));
+        e = launch_sweep_kernel(plans[0].K, plans[0].NK, prm, ctx->stage, ctx->num_sms, smem, s, ctx->use_pdl && !ctx->timing, nullptr);
         if (e != cudaSuccess)
             return fail(MBAVO_ECUDA, "sweep kernel launch: %s", cudaGetErrorString(e));
+        if (ctx->timing)
+            CUDA_TRY(cudaEventRecord(ctx->ev1, s));
         ctx->sweep_base += 2u * (unsigned int)nlev;
+        // levels of the upload this sweep does not visit are not covered by its flag waits
+        if (ctx->join_pending && !(level_coarse - nlev + 1 == 0 && level_coarse + 1 >= ctx->upload_levels))
+            return join_uploads(ctx);
         return MBAVO_OK;
     }
 } // namespace
@@ -792,6 +846,7 @@ extern "C"
         cudaFree(ctx->phase_times_dev);
         cudaFree(ctx->gn_state);
         cudaFree(ctx->sweep_ctl);
+        cudaFree(ctx->sweep_pass_times);
         cudaFree(ctx->kf_dev);
         cudaFreeHost(ctx->kf_host);
         cudaFree(ctx->sel_cells);
@@ -817,6 +872,10 @@ extern "C"
             cudaStreamDestroy(ctx->copy_stream);
         if (ctx->copy_done)
             cudaEventDestroy(ctx->copy_done);
+        if (ctx->images_done)
+            cudaEventDestroy(ctx->images_done);
+        cudaFree(ctx->ready_dev);
+        cudaFreeHost(ctx->ready_src);
         cudaGetLastError();
         delete ctx;
         return MBAVO_OK;
@@ -871,8 +930,11 @@ extern "C"
         cudaStream_t s = ctx->stream;
         // nothing in flight may still read the buffers we are about to replace (only mbavo_evaluate_async leaves work in
         // flight; every other entry point returns with the stream idle)
-        if (cudaStreamQuery(s) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(s));
+        {
+            const int rcq = quiesce(ctx);
+            if (rcq != MBAVO_OK)
+                return rcq;
+        }
         const size_t npix = (size_t)d->H * d->W;
         const int P = d->num_keypoints, F = d->n_frames;
 
@@ -990,8 +1052,13 @@ extern "C"
     }
 
     // validation, allocation and the enqueue of the upload + pyramid / gradient / texel kernels on `s` (no synchronisation)
-    static int enqueue_keyframe_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0, cudaStream_t s)
+    // what: bit 0 = allocate + enqueue the level-0 copy on s_copy, bit 1 = enqueue the kernels on s (mbavo_set_frame issues the copies
+    // of both images first, on its copy stream, and the kernels afterwards)
+    static int enqueue_keyframe_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0, cudaStream_t s,
+                                        int what = 3, cudaStream_t s_copy = nullptr)
     {
+        if (!s_copy)
+            s_copy = s;
         if (!ctx || !ref_I0 || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS || (mem != MBAVO_MEM_HOST && mem != MBAVO_MEM_DEVICE))
             return fail(MBAVO_EINVAL, "bad arguments");
         if ((H0 >> (n_levels - 1)) < 2 || (W0 >> (n_levels - 1)) < 2)
@@ -1029,13 +1096,16 @@ extern "C"
                 CUDA_TRY(cudaMalloc(&L.pyr_grad, npix * 2 * sizeof(float)));
                 L.pyr_cap_grad = npix;
             }
-            if (l == 0)
-                CUDA_TRY(cudaMemcpyAsync(L.pyr_ref, ref_I0, npix, mem == MBAVO_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-            else
-                CUDA_TRY(launch_pyr_down_kernel(ctx->levels[l - 1].pyr_ref, W0 / (1 << (l - 1)), L.pyr_ref, H, W, s));
-            CUDA_TRY(launch_pack_image_kernel(L.pyr_ref, H, W, ctx->use_texels ? L.tex_pair : nullptr, ctx->use_texels ? L.tex_quad : nullptr,
-                                              ctx->use_texels ? nullptr : L.pyr_grad, s));
-            ctx->launches += l == 0 ? 1 : 2;
+            if (l == 0 && (what & 1))
+                CUDA_TRY(cudaMemcpyAsync(L.pyr_ref, ref_I0, npix, mem == MBAVO_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s_copy));
+            if (what & 2)
+            {
+                if (l > 0)
+                    CUDA_TRY(launch_pyr_down_kernel(ctx->levels[l - 1].pyr_ref, W0 / (1 << (l - 1)), L.pyr_ref, H, W, s));
+                CUDA_TRY(launch_pack_image_kernel(L.pyr_ref, H, W, ctx->use_texels ? L.tex_pair : nullptr, ctx->use_texels ? L.tex_quad : nullptr,
+                                                  ctx->use_texels ? nullptr : L.pyr_grad, s));
+                ctx->launches += l == 0 ? 1 : 2;
+            }
             if (L.owns)
                 free_level(L); // buffers of an earlier mbavo_set_level
             L.dev.H = H, L.dev.W = W;
@@ -1055,8 +1125,11 @@ extern "C"
             return fail(MBAVO_EINVAL, "null context");
         DeviceGuard guard(ctx->device);
         cudaStream_t s = ctx->stream;
-        if (cudaStreamQuery(s) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(s));
+        {
+            const int rcq = quiesce(ctx);
+            if (rcq != MBAVO_OK)
+                return rcq;
+        }
         int rc = enqueue_keyframe_pyramid(ctx, n_levels, mem, ref_I0, H0, W0, s);
         cudaError_t e = cudaStreamSynchronize(s); // the host image is only borrowed for the call
         if (rc == MBAVO_OK && e != cudaSuccess)
@@ -1064,8 +1137,11 @@ extern "C"
         return rc;
     }
 
-    static int enqueue_live_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *const *cur_I0, int n_frames, cudaStream_t s)
+    static int enqueue_live_pyramid(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *const *cur_I0, int n_frames, cudaStream_t s,
+                                    int what = 3, cudaStream_t s_copy = nullptr)
     {
+        if (!s_copy)
+            s_copy = s;
         if (!ctx || !cur_I0 || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS || (mem != MBAVO_MEM_HOST && mem != MBAVO_MEM_DEVICE))
             return fail(MBAVO_EINVAL, "bad arguments");
         if (n_frames < 1 || n_frames > ctx->lim.max_num_frames)
@@ -1095,9 +1171,10 @@ extern "C"
                 {
                     if (!cur_I0[f])
                         return fail(MBAVO_EINVAL, "null image");
-                    CUDA_TRY(cudaMemcpyAsync(L.pyr_cur[f], cur_I0[f], npix, mem == MBAVO_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+                    if (what & 1)
+                        CUDA_TRY(cudaMemcpyAsync(L.pyr_cur[f], cur_I0[f], npix, mem == MBAVO_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s_copy));
                 }
-                else
+                else if (what & 2)
                 {
                     CUDA_TRY(launch_pyr_down_kernel(ctx->levels[l - 1].pyr_cur[f], ctx->levels[l - 1].dev.W, L.pyr_cur[f], L.dev.H, L.dev.W, s));
                     ctx->launches += 1;
@@ -1107,7 +1184,7 @@ extern "C"
             for (int f = n_frames; f < kMaxFrames; ++f)
                 L.dev.cur_I[f] = nullptr;
             L.dev.F = n_frames;
-            if (L.flags)
+            if (L.flags && (what & 2))
                 CUDA_TRY(cudaMemsetAsync(L.flags, 0, ctx->lim.max_num_keypoints, s)); // tracker.cpp:600-601
             L.num_bad = 0;
             L.has_live = true;
@@ -1122,8 +1199,11 @@ extern "C"
             return fail(MBAVO_EINVAL, "null context");
         DeviceGuard guard(ctx->device);
         cudaStream_t s = ctx->stream;
-        if (cudaStreamQuery(s) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(s));
+        {
+            const int rcq = quiesce(ctx);
+            if (rcq != MBAVO_OK)
+                return rcq;
+        }
         int rc = enqueue_live_pyramid(ctx, n_levels, mem, cur_I0, n_frames, s);
         cudaError_t e = cudaStreamSynchronize(s);
         if (rc == MBAVO_OK && e != cudaSuccess)
@@ -1133,8 +1213,12 @@ extern "C"
 
 
     // enqueue the uploads of one level's points on the context's stream (no synchronisation)
-    static int enqueue_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d, cudaStream_t s)
+    // s: stream of the copies; s_flags: stream of the outlier-flag memset.  They differ in mbavo_set_frame: a memset is a KERNEL, and
+    // a kernel on the copy stream could not start while a persistent sweep kernel that waits for this very upload holds every SM.
+    static int enqueue_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d, cudaStream_t s, cudaStream_t s_flags = nullptr)
     {
+        if (!s_flags)
+            s_flags = s;
         if (!ctx || !d || level < 0 || level >= MBAVO_MAX_LEVELS)
             return fail(MBAVO_EINVAL, "bad context / level");
         if (d->mem != MBAVO_MEM_HOST && d->mem != MBAVO_MEM_DEVICE)
@@ -1187,7 +1271,7 @@ extern "C"
             L.dev.z = d->keypoint_z;
         }
         CUDA_TRY(cudaMemcpyAsync(L.pattern, d->pattern_xy, sizeof(int2) * d->patch_size, cudaMemcpyDefault, s));
-        CUDA_TRY(cudaMemsetAsync(L.flags, 0, P, s));
+        CUDA_TRY(cudaMemsetAsync(L.flags, 0, P, s_flags));
         L.num_bad = 0;
         L.dev.fx = d->fx, L.dev.fy = d->fy, L.dev.cx = d->cx, L.dev.cy = d->cy;
         L.dev.inv_fx = 1.0 / d->fx, L.dev.inv_fy = 1.0 / d->fy;
@@ -1206,8 +1290,11 @@ extern "C"
         if (!ctx)
             return fail(MBAVO_EINVAL, "null context");
         DeviceGuard guard(ctx->device);
-        if (cudaStreamQuery(ctx->stream) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        {
+            const int rcq = quiesce(ctx);
+            if (rcq != MBAVO_OK)
+                return rcq;
+        }
         int rc = enqueue_level_points(ctx, level, d, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream); // host buffers are only borrowed for the call
         if (rc == MBAVO_OK && e != cudaSuccess)
@@ -1220,8 +1307,11 @@ extern "C"
         if (!ctx || !points || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS)
             return fail(MBAVO_EINVAL, "bad arguments");
         DeviceGuard guard(ctx->device);
-        if (cudaStreamQuery(ctx->stream) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        {
+            const int rcq = quiesce(ctx);
+            if (rcq != MBAVO_OK)
+                return rcq;
+        }
         int rc = MBAVO_OK;
         for (int l = 0; l < n_levels && rc == MBAVO_OK; ++l)
             rc = enqueue_level_points(ctx, l, points + l, ctx->stream);
@@ -1239,25 +1329,54 @@ extern "C"
     int mbavo_set_frame(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0,
                         const unsigned char *const *cur_I0, int n_frames, const mbavo_level_points *points, int flags)
     {
-        if (!ctx || !points || (!ref_I0 && !cur_I0))
+        if (!ctx || !points || (!ref_I0 && !cur_I0) || n_levels < 1 || n_levels > MBAVO_MAX_LEVELS)
             return fail(MBAVO_EINVAL, "bad arguments");
         DeviceGuard guard(ctx->device);
         cudaStream_t s = ctx->stream;
-        if (cudaStreamQuery(s) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(s));
         if (!ctx->copy_stream)
         {
             CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->images_done, cudaEventDisableTiming));
+            CUDA_TRY(cudaMalloc(&ctx->ready_dev, sizeof(unsigned int) * MBAVO_MAX_LEVELS));
+            CUDA_TRY(cudaMemset(ctx->ready_dev, 0, sizeof(unsigned int) * MBAVO_MAX_LEVELS));
+            CUDA_TRY(cudaMallocHost(&ctx->ready_src, sizeof(unsigned int)));
         }
+        // nothing of an earlier frame may still be in flight on either stream (its buffers are about to be replaced)
+        if (cudaStreamQuery(s) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(s));
+        if (cudaStreamQuery(ctx->copy_stream) != cudaSuccess)
+            CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->join_pending = false;
         int rc = MBAVO_OK;
-        // points first: their copies are the bulk of the bytes and depend on nothing
         for (int l = 0; l < n_levels && rc == MBAVO_OK; ++l)
-        {
             if (!ref_I0 && !ctx->levels[l].has_key)
                 rc = fail(MBAVO_ENOTREADY, "level %d has no keyframe pyramid", l);
-            else
-                rc = enqueue_level_points(ctx, l, points + l, ctx->copy_stream);
+        // 1. every copy goes to the second stream, the images first (everything waits for them), and is issued BEFORE any kernel: the
+        //    link starts working at once while the host is still enqueuing
+        cudaStream_t cs = ctx->copy_stream;
+        if (rc == MBAVO_OK && ref_I0)
+            rc = enqueue_keyframe_pyramid(ctx, n_levels, mem, ref_I0, H0, W0, s, 1, cs);
+        if (rc == MBAVO_OK && cur_I0)
+            rc = enqueue_live_pyramid(ctx, n_levels, mem, cur_I0, n_frames, s, 1, cs);
+        if (rc == MBAVO_OK)
+        {
+            cudaError_t e = cudaEventRecord(ctx->images_done, cs);
+            if (e != cudaSuccess)
+                rc = fail(MBAVO_ECUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
+        }
+        // 2. the points, coarse level first (the order a sweep needs them), behind the images on the same stream; behind each level's
+        //    points goes its ready flag
+        *ctx->ready_src = ++ctx->upload_epoch;
+        for (int l = n_levels - 1; l >= 0 && rc == MBAVO_OK; --l)
+        {
+            rc = enqueue_level_points(ctx, l, points + l, ctx->copy_stream, s); // copies on the copy stream, flag memset on the context's
+            if (rc == MBAVO_OK)
+            {
+                cudaError_t e = cudaMemcpyAsync(ctx->ready_dev + l, ctx->ready_src, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->copy_stream);
+                if (e != cudaSuccess)
+                    rc = fail(MBAVO_ECUDA, "ready flag: %s", cudaGetErrorString(e));
+            }
         }
         if (rc == MBAVO_OK)
         {
@@ -1265,22 +1384,26 @@ extern "C"
             if (e != cudaSuccess)
                 rc = fail(MBAVO_ECUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
         }
-        if (rc == MBAVO_OK && ref_I0)
-            rc = enqueue_keyframe_pyramid(ctx, n_levels, mem, ref_I0, H0, W0, s);
-        if (rc == MBAVO_OK && cur_I0)
-            rc = enqueue_live_pyramid(ctx, n_levels, mem, cur_I0, n_frames, s);
+        // 3. the context's stream: pyramid / gradient / texel kernels as soon as the images are there (and the outlier-flag memsets)
         if (rc == MBAVO_OK)
         {
-            cudaError_t e = cudaStreamWaitEvent(s, ctx->copy_done, 0);
+            cudaError_t e = cudaStreamWaitEvent(s, ctx->images_done, 0);
             if (e != cudaSuccess)
                 rc = fail(MBAVO_ECUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));
         }
-        if (rc != MBAVO_OK || !(flags & MBAVO_UPLOAD_ASYNC))
+        if (rc == MBAVO_OK && ref_I0)
+            rc = enqueue_keyframe_pyramid(ctx, n_levels, mem, ref_I0, H0, W0, s, 2);
+        if (rc == MBAVO_OK && cur_I0)
+            rc = enqueue_live_pyramid(ctx, n_levels, mem, cur_I0, n_frames, s, 2);
+        if (rc == MBAVO_OK && (flags & MBAVO_UPLOAD_ASYNC))
         {
-            cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(s);
-            if (rc == MBAVO_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
-                return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            ctx->join_pending = true; // joined lazily: by the first entry point that needs the points on the context's stream
+            ctx->upload_levels = n_levels;
+            return MBAVO_OK;
         }
+        cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(s);
+        if (rc == MBAVO_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
+            return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
         return rc;
     }
 
@@ -1304,8 +1427,11 @@ extern "C"
                 return fail(MBAVO_ENOTREADY, "level %d has no keyframe pyramid (mbavo_set_keyframe_pyramid comes first)", l);
         DeviceGuard guard(ctx->device);
         cudaStream_t s = ctx->stream;
-        if (cudaStreamQuery(s) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(s));
+        {
+            const int rcq = quiesce(ctx);
+            if (rcq != MBAVO_OK)
+                return rcq;
+        }
         const int H0 = ctx->levels[0].dev.H, W0 = ctx->levels[0].dev.W;
         SelectParams prm{};
         int total_cells = 0;
@@ -1432,6 +1558,11 @@ extern "C"
         if (capacity < P)
             return fail(MBAVO_ECAPACITY, "level %d holds %d points, capacity is %d", level, P, capacity);
         DeviceGuard guard(ctx->device);
+        {
+            const int rcj = join_uploads(ctx);
+            if (rcj != MBAVO_OK)
+                return rcj;
+        }
         cudaStream_t s = ctx->stream;
         if (xy)
             CUDA_TRY(cudaMemcpy2DAsync(xy, 16, L.dev.xy + L.dev.xy_offset, L.dev.xy_stride, 16, P, cudaMemcpyDeviceToHost, s));
@@ -1452,8 +1583,11 @@ extern "C"
             return fail(MBAVO_EINVAL, "mem must match the memory kind the level was set with");
         DeviceGuard guard(ctx->device);
         cudaStream_t s = ctx->stream;
-        if (cudaStreamQuery(s) != cudaSuccess)
-            CUDA_TRY(cudaStreamSynchronize(s));
+        {
+            const int rcq = quiesce(ctx);
+            if (rcq != MBAVO_OK)
+                return rcq;
+        }
         const size_t npix = (size_t)L.dev.H * L.dev.W;
         for (int f = 0; f < n_frames; ++f)
         {
@@ -1475,6 +1609,11 @@ extern "C"
         if (!ctx || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
             return fail(MBAVO_ENOTREADY, "level not set");
         DeviceGuard guard(ctx->device);
+        {
+            const int rcj = join_uploads(ctx);
+            if (rcj != MBAVO_OK)
+                return rcj;
+        }
         LevelStore &L = ctx->levels[level];
         const int pts_all = ctx->shard.world > 1 && ctx->points_global[level] > 0 ? ctx->points_global[level] : L.dev.P;
         if (num_bad < 0 || num_bad >= pts_all)
@@ -1567,6 +1706,102 @@ extern "C"
         return mbavo_unpack(ctx->result_vals.data(), pl.kmin, pl.NK, sp->num_ctrl_knots, total_cost, H, g);
     }
 
+    // One Hessian-pass evaluation whose per-stage intermediates come back to the host (SURVEY.md §8d stage gates): the fp64 pose
+    // and spline Jacobian blocks of every exposure sample before they are rounded into the fp32 sample records, the fp64 patch
+    // centres, and every pixel's raw residual and raw 1 x 6NK Jacobian row.  Runs the PRODUCT kernels with their debug stores
+    // switched on (pose_kernel's dbg pointer, track_pass<DBG = true>), not a second implementation.
+    int mbavo_debug_dump(mbavo_ctx *ctx, int level, const mbavo_spline *sp, double huber_a, mbavo_debug_out *out)
+    {
+        if (!ctx || !out)
+            return fail(MBAVO_EINVAL, "null argument");
+        DeviceGuard guard(ctx->device);
+        EvalPlan pl;
+        int rc = plan_evaluation(ctx, level, sp, true, pl);
+        if (rc != MBAVO_OK)
+            return rc;
+        LevelStore &L = ctx->levels[level];
+        if (ctx->shard.world > 1)
+            return fail(MBAVO_EINVAL, "mbavo_debug_dump works on an unsharded context");
+        const long long nres = (long long)(pl.P - L.num_bad) * pl.F * pl.S;
+        if (nres <= 0)
+            return fail(MBAVO_EINVAL, "no residuals left");
+        cudaStream_t s = ctx->stream;
+        rc = join_uploads(ctx);
+        if (rc != MBAVO_OK)
+            return rc;
+        const size_t n_samp = (size_t)pl.N * pl.F, n_pts = (size_t)pl.P * pl.F, n_pix = n_pts * pl.S;
+        double *d_pose = nullptr;
+        double2 *d_centres = nullptr;
+        float *d_r = nullptr, *d_J = nullptr;
+        struct Free
+        {
+            void **p[4];
+            ~Free()
+            {
+                for (auto q : p)
+                    cudaFree(*q);
+            }
+        } undo{{(void **)&d_pose, (void **)&d_centres, (void **)&d_r, (void **)&d_J}};
+        CUDA_TRY(cudaMalloc(&d_pose, sizeof(double) * n_samp * 47));
+        CUDA_TRY(cudaMalloc(&d_centres, sizeof(double2) * n_pts));
+        CUDA_TRY(cudaMalloc(&d_r, sizeof(float) * n_pix));
+        CUDA_TRY(cudaMalloc(&d_J, sizeof(float) * n_pix * 6 * pl.NK));
+        CUDA_TRY(cudaMemsetAsync(d_centres, 0, sizeof(double2) * n_pts, s));
+        CUDA_TRY(cudaMemsetAsync(d_r, 0, sizeof(float) * n_pix, s));
+        CUDA_TRY(cudaMemsetAsync(d_J, 0, sizeof(float) * n_pix * 6 * pl.NK, s));
+        // small block shape, texel / direct variant as the level dictates
+        pl.big = false;
+        pl.smem = track_kernel_smem_bytes(pl.K, pl.NK, true, false, pl.N, pl.S, pl.TP);
+        const int wpb = track_warps(true, pl.NK, false);
+        int want = (pl.batches_per_frame + wpb - 1) / wpb;
+        pl.grid = dim3(want < 4 * ctx->num_sms ? want : 4 * ctx->num_sms, pl.F, 1);
+        rc = ensure_block_partials(ctx, (size_t)pl.grid.x * pl.grid.y * pl.E);
+        if (rc != MBAVO_OK)
+            return rc;
+        CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, 1, ctx->samples, ctx->mid, ctx->seg_end, s, nullptr, 0, false, kBufA,
+                                    ctx->samples_stride, kMidDoubles * kMaxFrames, kMaxSegments * kMaxFrames, d_pose));
+        TrackParams prm;
+        fill_track_params(ctx, level, pl, ctx->packed_dev, true, 1.0 / (double)nres, huber_a, nullptr, prm);
+        prm.dbg_centres = d_centres, prm.dbg_r = d_r, prm.dbg_J = d_J;
+        cudaError_t e = launch_track_debug_kernel(pl.K, pl.NK, prm, pl.grid, pl.smem, s);
+        if (e == cudaErrorNotSupported)
+        {
+            cudaGetLastError();
+            return fail(MBAVO_ECAPACITY, "mbavo_debug_dump is built for k=2 with 2 or 3 knots in the window and k=4 with 4 (texel path)");
+        }
+        if (e != cudaSuccess)
+            return fail(MBAVO_ECUDA, "debug kernel: %s", cudaGetErrorString(e));
+        ctx->launches += 2;
+        L.last_eval_frames = pl.F;
+        rc = wait_result(ctx);
+        if (rc != MBAVO_OK)
+            return rc;
+        CUDA_TRY(cudaStreamSynchronize(s));
+        out->kmin = pl.kmin, out->knot_window = pl.NK, out->spline_deg_k = pl.K;
+        out->cost = ctx->result_vals[0];
+        std::vector<double> hp(n_samp * 47);
+        CUDA_TRY(cudaMemcpy(hp.data(), d_pose, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost));
+        for (size_t g = 0; g < n_samp; ++g)
+        {
+            const double *o = hp.data() + g * 47;
+            if (out->poses_tq)
+                std::memcpy(out->poses_tq + 7 * g, o, sizeof(double) * 7);
+            if (out->blend_weights)
+                std::memcpy(out->blend_weights + pl.K * g, o + 7, sizeof(double) * pl.K);
+            if (out->theta)
+                std::memcpy(out->theta + 9 * pl.K * g, o + 11, sizeof(double) * 9 * pl.K);
+            if (out->segment_start_knot)
+                out->segment_start_knot[g] = pl.kmin + ctx->stage.seg_off[g];
+        }
+        if (out->patch_centres)
+            CUDA_TRY(cudaMemcpy(out->patch_centres, d_centres, sizeof(double2) * n_pts, cudaMemcpyDeviceToHost));
+        if (out->residuals)
+            CUDA_TRY(cudaMemcpy(out->residuals, d_r, sizeof(float) * n_pix, cudaMemcpyDeviceToHost));
+        if (out->jacobians)
+            CUDA_TRY(cudaMemcpy(out->jacobians, d_J, sizeof(float) * n_pix * 6 * pl.NK, cudaMemcpyDeviceToHost));
+        return MBAVO_OK;
+    }
+
     int mbavo_evaluate_async(mbavo_ctx *ctx, int level, const mbavo_spline *sp, double huber_a, int with_hessian,
                              long long num_residuals_global, double *packed_dev, int *kmin, int *knot_window)
     {
@@ -1601,8 +1836,10 @@ extern "C"
     int mbavo_gn_sweep_device(mbavo_ctx *ctx, int level_coarse, int level_fine, int chain, int k, double t0, double dt, int n,
                               double *knots_t, double *knots_R, double radius, double huber_a, double *costs)
     {
-        if (!ctx || !ctx->use_device_sweep || ctx->timing || ctx->force_phases > 0)
+        if (!ctx || !ctx->use_device_sweep || ctx->force_phases > 0)
             return 1;
+        // event timing brackets ONE kernel: the persistent sweep kernel qualifies, a chain of per-pass launches does not
+        const bool timing_needs_persistent = ctx->timing;
         const int nlev = level_coarse - level_fine + 1;
         if (nlev < 1 || nlev > MBAVO_MAX_LEVELS || n < 2 || n > 16)
             return 1;
@@ -1633,6 +1870,8 @@ extern "C"
                              ctx->levels[level_coarse - li].dev.N == ctx->levels[level_coarse].dev.N;
         }
         persistent = persistent && ctx->use_persistent;
+        if (timing_needs_persistent && !persistent)
+            return 1;
         for (int li = 0; li < nlev && persistent; ++li)
         {
             const LevelStore &L = ctx->levels[level_coarse - li];
@@ -1644,6 +1883,8 @@ extern "C"
             if (rcp < 0)
                 return rcp;
             persistent = rcp == MBAVO_OK; // 1: no instantiation for this window, fall through
+            if (timing_needs_persistent && !persistent)
+                return 1;
         }
         for (int li = 0; li < nlev && !persistent; ++li)
         {
@@ -1695,6 +1936,9 @@ extern "C"
             if (persistent && ctx->sweep_ctl)
             {
                 // a block gave up (SweepCtl::abort) or the launch failed: drain the stream and re-arm the pass barrier
+                if (ctx->copy_stream)
+                    cudaStreamSynchronize(ctx->copy_stream);
+                ctx->join_pending = false;
                 cudaStreamSynchronize(ctx->stream);
                 cudaMemset(ctx->sweep_ctl, 0, sizeof(SweepCtl));
                 cudaMemset(ctx->counter, 0, sizeof(unsigned int));
@@ -1728,7 +1972,10 @@ extern "C"
         }
         ++ctx->device_sweeps;
         if (persistent)
+        {
             ++ctx->persistent_sweeps;
+            ctx->join_pending = false; // every level's Hessian pass saw its ready flag: the point copies have all landed
+        }
         if (chain)
         {
             for (int e = 0; e < 3 * n; ++e)
@@ -1744,6 +1991,11 @@ extern "C"
         if (!ctx || !poses_tq || !avg_flow || !avg_kernel_len || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
             return fail(MBAVO_ENOTREADY, "level not set");
         DeviceGuard guard(ctx->device);
+        {
+            const int rcj = join_uploads(ctx);
+            if (rcj != MBAVO_OK)
+                return rcj;
+        }
         LevelStore &L = ctx->levels[level];
         cudaStream_t s = ctx->stream;
         if (!ctx->kf_dev)
@@ -1775,6 +2027,11 @@ extern "C"
         if (!ctx || !out || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
             return fail(MBAVO_ENOTREADY, "level not set");
         DeviceGuard guard(ctx->device);
+        {
+            const int rcj = join_uploads(ctx);
+            if (rcj != MBAVO_OK)
+                return rcj;
+        }
         LevelStore &L = ctx->levels[level];
         if (L.last_eval_frames == 0)
             return fail(MBAVO_ENOTREADY, "no evaluation has run on level %d", level);
@@ -1789,6 +2046,11 @@ extern "C"
         if (!ctx || !num_bad || level < 0 || level >= MBAVO_MAX_LEVELS || !ctx->levels[level].set)
             return fail(MBAVO_ENOTREADY, "level not set");
         DeviceGuard guard(ctx->device);
+        {
+            const int rcj = join_uploads(ctx);
+            if (rcj != MBAVO_OK)
+                return rcj;
+        }
         LevelStore &L = ctx->levels[level];
         if (L.last_eval_frames == 0)
             return fail(MBAVO_ENOTREADY, "no evaluation has run on level %d", level);
@@ -1889,6 +2151,10 @@ extern "C"
                 CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
                 sh.peer[r] = static_cast<Mailbox *>(p);
                 ctx->peer_is_ipc[r] = true;
+                cudaPointerAttributes at{};
+                if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.device == ctx->device)
+                    ctx->shard_shares_device = true; // another PROCESS on this GPU: its grids time-slice with ours
+                cudaGetLastError();
             }
         }
         ctx->shard = sh;
@@ -1944,6 +2210,26 @@ extern "C"
     long long mbavo_kernel_launches(const mbavo_ctx *ctx) { return ctx ? ctx->launches : 0; }
     long long mbavo_device_sweeps(const mbavo_ctx *ctx) { return ctx ? ctx->device_sweeps : 0; }
     long long mbavo_persistent_sweeps(const mbavo_ctx *ctx) { return ctx ? ctx->persistent_sweeps : 0; }
+
+    int mbavo_sweep_pass_times(mbavo_ctx *ctx, double *us_out, int capacity, int *num_passes)
+    {
+        if (!ctx || !us_out || !num_passes)
+            return fail(MBAVO_EINVAL, "null argument");
+        *num_passes = 0;
+        if (!ctx->sweep_pass_times || ctx->sweep_last_levels < 1)
+            return fail(MBAVO_ENOTREADY, "no persistent sweep has run on this context");
+        const int n = 2 * ctx->sweep_last_levels;
+        if (capacity < n)
+            return fail(MBAVO_ECAPACITY, "%d passes, capacity %d", n, capacity);
+        DeviceGuard guard(ctx->device);
+        unsigned long long t[1 + 2 * kMaxSweepLevels];
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpy(t, ctx->sweep_pass_times, sizeof(unsigned long long) * (n + 1), cudaMemcpyDeviceToHost));
+        for (int p = 0; p < n; ++p)
+            us_out[p] = (double)(t[p + 1] - t[p]) * 1e-3;
+        *num_passes = n;
+        return MBAVO_OK;
+    }
 
     int mbavo_level_uses_texels(const mbavo_ctx *ctx, int level)
     {

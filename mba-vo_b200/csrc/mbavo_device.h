@@ -128,6 +128,12 @@ namespace mbavo
     {
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
     }
+    __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p)
+    {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    }
     __device__ __forceinline__ unsigned long long global_timer_ns()
     {
         unsigned long long t;
@@ -241,6 +247,14 @@ namespace mbavo
         unsigned long long seq;
         ShardParams shard;                    // point sharding: the vector published is the sum over all ranks
         GnParams gn;                          // device-resident Gauss-Newton sweep
+        // persistent sweep after an asynchronous mbavo_set_frame: the level's points are valid once *ready_flag == ready_epoch (the
+        // copy stream writes the flag right behind the points); nullptr: no wait
+        const unsigned int *ready_flag;
+        unsigned int ready_epoch;
+        // mbavo_debug_dump (track_debug_kernel only): per-stage intermediates, device memory, each nullable
+        double2 *dbg_centres;                 // [F * P] patch centre of every point (compute_local_patches_xy.cu:26-49)
+        float *dbg_r;                         // [F * P * S] raw residual of every pixel
+        float *dbg_J;                         // [F * P * S * 6 NK] raw Jacobian row of every pixel, ordered [t-block | w-block] of the window
         unsigned long long *phase_times;      // development: globaltimer stamps of kernel phases (MBAVO_PROFILE_PHASES builds),
         int trace_row;                        // 16 stamps per row; row = ordinal of the launch since the trace was armed
     };
@@ -264,6 +278,9 @@ namespace mbavo
         int n_levels;
         SweepCtl *ctl;
         unsigned int base;                     // value of ctl->done when this sweep starts
+        // globaltimer stamps (ns): [0] kernel entry (after the wait for the pose kernel), [1 + p] release of pass p — so that
+        // pass p lasted stamps[1 + p] - stamps[p], everything included (wait, records, batches, reduction, solve, pose)
+        unsigned long long *pass_times;
     };
 
     // ---- semi-dense point selection (select_kernel.cu) -------------------------------------------------------------------

@@ -286,9 +286,12 @@ namespace mbavo
         // with_jacobian: 0 = pose only (Theta fields zero), 1 = whole record, kPoseJacobianOnly = only the Theta fields of a record
         // whose pose part is already in place (persistent sweep: the two halves are computed at different times)
         constexpr int kPoseJacobianOnly = 2;
+        // dbg (nullable): fp64 values BEFORE the rounding to the fp32 record, per sample [t(3) q(4) wt(K) Theta(9K)] with stride
+        // kPoseDebugStride doubles (mbavo_debug_dump)
+        constexpr int kPoseDebugStride = 7 + 4 + 36;
         template <int K>
         __host__ __device__ inline void pose_one(const EvalStage *st, const double *knots_t, const double *knots_R, int g,
-                                                 int with_jacobian, float *samples, double *mid, int *seg_end)
+                                                 int with_jacobian, float *samples, double *mid, int *seg_end, double *dbg = nullptr)
         {
             const int N = st->N;
             const int f = g / N, i = g % N;
@@ -302,6 +305,15 @@ namespace mbavo
             Q q;
             spline_pose<K>(knots_t + 3 * idx, knots_R + 4 * idx, u, tt, q, wt, with_jacobian ? Theta : nullptr);
 
+            if (dbg)
+            {
+                double *o = dbg + (size_t)g * kPoseDebugStride;
+                o[0] = tt[0], o[1] = tt[1], o[2] = tt[2], o[3] = q.x, o[4] = q.y, o[5] = q.z, o[6] = q.w;
+                for (int j = 0; j < K; ++j)
+                    o[7 + j] = wt[j];
+                for (int e = 0; e < 9 * K; ++e)
+                    o[11 + e] = with_jacobian ? Theta[e] : 0.0;
+            }
             double R[9];
             rotation_matrix(q, R);
             constexpr int REC = sample_rec_floats(K);

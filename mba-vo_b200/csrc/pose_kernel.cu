@@ -17,7 +17,7 @@ namespace mbavo
         template <int K>
         __global__ void pose_kernel(const __grid_constant__ EvalStage stage, int with_jacobian, float *__restrict__ samples,
                                     double *__restrict__ mid, int *__restrict__ seg_end, GnState *gn, int knots_from, int buf_select,
-                                    int samples_stride, int mid_stride, int seg_end_stride)
+                                    int samples_stride, int mid_stride, int seg_end_stride, double *dbg)
         {
             cudaTriggerProgrammaticLaunchCompletion(); // the tracking kernel may start its prologue now
             const double *kt = stage.knots_t, *kR = stage.knots_R;
@@ -45,7 +45,7 @@ namespace mbavo
             samples += (size_t)buf * samples_stride, mid += (size_t)buf * mid_stride, seg_end += (size_t)buf * seg_end_stride;
             const int g = blockIdx.x * blockDim.x + threadIdx.x;
             if (g < stage.N * stage.F)
-                pose_one<K>(&stage, kt, kR, g, with_jacobian, samples, mid, seg_end);
+                pose_one<K>(&stage, kt, kR, g, with_jacobian, samples, mid, seg_end, dbg);
         }
     } // namespace
 
@@ -69,7 +69,7 @@ namespace mbavo
     // kernel then waits for it before it reads the sweep state).
     cudaError_t launch_pose_kernel(int K, const EvalStage &stage, int total_samples, int with_jacobian, float *samples,
                                    double *mid, int *seg_end, cudaStream_t stream, GnState *gn, int knots_from, bool dependent,
-                                   int buf_select, int samples_stride, int mid_stride, int seg_end_stride)
+                                   int buf_select, int samples_stride, int mid_stride, int seg_end_stride, double *dbg)
     {
         const int threads = 64;
         const int blocks = (total_samples + threads - 1) / threads;
@@ -81,8 +81,8 @@ namespace mbavo
         cfg.attrs = attr, cfg.numAttrs = (dependent && gn) ? 1 : 0;
         if (K == 2)
             return cudaLaunchKernelEx(&cfg, pose_kernel<2>, stage, with_jacobian, samples, mid, seg_end, gn, knots_from, buf_select, samples_stride,
-                                      mid_stride, seg_end_stride);
+                                      mid_stride, seg_end_stride, dbg);
         return cudaLaunchKernelEx(&cfg, pose_kernel<4>, stage, with_jacobian, samples, mid, seg_end, gn, knots_from, buf_select, samples_stride,
-                                  mid_stride, seg_end_stride);
+                                  mid_stride, seg_end_stride, dbg);
     }
 } // namespace mbavo

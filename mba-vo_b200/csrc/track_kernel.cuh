@@ -140,7 +140,7 @@ namespace mbavo
         // Per-item setup: patch centre (fp64), integer live pixel, ray.  compute_local_patches_xy.cu:26-49,
         // compute_hessian_gradients_cost.cu:63-78.
         __device__ __forceinline__ PixelRec setup_pixel(const LevelDev &lv, const double *__restrict__ mid, int f, int p,
-                                                        int j, const int2 *__restrict__ pattern_s)
+                                                        int j, const int2 *__restrict__ pattern_s, double2 *centre_out = nullptr)
         {
             PixelRec ps;
             ps.state = 0;
@@ -161,6 +161,8 @@ namespace mbavo
             const double Pcz = mid[6] * Prx + mid[7] * Pry + mid[8] * Prz + mid[11];
             const double ccx = Pcx / Pcz * lv.fx + lv.cx;
             const double ccy = Pcy / Pcz * lv.fy + lv.cy;
+            if (centre_out)
+                *centre_out = make_double2(ccx, ccy);
             const int2 d = pattern_s[j];
             const double px = ccx + d.x, py = ccy + d.y;
             // (int) of a double: truncation toward zero; guard the conversion range first
@@ -635,6 +637,7 @@ namespace mbavo
             SweepCtl *ctl;
             unsigned int target;     // ctl->done value that makes the records of this pass valid
             const EvalStage *stage;  // frame times / segment table for the candidate's sample records
+            unsigned long long *t_release; // where the pass's last block stamps the globaltimer when it releases the pass
         };
 
         // spin (thread 0) until ctl->done reaches target; false: aborted or timed out (the caller leaves the kernel)
@@ -668,6 +671,32 @@ namespace mbavo
             return go;
         }
 
+        // spin (thread 0) until the copy engine has delivered the level's points (TrackParams::ready_flag); false: timed out
+        __device__ __forceinline__ bool wait_ready(const unsigned int *flag, unsigned int epoch, SweepCtl *ctl)
+        {
+            __shared__ int ready_s;
+            if (threadIdx.x == 0)
+            {
+                int go = 1;
+                const unsigned long long t0 = global_timer_ns();
+                while (ld_acquire_sys_u32(flag) != epoch)
+                {
+                    if (*reinterpret_cast<volatile int *>(&ctl->abort) != 0 || global_timer_ns() - t0 > 4000000000ull)
+                    {
+                        *reinterpret_cast<volatile int *>(&ctl->abort) = 1;
+                        go = 0;
+                        break;
+                    }
+                    __nanosleep(64);
+                }
+                ready_s = go;
+            }
+            __syncthreads();
+            const bool go = ready_s != 0;
+            __syncthreads();
+            return go;
+        }
+
         // the candidate's sample records, computed by the threads of ONE block (the pass's last block) right after the solve:
         // same arithmetic as pose_kernel, one thread per (frame, sample)
         template <int K>
@@ -684,7 +713,8 @@ namespace mbavo
         // PERSIST = false: the body of track_kernel (one launch per pass).  PERSIST = true: one pass of sweep_kernel — all
         // blocks stay resident, the pass starts when SweepCtl::done reaches pa.target and its last block releases done =
         // target + 1.  Returns false when the sweep was aborted.
-        template <int K, int NK, bool WITH_J, bool PACKED, int WARPS, bool PERSIST>
+        // DBG: also writes the per-stage intermediates of mbavo_debug_dump (patch centres, raw residuals, raw 1 x 6NK rows)
+        template <int K, int NK, bool WITH_J, bool PACKED, int WARPS, bool PERSIST, bool DBG = false>
         __device__ __forceinline__ bool track_pass(const TrackParams &prm, unsigned char *smem_raw, const PersistArgs pa)
         {
             using G = RowGeom<NK, WITH_J>;
@@ -738,6 +768,8 @@ namespace mbavo
             if constexpr (PERSIST)
             {
                 if (!wait_pass(pa.ctl, pa.target))
+                    return false;
+                if (prm.ready_flag != nullptr && !wait_ready(prm.ready_flag, prm.ready_epoch, pa.ctl))
                     return false;
             }
             else
@@ -805,7 +837,13 @@ namespace mbavo
                     {
                         const int it = base + lane;
                         const bool in_batch = it < items;
-                        my_pix[lane] = setup_pixel(lv, mid, f, in_batch ? p0 + it / S : lv.P, in_batch ? it % S : 0, pattern_s);
+                        double2 *centre_out = nullptr;
+                        if constexpr (DBG)
+                        {
+                            if (in_batch && it % S == 0 && p0 + it / S < lv.P && prm.dbg_centres)
+                                centre_out = prm.dbg_centres + (size_t)f * lv.P + p0 + it / S;
+                        }
+                        my_pix[lane] = setup_pixel(lv, mid, f, in_batch ? p0 + it / S : lv.P, in_batch ? it % S : 0, pattern_s, centre_out);
                     }
                     __syncwarp();
                     MBAVO_STAMP(4);
@@ -867,6 +905,29 @@ namespace mbavo
                         const float r = valid ? sumI * inv_N - icur : 0.f;
                         float sw;
                         const float rho = huber(r, huber_a, sw);
+                        if constexpr (DBG && WITH_J)
+                        {
+                            // the pixel's raw residual and Jacobian row (compute_hessian_gradients_cost.cu:115-151), before Huber
+                            const int pp = p0 + (base + q) / S;
+                            if (phase == 0 && q < chunk && pp < lv.P)
+                            {
+                                const size_t pix = ((size_t)f * lv.P + pp) * S + (base + q) % S;
+                                if (prm.dbg_r)
+                                    prm.dbg_r[pix] = r;
+                                if (prm.dbg_J)
+                                {
+                                    float *o = prm.dbg_J + pix * (6 * NK);
+#pragma unroll
+                                    for (int a = 0; a < NK; ++a)
+                                    {
+                                        o[3 * a + 0] = valid ? inv_N * J[a][0].x : 0.f, o[3 * a + 1] = valid ? inv_N * J[a][0].y : 0.f;
+                                        o[3 * a + 2] = valid ? inv_N * J[a][1].x : 0.f;
+                                        o[3 * NK + 3 * a + 0] = valid ? inv_N * J[a][1].y : 0.f;
+                                        o[3 * NK + 3 * a + 1] = valid ? inv_N * J[a][2].x : 0.f, o[3 * NK + 3 * a + 2] = valid ? inv_N * J[a][2].y : 0.f;
+                                    }
+                                }
+                            }
+                        }
                         if (phase == 0 && q < chunk)
                         {
                             my_rho[base + q] = rho;
@@ -1150,6 +1211,7 @@ namespace mbavo
                         if (lane32 == 0)
                         {
                             *prm.counter = 0u;
+                            *pa.t_release = global_timer_ns();
                             st_release_gpu(&pa.ctl->done, pa.target + 1u);
                         }
                     }
@@ -1193,6 +1255,7 @@ namespace mbavo
                 if (threadIdx.x == 0)
                 {
                     *prm.counter = 0u;
+                    *pa.t_release = global_timer_ns();
                     st_release_gpu(&pa.ctl->done, pa.target + 1u);
                 }
             }
@@ -1212,6 +1275,24 @@ namespace mbavo
             track_pass<K, NK, WITH_J, PACKED, track_warps(WITH_J, NK, BIG), false>(prm, smem_raw, PersistArgs{});
         }
 
+        // Hessian pass that also dumps its per-stage intermediates (mbavo_debug_dump): test infrastructure of the product kernel,
+        // same code path with DBG = true; small block shape.
+        template <int K, int NK, bool PACKED>
+        __global__ void __launch_bounds__(track_warps(true, NK, false) * 32, 1) track_debug_kernel(const __grid_constant__ TrackParams prm)
+        {
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            track_pass<K, NK, true, PACKED, track_warps(true, NK, false), false, true>(prm, smem_raw, PersistArgs{});
+        }
+        template <int K, int NK, bool PACKED>
+        cudaError_t launch_debug_one(const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream)
+        {
+            cudaError_t e = cudaFuncSetAttribute(track_debug_kernel<K, NK, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess)
+                return e;
+            track_debug_kernel<K, NK, PACKED><<<grid, track_warps(true, NK, false) * 32, smem, stream>>>(prm);
+            return cudaGetLastError();
+        }
+
         // The whole coarse-to-fine sweep in one launch: one block per SM, all passes inside (see SweepCtl).  The sample records
         // of the knots the sweep starts from come from the pose kernel launched right before it.
         template <int K, int NK, bool PACKED>
@@ -1221,12 +1302,14 @@ namespace mbavo
             extern __shared__ __align__(16) unsigned char smem_raw[];
             constexpr int WARPS = track_warps(true, NK, true);
             cudaGridDependencySynchronize(); // the pose kernel's records (and the sweep state it initialised)
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+                sp.pass_times[0] = global_timer_ns();
             for (int li = 0; li < sp.n_levels; ++li)
             {
-                const PersistArgs ph{sp.ctl, sp.base + 2u * (unsigned int)li, &stage};
+                const PersistArgs ph{sp.ctl, sp.base + 2u * (unsigned int)li, &stage, sp.pass_times + 1 + 2 * li};
                 if (!track_pass<K, NK, true, PACKED, WARPS, true>(sp.pass[2 * li], smem_raw, ph))
                     return;
-                const PersistArgs pc{sp.ctl, sp.base + 2u * (unsigned int)li + 1u, &stage};
+                const PersistArgs pc{sp.ctl, sp.base + 2u * (unsigned int)li + 1u, &stage, sp.pass_times + 2 + 2 * li};
                 if (!track_pass<K, NK, false, PACKED, WARPS, true>(sp.pass[2 * li + 1], smem_raw, pc))
                     return;
             }

@@ -153,6 +153,64 @@ def ramp_image(H: int, W: int) -> np.ndarray:
     return ((c + r) % 255).astype(np.uint8)
 
 
+# the reference's synthetic scene: five rectangles (top-left corner, size) and two triangles, white on black
+SHAPES_RECTS = [((300, 50), (50, 100)), ((250, 200), (100, 50)), ((400, 300), (100, 100)), ((500, 50), (100, 100)), ((250, 300), (100, 100))]
+SHAPES_TRIANGLES = [[(500, 50), (400, 150), (550, 250)], [(150, 300), (50, 450), (250, 400)]]
+
+
+def _line_pixels(p0, p1):
+    """cv::LineIterator, 8-connected, left to right (what cv::fillPoly draws along every polygon edge with LINE_8)."""
+    if p1[0] < p0[0]:
+        p0, p1 = p1, p0
+    (x, y), (x1, y1) = p0, p1
+    dx, dy = x1 - x, abs(y1 - y)
+    sy = 1 if y1 >= y else -1
+    out = []
+    if dx >= dy:
+        err = dx - 2 * dy
+        for _ in range(dx + 1):
+            out.append((x, y))
+            if err < 0:
+                err += 2 * dx
+                y += sy
+            err -= 2 * dy
+            x += 1
+    else:
+        err = dy - 2 * dx
+        for _ in range(dy + 1):
+            out.append((x, y))
+            if err < 0:
+                err += 2 * dy
+                x += 1
+            err -= 2 * dx
+            y += sy
+    return out
+
+
+def shapes_image(H: int = 480, W: int = 640) -> np.ndarray:
+    """synthesize_img_with_rand_shapes (src/ba_tracker/generate_synthetic_data.cpp:11-125): the reference's own test scene — five
+    rectangles and two triangles filled white (255) on black by cv::fillPoly(..., LINE_8).  For these integer-vertex convex
+    polygons fillPoly covers the lattice points of the closed polygon plus the Bresenham line (cv::LineIterator, 8-connected,
+    left to right) along every edge; pinned byte for byte to OpenCV's own output in tests/golden/shapes.npz."""
+    im = np.zeros((H, W), dtype=np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    polys = [[(x, y), (x + w, y), (x + w, y + h), (x, y + h)] for (x, y), (w, h) in SHAPES_RECTS] + SHAPES_TRIANGLES
+    for pts in polys:
+        n = len(pts)
+        area = sum(pts[i][0] * pts[(i + 1) % n][1] - pts[(i + 1) % n][0] * pts[i][1] for i in range(n))
+        sgn = 1 if area > 0 else -1
+        inside = np.ones((H, W), dtype=bool)
+        for i in range(n):
+            (x0, y0), (x1, y1) = pts[i], pts[(i + 1) % n]
+            inside &= sgn * ((x1 - x0) * (yy - y0) - (y1 - y0) * (xx - x0)) >= 0
+        im[inside] = 255
+        for i in range(n):
+            for x, y in _line_pixels(pts[i], pts[(i + 1) % n]):
+                if 0 <= x < W and 0 <= y < H:
+                    im[y, x] = 255
+    return im
+
+
 def image_gradient(I: np.ndarray) -> np.ndarray:
     """Gradient.h:17-75 — 0.5 * central difference, zero 1-px border, interleaved (dx, dy) float32."""
     H, W = I.shape
@@ -266,7 +324,7 @@ def make_problem(name: str, W: int, H: int, levels: int, P0: int, N: int, n_knot
                                 trans_per_seg=0.05 * plane_z * motion_scale / n_seg)
     init_t, init_R = perturb_knots(gt_t, gt_R, rng, sigma_init)
 
-    I0 = make_texture(H, W, seed + 17) if image == "texture" else ramp_image(H, W)
+    I0 = make_texture(H, W, seed + 17) if image == "texture" else (shapes_image(H, W) if image == "shapes" else ramp_image(H, W))
     cur0 = [synthesize_blurred(I0, plane_z, fx0, fy0, cx0, cy0, k, gt_t, gt_R, t0, dt, cap[f], exp[f], n_gt_samples)
             for f in range(F)]
 

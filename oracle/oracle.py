@@ -246,6 +246,17 @@ class RefLib(_Lib):
     def available() -> bool:
         return os.path.exists(os.path.join(_HERE, "_ref", "libmbavo_ref.so"))
 
+    def spline_pose(self, k, t0, dt, knots_t, knots_R, t):
+        """One pose by the reference's spline functors -> [tx ty tz qx qy qz qw]."""
+        kt = np.ascontiguousarray(knots_t, dtype=np.float64)
+        kR = np.ascontiguousarray(knots_R, dtype=np.float64)
+        out = np.zeros(7)
+        f = self.fn("spline_pose")
+        f.restype = C.c_int
+        if f(C.c_int(k), C.c_double(t0), C.c_double(dt), _ptr(kt, _dp), _ptr(kR, _dp), C.c_double(t), _ptr(out, _dp)) != 0:
+            raise RuntimeError("mbavo_ref_spline_pose failed")
+        return out
+
     def synthesize_blurred(self, I, D, fx, fy, cx, cy, k, t0, dt, knots_t, knots_R, cap, exp, num_samples):
         H, W = I.shape
         kt = np.ascontiguousarray(knots_t, dtype=np.float64)

@@ -135,6 +135,17 @@ extern "C"
         return cudaDeviceSynchronize() == cudaSuccess ? 0 : 2;
     }
 
+    // outlier flags as detectOutliersAndUploadToGpu leaves them (tracker.cpp:696-698); flags == nullptr clears them
+    int mbavo_refcuda_set_flags(void *h, const unsigned char *flags)
+    {
+        RefCtx *c = (RefCtx *)h;
+        if (flags)
+            cudaMemcpy(c->flags, flags, c->P, cudaMemcpyHostToDevice);
+        else
+            cudaMemset(c->flags, 0, c->maxP);
+        return cudaDeviceSynchronize() == cudaSuccess ? 0 : 2;
+    }
+
     // evaluate_cost_hessian_gradient (spline_update_step.cpp:97-349) + merge (merge_hessian_gradient_cost.cpp:8-87)
     int mbavo_refcuda_evaluate(void *h, double t0, double dt, const double *knots_t, const double *knots_R, int n_knots,
                                const int *seg_start, double huber_a, int num_bad, double *total_cost, double *Hout,

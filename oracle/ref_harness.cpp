@@ -415,6 +415,32 @@ extern "C"
         return VO::compute_pixel_intensity<double>(I_ref, dIxy, H, W, pose + 3, pose, D, fx, fy, cx, cy, cur, intensity, J7) ? 1 : 0;
     }
 
+    // One pose on the spline by the reference functors (what SplineSE3::GetPose evaluates, Spline.h:120-170): out7 = t then q (x,y,z,w).
+    // Used by tests/golden/make_golden.py to store, next to the golden blurred frame, the very poses it was rendered with.
+    int mbavo_ref_spline_pose(int k, double t0, double dt, const double *knots_t, const double *knots_R, double t, double *out7)
+    {
+        int idx;
+        double u;
+        Core::SplineSegmentStartKnotIdxAndNormalizedU(t, t0, dt, idx, u);
+        Core::Vector3d tc;
+        Core::Quaterniond Rc;
+        if (k == 2)
+        {
+            tc = Core::C2SplineVec3Functor(knots_t + idx * 3, u);
+            Rc = Core::C2SplineRot3Functor(knots_R + idx * 4, u);
+        }
+        else if (k == 4)
+        {
+            tc = Core::C4SplineVec3Functor(knots_t + idx * 3, u);
+            Rc = Core::C4SplineRot3Functor(knots_R + idx * 4, u);
+        }
+        else
+            return 1;
+        out7[0] = tc(0), out7[1] = tc(1), out7[2] = tc(2);
+        out7[3] = Rc.x, out7[4] = Rc.y, out7[5] = Rc.z, out7[6] = Rc.w;
+        return 0;
+    }
+
     // generate_synthetic_data.cpp:127-180 (warp_image + synthesize_motion_blurred_img) with the pose supplied by
     // the reference spline functors (SplineSE3::GetPose uses the same functors, Spline.h:120-170).
     int mbavo_ref_synthesize_blurred(const unsigned char *I_ref, int H, int W, double plane_depth,

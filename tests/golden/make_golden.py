@@ -30,8 +30,39 @@ def problem_arrays(prob):
                 knots_t=prob.knots_t, knots_R=prob.knots_R, huber_a=prob.huber_a, seg_start=prob.seg_start)
 
 
+def golden_blurred(ref):
+    """4. synthetic blurred frame (generate_synthetic_data.cpp:152-180), stored with the very poses the reference functors gave
+    for its exposure samples (sample time as :161: capture - exposure / 2 + i * exposure / (n - 1))."""
+    prob = synth.make_problem("golden_blur", W=96, H=64, levels=1, P0=4, N=4, n_knots=2, seed=5, margin=10)
+    cap, exp, n = 0.45, 0.9, 16
+    out = ref.synthesize_blurred(prob.levels[0].ref_I, 7.5, 48.0, 48.0, 48.0, 32.0, 2, 0.0, 1.0, prob.gt_knots_t,
+                                 prob.gt_knots_R, cap, exp, n)
+    poses = np.stack([ref.spline_pose(2, 0.0, 1.0, prob.gt_knots_t, prob.gt_knots_R, cap - exp * 0.5 + i * exp / (n - 1)) for i in range(n)])
+    np.savez_compressed(os.path.join(HERE, "blurred.npz"), ref_I=prob.levels[0].ref_I, knots_t=prob.gt_knots_t,
+                        knots_R=prob.gt_knots_R, D=7.5, fx=48.0, fy=48.0, cx=48.0, cy=32.0, cap=cap, exp=exp, n=n, out=out, poses_tq=poses)
+
+
+def golden_shapes():
+    """7. the reference's synthetic scene (generate_synthetic_data.cpp:11-125: synthesize_img_with_rand_shapes) drawn by OpenCV's own
+    cv::fillPoly through cv2 — same vertices, colours and LINE_8 as the reference passes."""
+    import cv2
+
+    im = np.zeros((480, 640), np.uint8)
+    for (x, y), (w, h) in synth.SHAPES_RECTS:
+        cv2.fillPoly(im, [np.array([[x, y], [x + w, y], [x + w, y + h], [x, y + h]], np.int32)], 255, cv2.LINE_8)
+    for tri in synth.SHAPES_TRIANGLES:
+        cv2.fillPoly(im, [np.array(tri, np.int32)], 255, cv2.LINE_8)
+    np.savez_compressed(os.path.join(HERE, "shapes.npz"), image=im, opencv_version=cv2.__version__)
+
+
 def main():
+    if "--only-shapes" in sys.argv:
+        golden_shapes()
+        return
     ref = O.RefLib()
+    if "--only-blurred" in sys.argv:
+        golden_blurred(ref)
+        return
     # 1. virtual poses + Jacobians on the reference test's 7-knot spline (test_compute_virtual_camera_poses, :183-342)
     kt, kR = reference_test_spline()
     cap = 0.25 + 0.5 * np.arange(4)
@@ -71,12 +102,7 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"evaluate_{tag}.npz"), cost=c, Hessian=Hm, gradient=gv, patch_costs=pc, cost_only=c2,
                             flags=flags, cost_flagged=cf, H_flagged=Hf, g_flagged=gf, patch_costs_flagged=pcf, **arrs)
 
-    # 4. synthetic blurred frame (generate_synthetic_data.cpp:152-180)
-    prob = synth.make_problem("golden_blur", W=96, H=64, levels=1, P0=4, N=4, n_knots=2, seed=5, margin=10)
-    out = ref.synthesize_blurred(prob.levels[0].ref_I, 7.5, 48.0, 48.0, 48.0, 32.0, 2, 0.0, 1.0, prob.gt_knots_t,
-                                 prob.gt_knots_R, 0.45, 0.9, 16)
-    np.savez_compressed(os.path.join(HERE, "blurred.npz"), ref_I=prob.levels[0].ref_I, knots_t=prob.gt_knots_t,
-                        knots_R=prob.gt_knots_R, D=7.5, fx=48.0, fy=48.0, cx=48.0, cy=32.0, cap=0.45, exp=0.9, n=16, out=out)
+    golden_blurred(ref)  # 4.
     # 5. semi-dense point selection by the reference's own detector sources (oracle/_ref/libmbavo_refselect.so):
     #    a textured image and the reference test's ramp image (ties in every cell), a depth map with holes
     sel = O.RefSelect()
@@ -102,6 +128,7 @@ def main():
     pyr = sel.pyramid(img, 3)
     np.savez_compressed(os.path.join(HERE, "pyramid.npz"), **{f"I{l}": im for l, (im, _) in enumerate(pyr)},
                         **{f"g{l}": g for l, (_, g) in enumerate(pyr)})
+    golden_shapes()  # 7.
     print("golden vectors written to", HERE)
 
 

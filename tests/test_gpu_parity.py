@@ -74,10 +74,13 @@ def test_golden_reference_vectors(pkg, api, O, synth, tag):
                  (float(z["cost_flagged"]), z["H_flagged"], z["g_flagged"], z["patch_costs_flagged"]))
 
 
-@pytest.mark.parametrize("name,levels", [("tiny", None), ("C1", None), ("C2", None), ("C3", [0, 4]), ("C5", None),
+@pytest.mark.parametrize("name,levels", [("tiny", None), ("C1", None), ("C2", None), ("C3", None), ("C5", None),
                                          ("C5cubic", None)])
 def test_baseline_configs_against_oracle(pkg, api, O, orc, synth, name, levels):
-    """BASELINE.json configs (C3's middle levels skipped to bound the CPU time): Hessian pass and cost-only pass."""
+    """BASELINE.json configs, every pyramid level (the oracle runs on all host cores): Hessian pass and cost-only pass."""
+    import os
+
+    orc.set_num_threads(len(os.sched_getaffinity(0)))
     prob = synth.make_config(name)
     with pkg.Context(api.limits_for(prob)) as ctx:
         api.upload_problem(ctx, prob)
@@ -125,6 +128,35 @@ def test_image_borders_and_invalid_samples(pkg, api, O, orc, synth):
     prob2.levels[0].xy[0] = [62.9999, 46.9999]
     prob2.levels[0].pattern = np.array([[0, 0], [1, 1], [0, 1], [1, 0]], dtype=np.int32)
     check_parity(O, gpu_eval(pkg, api, prob2), orc.evaluate(prob2, 0), cost_tol=1e-5, delta_tol=1.0)
+
+
+def test_reference_shapes_scene(pkg, api, O, orc, synth):
+    """The reference's own synthetic scene (synthesize_img_with_rand_shapes, generate_synthetic_data.cpp:11-125: white rectangles
+    and triangles on black, i.e. zero gradient almost everywhere and 127.5-per-pixel steps on the edges) blurred along a spline
+    as synthesize_motion_blurred_img does: evaluation parity on semi-dense points picked on its edges by the GPU selection, which
+    must be the oracle's selection."""
+    img = synth.shapes_image(480, 640)
+    assert np.array_equal(img, golden("shapes.npz")["image"])
+    prob = synth.make_problem("shapes", W=640, H=480, levels=2, P0=8, N=16, n_knots=2, k=2, seed=3, image="shapes", depth_mode="plane")
+    depth = np.full((480, 640), 7.5, dtype=np.float32)
+    lv0 = prob.levels[0]
+    with pkg.Context(api.Limits(max_num_keypoints=4096, max_num_virtual_poses_per_frame=16, max_patch_size=8, max_num_ctrl_knots=2)) as ctx:
+        ctx.set_frame_times(prob.cap, prob.exp)
+        ctx.set_keyframe_pyramid(2, lv0.ref_I)
+        ctx.set_live_pyramid(2, lv0.cur_I)
+        counts = ctx.select_points(2, depth, lv0.fx, lv0.fy, lv0.cx, lv0.cy, lv0.pattern, lv0.N, 25.0, 30, 30)
+        want_pts = O.select_points(lv0.ref_I, 2, 25.0, 30, 30, depth)
+        assert counts == [len(z) for _, z in want_pts] and counts[0] > 50
+        for level in range(2):
+            xy, z = ctx.get_points(level)
+            assert np.array_equal(xy, want_pts[level][0]) and np.array_equal(z, want_pts[level][1])
+            # keep the points whose patch stays inside the frame under the blur; evaluate on exactly those
+            lv = prob.levels[level]
+            m = 24 >> level
+            keep = (xy[:, 0] > m) & (xy[:, 0] < lv.W - 1 - m) & (xy[:, 1] > m) & (xy[:, 1] < lv.H - 1 - m)
+            lv.xy, lv.z = np.ascontiguousarray(xy[keep]), np.ascontiguousarray(z[keep])
+    check_parity(O, gpu_eval(pkg, api, prob, 0), orc.evaluate(prob, 0))
+    check_parity(O, gpu_eval(pkg, api, prob, 1), orc.evaluate(prob, 1))
 
 
 def test_keyframe_texels_and_direct_gather(pkg, api, O, orc, synth, monkeypatch):
@@ -238,7 +270,7 @@ def test_set_frame_single_call_upload(pkg, api, O, orc, synth, async_upload):
 
 def test_synthetic_blurred_frame_bit_exact(pkg, api, orc, synth):
     """mbavo_synthesize_blurred (generate_synthetic_data.cpp:127-180) is byte work: bit-exact against the oracle's
-    restatement on the same poses, and equal to the reference-generated golden frame up to the pose rounding."""
+    restatement on the same poses, and bit-exact against the reference-generated golden frame."""
     prob = synth.make_problem("blur", W=160, H=120, levels=1, P0=4, N=4, n_knots=3, k=2, seed=5, margin=10, motion_scale=3.0)
     I = prob.levels[0].ref_I
     ts = 0.1 + np.arange(24) * 1.7 / 23
@@ -247,14 +279,12 @@ def test_synthetic_blurred_frame_bit_exact(pkg, api, orc, synth):
     want = orc.warp_mean(I, 7.5, 80.0, 80.0, 80.0, 60.0, poses)
     assert np.array_equal(got, want)
     assert (got == 0).any() and (got > 0).any()  # the strong motion leaves part of the frame without keyframe coverage
+    # the frame the reference's own warp_image + synthesize_motion_blurred_img rendered (oracle/_ref), with the very poses its
+    # spline functors gave for the exposure samples: byte for byte
     z = golden("blurred.npz")
-    n, cap, exp = int(z["n"]), float(z["cap"]), float(z["exp"])
-    ts = [cap - exp * 0.5 + i * exp / (n - 1) for i in range(n)]
-    poses = np.array([np.concatenate(synth.spline_pose(2, z["knots_t"], z["knots_R"], 0.0, 1.0, t)) for t in ts])
     got = api.synthesize_blurred(np.ascontiguousarray(z["ref_I"]), float(z["D"]), float(z["fx"]), float(z["fy"]), float(z["cx"]),
-                                 float(z["cy"]), poses)
-    diff = np.abs(got.astype(int) - z["out"].astype(int))
-    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+                                 float(z["cy"]), np.ascontiguousarray(z["poses_tq"]))
+    assert np.array_equal(got, z["out"])
 
 
 def test_point_selection_bit_exact(pkg, api, O, orc, synth):

@@ -144,3 +144,76 @@ def test_plain_c_tracker_loop(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "-> new keyframe" in r.stdout and r.stdout.count("frame ") >= 6
+
+
+@pytest.mark.parametrize("world", [2])
+def test_cross_process_sharding(pkg, synth, world):
+    """The cross-PROCESS form of point sharding — what torchrun + bench.py use at N > 1: every rank is its own process with its
+    own CUDA context, the mailboxes are mapped through CUDA IPC handles (cudaIpcGetMemHandle / cudaIpcOpenMemHandle), no barrier
+    between connect and the first collective.  One GPU per rank when the box has several; on a one-GPU box the ranks share GPU 0
+    (their kernels time-slice; the library then keeps each sweep pass in its own launch).  Evaluations, a chained sweep and a
+    whole collective LM loop give, on every rank, the result of the unsharded context."""
+    import multiprocessing as mp
+
+    import shard_worker
+    from mbavo_b200 import api
+
+    config = "tiny"
+    prob = synth.make_config(config)
+    top = len(prob.levels) - 1
+    a = (prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a)
+    with pkg.Context(api.limits_for(prob)) as ctx:
+        api.upload_problem(ctx, prob)
+        want_eval = [ctx.evaluate(l, *a, True) for l in range(top + 1)]
+        want_sweep = ctx.gn_sweep(top, 0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, 1e4, chain=True)
+        want_lm = ctx.optimize_level(top, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, huber_a=prob.huber_a)
+
+    mpc = mp.get_context("spawn")
+    pipes, procs = [], []
+    for r in range(world):
+        parent, child = mpc.Pipe()
+        p = mpc.Process(target=shard_worker.run_rank, args=(r, world, child, config))
+        p.start()
+        pipes.append(parent)
+        procs.append(p)
+    try:
+        handles = []
+        for r, c in enumerate(pipes):
+            assert c.poll(120), f"rank {r} did not export its mailbox"
+            kind, payload = c.recv()
+            assert kind == "handle", payload
+            handles.append(payload)
+        for c in pipes:
+            c.send(handles)
+        results = []
+        for r, c in enumerate(pipes):
+            assert c.poll(180), f"rank {r} did not finish"
+            kind, payload = c.recv()
+            assert kind == "result", payload
+            results.append(payload)
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for res in results:
+        for l in range(top + 1):
+            c, H, g = res["eval"][l]
+            cw, Hw, gw = want_eval[l]
+            # (a shard boundary that is not a multiple of the 4-point warp batch regroups the fp32 chunk sums: ~1e-8)
+            assert abs(c - cw) <= 1e-9 * cw and np.abs(H - Hw).max() <= 1e-6 * np.abs(Hw).max() and np.abs(g - gw).max() <= 1e-6 * np.abs(gw).max()
+            assert abs(res["cost_only"][l] - cw) <= 1e-6 * cw
+            # bit-identical on every rank: the slots are summed in rank order everywhere
+            assert c == results[0]["eval"][l][0] and np.array_equal(H, results[0]["eval"][l][1])
+        # the ~1e-8 regrouping difference of H goes through the solve: candidate knots and their costs agree to ~1e-7
+        costs, kt, kR = res["sweep"]
+        assert np.abs(costs - want_sweep[0]).max() <= 1e-5 * np.abs(want_sweep[0]).max()
+        assert np.abs(kt - want_sweep[1]).max() <= 1e-4 and np.abs(kR - want_sweep[2]).max() <= 1e-4  # (300 points: cond(H) ~ 1e6)
+        assert np.array_equal(costs, results[0]["sweep"][0]) and np.array_equal(kt, results[0]["sweep"][1])  # identical on every rank
+        lkt, lkR, decisions, final_cost, nbad = res["lm"]
+        assert decisions == want_lm[2]["decisions"] and nbad == want_lm[2]["num_bad_keypoints"]
+        assert np.abs(lkt - want_lm[0]).max() <= 1e-4 and abs(final_cost - want_lm[2]["final_cost"]) <= 1e-5 * want_lm[2]["final_cost"]
+    if len({res["device"] for res in results}) == world:
+        assert all(res["persistent_sweeps"] == 1 for res in results)  # a GPU per rank: the sweep ran as one launch on each
+    else:
+        assert all(res["persistent_sweeps"] == 0 for res in results)

@@ -362,3 +362,11 @@ def test_oracle_matches_reference_pyramid(orc, O, synth):
             assert np.array_equal(cur, im)
             assert np.array_equal(synth.image_gradient(cur).reshape(g.shape), g)
             assert np.array_equal(np.asarray(orc.image_gradient(cur)).reshape(g.shape), g)
+
+
+def test_shapes_image_restatement_matches_opencv(synth):
+    """synth.shapes_image (the reference's synthetic scene, generate_synthetic_data.cpp:11-125) against the image OpenCV's own
+    cv::fillPoly drew from the same vertices (tests/golden/shapes.npz, written by tests/golden/make_golden.py through cv2)."""
+    z = golden("shapes.npz")
+    assert np.array_equal(synth.shapes_image(480, 640), z["image"])
+    assert set(np.unique(z["image"])) == {0, 255} and 60000 < int((z["image"] == 255).sum()) < 70000
