@@ -413,6 +413,7 @@ def check_parity(arm, O, api):
         c, H, g = arm.evaluate(level, p.knots_t, p.knots_R, True)     # collective when sharded
         c2 = arm.evaluate(level, p.knots_t, p.knots_R, False)[0]
         got.append((c, H, g, c2))
+    sweep_sharded = arm.sweep() if world > 1 else None   # collective: the timed call itself, checked against the unsharded sweep below
     if rank != 0:
         return None
     orc = O.OracleLib()
@@ -439,6 +440,11 @@ def check_parity(arm, O, api):
         assert rec["first_lm_step_rel"] <= DELTA_GATE, ("first-LM-step parity", rec)
         out["levels"].append(rec)
     if single is not None:
+        top = arm.n_levels - 1
+        cs, kts, kRs = single.gn_sweep(top, 0, p.k, p.t0, p.dt, p.knots_t, p.knots_R, p.huber_a, 1e4, chain=True)
+        out["sharded_sweep_vs_unsharded"] = {"costs_rel_max": float(np.abs(sweep_sharded[0] - cs).max() / np.abs(cs).max()),
+                                             "knots_abs_max": float(max(np.abs(sweep_sharded[1] - kts).max(), np.abs(sweep_sharded[2] - kRs).max()))}
+        assert out["sharded_sweep_vs_unsharded"]["costs_rel_max"] <= 1e-5 and out["sharded_sweep_vs_unsharded"]["knots_abs_max"] <= 1e-5, out
         single.close()
     out["cost_rel_max"] = max(r["cost_rel"] for r in out["levels"])
     out["first_lm_step_rel_max"] = max(r["first_lm_step_rel"] for r in out["levels"])

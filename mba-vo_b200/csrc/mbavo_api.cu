@@ -138,6 +138,7 @@ struct mbavo_ctx
     // point sharding (mbavo_shard_*): this rank's mailbox, the mapped mailboxes of all ranks, exchange counters
     Mailbox *mailbox = nullptr;
     bool mailbox_fresh = false;             // zeroed by mbavo_shard_export and not yet consumed by a connect
+    unsigned char device_uuid[16] = {};     // of this context's GPU (peers on the same GPU are recognised by it)
     ShardParams shard{};                    // world <= 1: not sharded
     bool peer_is_ipc[kMaxShards] = {};      // opened with cudaIpcOpenMemHandle (to be closed)
     unsigned long long shard_seq = 0, aux_seq = 0;
@@ -581,7 +582,8 @@ namespace
             ctx->launches += 1;
             CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, (pl.with_h || (sweep && sweep->pose_with_j)) ? 1 : 0, ctx->samples,
                                         ctx->mid, ctx->seg_end, s, sweep ? sweep->gn.state : nullptr, sweep ? sweep->knots_from : 0,
-                                        sweep && !sweep->first, buf_select, ctx->samples_stride, kMidDoubles * kMaxFrames,
+                                        sweep && !sweep->first && ctx->use_pdl && !ctx->shard_shares_device, buf_select, ctx->samples_stride,
+                                        kMidDoubles * kMaxFrames,
                                         kMaxSegments * kMaxFrames));
         }
         ctx->launches += 1;
@@ -590,7 +592,10 @@ namespace
         if (ctx->timing)
             CUDA_TRY(cudaEventRecord(ctx->ev0, s));
         // event timing brackets the tracking kernel alone, so it is then launched fully serialised
-        CUDA_TRY(launch_track_kernel(pl.K, pl.NK, pl.with_h, pl.big, prm, pl.grid, pl.smem, s, nullptr, ctx->use_pdl && !ctx->timing));
+        // (ranks that time-slice one GPU run fully serialised: with programmatic dependent launches a sweep whose passes wait for
+        // a peer PROCESS on the same device was observed to read the candidate's records early — tests only; one GPU per rank otherwise)
+        CUDA_TRY(launch_track_kernel(pl.K, pl.NK, pl.with_h, pl.big, prm, pl.grid, pl.smem, s, nullptr,
+                                     ctx->use_pdl && !ctx->timing && !ctx->shard_shares_device));
         if (ctx->timing)
             CUDA_TRY(cudaEventRecord(ctx->ev1, s));
         return MBAVO_OK;
@@ -2085,6 +2090,11 @@ extern "C"
             CUDA_TRY(cudaMalloc(&ctx->mailbox, sizeof(Mailbox)));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         CUDA_TRY(cudaMemset(ctx->mailbox, 0, sizeof(Mailbox)));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+        static_assert(sizeof(prop.uuid) == 16, "device UUID");
+        CUDA_TRY(cudaMemcpy(ctx->mailbox->owner_uuid, &prop.uuid, 16, cudaMemcpyHostToDevice));
+        std::memcpy(ctx->device_uuid, &prop.uuid, 16);
         CUDA_TRY(cudaDeviceSynchronize());
         ctx->mailbox_fresh = true;
         return MBAVO_OK;
@@ -2132,8 +2142,6 @@ extern "C"
                 // same process: plain peer access (a no-op on the same device)
                 cudaPointerAttributes at{};
                 CUDA_TRY(cudaPointerGetAttributes(&at, mailbox_ptrs[r]));
-                if (at.device == ctx->device)
-                    ctx->shard_shares_device = true;
                 if (at.device != ctx->device)
                 {
                     cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
@@ -2151,11 +2159,19 @@ extern "C"
                 CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
                 sh.peer[r] = static_cast<Mailbox *>(p);
                 ctx->peer_is_ipc[r] = true;
-                cudaPointerAttributes at{};
-                if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.device == ctx->device)
-                    ctx->shard_shares_device = true; // another PROCESS on this GPU: its grids time-slice with ours
-                cudaGetLastError();
+
             }
+        }
+        // a peer on THIS GPU (another context of this process, or another process time-slicing the device)?  Its mailbox says
+        // which GPU it lives on.  Such ranks cannot all keep a whole-GPU persistent grid resident, so their sweeps run pass by pass.
+        for (int r = 0; r < world; ++r)
+        {
+            if (r == rank)
+                continue;
+            unsigned char peer_uuid[16];
+            CUDA_TRY(cudaMemcpy(peer_uuid, sh.peer[r]->owner_uuid, 16, cudaMemcpyDeviceToHost));
+            if (std::memcmp(peer_uuid, ctx->device_uuid, 16) == 0)
+                ctx->shard_shares_device = true;
         }
         ctx->shard = sh;
         ctx->shard_seq = ctx->aux_seq = 0; // the sequence numbers restart with the connection (mailbox zeroed by the export)

@@ -80,17 +80,23 @@ namespace mbavo
     // ---- point sharding over the GPUs of one node: one-shot all-reduce through peer-mapped mailboxes ---------------
     // Every rank owns one Mailbox in its device memory; all ranks map all mailboxes (CUDA IPC across processes, plain peer
     // access inside a process) and WRITE their contribution into every rank's mailbox over NVLink: the last block of the
-    // tracking kernel stores its packed vector into slot[parity][my_rank] of every peer, publishes the sequence number
-    // with a system-scope release, spins on the W flags of its OWN mailbox and sums the W slots in rank order (identical,
-    // deterministic result on every rank).  Two parities suffice: a rank can only be one evaluation ahead of a peer.
+    // tracking kernel stores its packed vector into slot[parity][my_rank] of every peer as self-validating words, polls the
+    // W slots of its OWN mailbox until every word carries the tag of this exchange and sums them in rank order (identical,
+    // deterministic result on every rank).  Two parities suffice: a rank can only be one evaluation ahead of a peer (it
+    // completes exchange k + 1 only after the peer has sent its k + 1 vector, i.e. after the peer finished reading k).
     constexpr int kMaxShards = 8;
     constexpr int kMailVec = (6 * kMaxKnotWindow + 1) * (6 * kMaxKnotWindow + 2) / 2; // packed_len(kMaxKnotWindow)
+    // The packed vector travels as self-validating words (like TrackParams::host_out, and like NCCL's LL protocol): every
+    // double is two 8-byte words (tag | low half) (tag | high half), tag = publish_tag(sequence number of the exchange), written
+    // with one 16-byte store per element and polled by the receiver word by word — no system-scope fence between data and a
+    // flag, no flag round trip: one NVLink traversal.  The small-vector exchanges of the outlier / keyframe statistics keep the
+    // fence + flag form (they run once per accepted LM step).
     struct Mailbox
     {
-        unsigned long long flag[2][kMaxShards];     // sequence number of the vector in slot[parity][source rank]
-        unsigned long long aux_flag[2][kMaxShards]; // same for the small-vector exchange of the outlier statistics
+        unsigned long long owner_uuid[2];           // UUID of the GPU the mailbox lives on (written at export, read by the peers at connect)
+        unsigned long long aux_flag[2][kMaxShards]; // sequence number of the small vector in aux[parity][source rank]
         double aux[2][kMaxShards][8];
-        double slot[2][kMaxShards][kMailVec];
+        ulonglong2 slot[2][kMaxShards][kMailVec];   // [parity][source rank][element] -> (tag | lo32, tag | hi32)
     };
     struct ShardParams
     {
@@ -139,6 +145,16 @@ namespace mbavo
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
         return t;
+    }
+    __device__ __forceinline__ void st_sys_v2(ulonglong2 *p, unsigned long long a, unsigned long long b)
+    {
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    }
+    __device__ __forceinline__ ulonglong2 ld_sys_v2(const ulonglong2 *p)
+    {
+        ulonglong2 v;
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+        return v;
     }
     // spin until *flag == seq; gives up after ~4 s (a peer that never arrives must not hang the GPU)
     __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long seq)

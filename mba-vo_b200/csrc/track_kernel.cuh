@@ -1108,37 +1108,46 @@ namespace mbavo
             }
             __syncthreads();
             MBAVO_STAMP(9);
-            __shared__ int shard_ok_s;
             const ShardParams &sh = prm.shard;
             if (sh.world > 1)
             {
-                // one-shot all-reduce over NVLink: push this rank's vector into every rank's mailbox, publish, wait for the
-                // W vectors in the own mailbox, sum them in rank order
+                // one-shot all-reduce over NVLink: every element goes into the slot [parity][my rank] of EVERY rank's mailbox as one
+                // 16-byte store of two self-validating words; then the same thread polls the W copies of its element in its own
+                // mailbox and sums them in rank order (identical bits on every rank).  No fence, no flag: one NVLink traversal.
                 const int par = (int)(sh.seq & 1ull);
-                for (int r = 0; r < sh.world; ++r)
+                const unsigned long long tagv = publish_tag(sh.seq), tag = tagv << 32;
+                for (int e = threadIdx.x; e < E; e += blockDim.x)
                 {
-                    double *dst = sh.peer[r]->slot[par][sh.rank];
-                    for (int e = threadIdx.x; e < E; e += blockDim.x)
-                        st_sys(dst + e, fin_s[e]);
+                    const unsigned long long b = (unsigned long long)__double_as_longlong(fin_s[e]);
+                    const unsigned long long w0 = tag | (b & 0xffffffffull), w1 = tag | (b >> 32);
+                    for (int r = 0; r < sh.world; ++r)
+                        st_sys_v2(&sh.peer[r]->slot[par][sh.rank][e], w0, w1);
                 }
-                if (threadIdx.x == 0)
-                    shard_ok_s = 1;
-                __threadfence_system();
-                __syncthreads();
-                if (threadIdx.x < sh.world)
-                {
-                    st_release_sys(&sh.peer[threadIdx.x]->flag[par][sh.rank], sh.seq);
-                    if (!wait_flag(&sh.peer[sh.rank]->flag[par][threadIdx.x], sh.seq))
-                        shard_ok_s = 0;
-                }
-                __syncthreads();
                 const Mailbox *mine = sh.peer[sh.rank];
                 for (int e = threadIdx.x; e < E; e += blockDim.x)
                 {
                     double s = 0.0;
-                    for (int r = 0; r < sh.world; ++r)
-                        s += ld_sys(&mine->slot[par][r][e]);
-                    fin_s[e] = shard_ok_s ? s : __longlong_as_double(0x7ff8000000000000ll); // NaN: a peer timed out
+                    bool ok = true;
+                    for (int r = 0; r < sh.world && ok; ++r)
+                    {
+                        ulonglong2 w = ld_sys_v2(&mine->slot[par][r][e]);
+                        if ((w.x >> 32) != tagv || (w.y >> 32) != tagv)
+                        {
+                            const unsigned long long t0 = global_timer_ns();
+                            do
+                            {
+                                __nanosleep(20);
+                                w = ld_sys_v2(&mine->slot[par][r][e]);
+                                if (global_timer_ns() - t0 > 4000000000ull) // a peer that never arrives must not hang the GPU
+                                {
+                                    ok = false;
+                                    break;
+                                }
+                            } while ((w.x >> 32) != tagv || (w.y >> 32) != tagv);
+                        }
+                        s += __longlong_as_double((long long)((w.x & 0xffffffffull) | (w.y << 32)));
+                    }
+                    fin_s[e] = ok ? s : __longlong_as_double(0x7ff8000000000000ll); // NaN: a peer timed out
                 }
                 __syncthreads();
             }
