@@ -431,6 +431,16 @@ typedef struct mbavo_debug_out
 } mbavo_debug_out;
 int mbavo_debug_dump(mbavo_ctx *ctx, int level, const mbavo_spline *spline, double huber_a, mbavo_debug_out *out);
 
+/* ---- experiment: TMA-staged cost pass (profiles/r2_tma_variant.md) --------------------------------------------------------
+ * The cost-only evaluation of `level` through the variant of the cost pass that stages, per host-map point, a box_w x box_h tile
+ * of the 8-bit keyframe in shared memory with cp.async.bulk.tensor.2d (TMA, double-buffered on mbarriers) and takes the bilinear
+ * taps from the tile (global fallback outside it) — the mechanism BASELINE's north star names, kept next to the product kernel
+ * (which gathers packed texels through L1) so that the two can be measured against each other.  Same result as the cost-only
+ * branch of mbavo_evaluate.  kernel_ms: CUDA-event time of the kernel; tile_fraction: share of the valid samples served from
+ * the tiles.  box_w a multiple of 16 (<= 256), box_w * box_h a multiple of 128, image width a multiple of 16. */
+int mbavo_debug_cost_tma(mbavo_ctx *ctx, int level, const mbavo_spline *spline, double huber_a, int box_w, int box_h,
+                         double *total_cost, float *kernel_ms, double *tile_fraction);
+
 /* ---- introspection for benchmarks ---------------------------------------------------------------------------- */
 
 /* Number of kernels this library has launched on behalf of ctx since creation */

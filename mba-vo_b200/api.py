@@ -19,7 +19,7 @@ SOLVER_SVD_JACOBI, SOLVER_LDLT = 0, 1
 EXPORTED_SYMBOLS = [
     "mbavo_last_error", "mbavo_version", "mbavo_create", "mbavo_destroy", "mbavo_set_stream", "mbavo_set_frame_times",
     "mbavo_set_level", "mbavo_set_keyframe_pyramid", "mbavo_set_live_pyramid", "mbavo_set_level_points", "mbavo_set_points_pyramid",
-    "mbavo_set_frame", "mbavo_debug_dump",
+    "mbavo_set_frame", "mbavo_debug_dump", "mbavo_debug_cost_tma",
     "mbavo_set_live_images", "mbavo_set_outliers", "mbavo_set_num_bad", "mbavo_evaluate", "mbavo_patch_costs",
     "mbavo_detect_outliers", "mbavo_packed_len", "mbavo_evaluate_async", "mbavo_unpack", "mbavo_trust_region_step",
     "mbavo_spline_plus", "mbavo_gn_iteration", "mbavo_gn_sweep", "mbavo_lm_default_options", "mbavo_optimize_level", "mbavo_kernel_launches",
@@ -313,6 +313,14 @@ class Context:
         d = 6 * out.knot_window
         return dict(poses_tq=poses, blend_weights=wts, theta=theta, segment_start_knot=seg, patch_centres=centres, residuals=r,
                     jacobians=J[: F * P * S * d].reshape(F, P, S, d).copy(), kmin=out.kmin, knot_window=out.knot_window, cost=out.cost)
+
+    def cost_tma(self, level: int, k: int, t0: float, dt: float, knots_t, knots_R, huber_a: float, box_w: int, box_h: int):
+        """mbavo_debug_cost_tma -> (cost, kernel_ms, fraction of samples served from the TMA tiles)."""
+        sp, kt, kR, n = self._spline(k, t0, dt, knots_t, knots_R)
+        cost, ms, frac = C.c_double(0), C.c_float(0), C.c_double(0)
+        self._check(self.lib.mbavo_debug_cost_tma(self._h, C.c_int(level), C.byref(sp), C.c_double(huber_a), C.c_int(box_w), C.c_int(box_h),
+                                                  C.byref(cost), C.byref(ms), C.byref(frac)))
+        return cost.value, ms.value, frac.value
 
     def packed_len(self, knot_window: int) -> int:
         return int(self.lib.mbavo_packed_len(C.c_int(knot_window)))

@@ -7,6 +7,8 @@
 #include "../../include/mbavo.h"
 #include "mbavo_device.h"
 
+#include <cuda.h>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -21,6 +23,9 @@ namespace mbavo
                                    double *mid, int *seg_end, cudaStream_t stream, GnState *gn, int knots_from, bool dependent,
                                    int buf_select, int samples_stride, int mid_stride, int seg_end_stride, double *dbg = nullptr);
     cudaError_t launch_track_debug_kernel(int K, int NK, const TrackParams &prm, dim3 grid, size_t smem, cudaStream_t stream);
+    size_t track_cost_tma_smem_bytes(int K, int N, int S, int TP, int box_w, int box_h);
+    cudaError_t launch_track_cost_tma(int K, const TrackParams &prm, const void *tmap, int box_w, int box_h, int grid, size_t smem,
+                                      double *cost_out, unsigned long long *counters, cudaStream_t stream);
     cudaError_t launch_track_kernel(int K, int NK, bool with_j, bool big, const TrackParams &prm, dim3 grid, size_t smem,
                                     cudaStream_t stream, int *query_occupancy, bool dependent);
     size_t track_kernel_smem_bytes(int K, int NK, bool with_j, bool big, int N, int S, int TP);
@@ -1804,6 +1809,89 @@ extern "C"
             CUDA_TRY(cudaMemcpy(out->residuals, d_r, sizeof(float) * n_pix, cudaMemcpyDeviceToHost));
         if (out->jacobians)
             CUDA_TRY(cudaMemcpy(out->jacobians, d_J, sizeof(float) * n_pix * 6 * pl.NK, cudaMemcpyDeviceToHost));
+        return MBAVO_OK;
+    }
+
+    // EXPERIMENT: one cost-only evaluation through the TMA-staged variant of the cost pass (csrc/track_cost_tma.cu) — per point a
+    // box_w x box_h tile of the 8-bit keyframe fetched by cp.async.bulk.tensor.2d into shared memory, taps from the tile, global
+    // fallback outside it.  Same arithmetic and result as mbavo_evaluate's cost-only branch; returns the kernel time (CUDA
+    // events) and the fraction of samples served from the tiles so that it can be judged against the product kernel.
+    int mbavo_debug_cost_tma(mbavo_ctx *ctx, int level, const mbavo_spline *sp, double huber_a, int box_w, int box_h, double *total_cost,
+                             float *kernel_ms, double *tile_fraction)
+    {
+        if (!ctx || !total_cost)
+            return fail(MBAVO_EINVAL, "null argument");
+        DeviceGuard guard(ctx->device);
+        EvalPlan pl;
+        int rc = plan_evaluation(ctx, level, sp, false, pl);
+        if (rc != MBAVO_OK)
+            return rc;
+        LevelStore &L = ctx->levels[level];
+        if (ctx->shard.world > 1 || pl.F != 1 || pl.S != 8 || pl.TP != 4 || !L.dev.ref_quad)
+            return fail(MBAVO_ECAPACITY, "the TMA variant is built for one frame, 8-pixel patterns, texel levels, unsharded contexts");
+        if (box_w < 16 || box_w > 256 || box_w % 16 || box_h < 2 || box_h > 256 || (box_w * box_h) % 128 || L.dev.W % 16 ||
+            ((uintptr_t)L.dev.ref_I & 15))
+            return fail(MBAVO_EINVAL, "box must be 16k x h with 128 | box bytes, image width a multiple of 16, image 16-byte aligned");
+        const size_t smem = track_cost_tma_smem_bytes(pl.K, pl.N, pl.S, pl.TP, box_w, box_h);
+        if (smem > 220 * 1024)
+            return fail(MBAVO_ECAPACITY, "box %d x %d needs %zu B of shared memory per block", box_w, box_h, smem);
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess)
+            return fail(MBAVO_ECUDA, "cuTensorMapEncodeTiled is not available");
+        alignas(64) CUtensorMap map;
+        const cuuint64_t gdim[2] = {(cuuint64_t)L.dev.W, (cuuint64_t)L.dev.H}, gstride[1] = {(cuuint64_t)L.dev.W};
+        const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
+        const CUresult cr = ((encode_fn)fn)(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<unsigned char *>(L.dev.ref_I), gdim, gstride, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS)
+            return fail(MBAVO_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+        cudaStream_t s = ctx->stream;
+        rc = join_uploads(ctx);
+        if (rc != MBAVO_OK)
+            return rc;
+        double *d_cost = nullptr;
+        CUDA_TRY(cudaMalloc(&d_cost, sizeof(double) + 2 * sizeof(unsigned long long)));
+        unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(d_cost + 1);
+        CUDA_TRY(cudaMemsetAsync(d_cost, 0, sizeof(double) + 2 * sizeof(unsigned long long), s));
+        CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N, 0, ctx->samples, ctx->mid, ctx->seg_end, s, nullptr, 0, false, kBufA, ctx->samples_stride,
+                                    kMidDoubles * kMaxFrames, kMaxSegments * kMaxFrames));
+        TrackParams prm;
+        const long long nres = (long long)(pl.P - L.num_bad) * pl.F * pl.S;
+        fill_track_params(ctx, level, pl, ctx->packed_dev, false, 1.0 / (double)nres, huber_a, nullptr, prm);
+        int per_sm = (int)((220 * 1024) / smem);
+        per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+        int grid = (pl.batches_per_frame + 7) / 8;
+        grid = grid < ctx->num_sms * per_sm ? grid : ctx->num_sms * per_sm;
+        CUDA_TRY(cudaEventRecord(ctx->ev0, s));
+        cudaError_t e = launch_track_cost_tma(pl.K, prm, &map, box_w, box_h, grid, smem, d_cost, d_cnt, s);
+        if (e != cudaSuccess)
+        {
+            cudaFree(d_cost);
+            return fail(MBAVO_ECUDA, "TMA cost kernel: %s", cudaGetErrorString(e));
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev1, s));
+        ctx->launches += 2;
+        struct
+        {
+            double cost;
+            unsigned long long cnt[2];
+        } h;
+        e = cudaMemcpyAsync(&h, d_cost, sizeof h, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(s);
+        cudaFree(d_cost);
+        if (e != cudaSuccess)
+            return fail(MBAVO_ECUDA, "TMA cost kernel failed: %s", cudaGetErrorString(e));
+        *total_cost = h.cost;
+        if (kernel_ms)
+            cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1);
+        if (tile_fraction)
+            *tile_fraction = (h.cnt[0] + h.cnt[1]) ? (double)h.cnt[0] / (double)(h.cnt[0] + h.cnt[1]) : 0.0;
         return MBAVO_OK;
     }
 

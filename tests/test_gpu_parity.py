@@ -159,6 +159,29 @@ def test_reference_shapes_scene(pkg, api, O, orc, synth):
     check_parity(O, gpu_eval(pkg, api, prob, 1), orc.evaluate(prob, 1))
 
 
+def test_tma_staged_cost_pass_variant(pkg, api, O, orc, synth):
+    """mbavo_debug_cost_tma — the cost pass with TMA-staged 8-bit keyframe tiles (cp.async.bulk.tensor.2d + mbarriers,
+    csrc/track_cost_tma.cu; measured against the product pass in profiles/r2_tma_variant.md): the oracle's cost whatever the box,
+    because samples outside a point's tile fall back to the global gather."""
+    for name, level in (("tiny", 0), ("tiny", 1), ("C1", 0)):
+        prob = synth.make_config(name)
+        want = orc.evaluate(prob, level, with_hessian=False)[0]
+        with pkg.Context(api.limits_for(prob)) as ctx:
+            api.upload_problem(ctx, prob)
+            a = (level, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a)
+            product = ctx.evaluate(*a, False)[0]
+            fractions = []
+            for box in ((16, 8), (32, 16), (64, 32)):
+                for _ in range(2):  # the second call re-uses the mbarriers' phases from a fresh launch
+                    c, ms, frac = ctx.cost_tma(*a, *box)
+                assert abs(c - want) <= COST_TOL * want and abs(c - product) <= 1e-6 * product, (name, box, c, product)
+                assert ms > 0
+                fractions.append(frac)
+            assert fractions[0] < fractions[-1] and fractions[-1] > 0.99, fractions  # small boxes really exercise the fallback
+            with pytest.raises(pkg.MbavoError):
+                ctx.cost_tma(*a, 24, 16)  # box width must be a multiple of 16
+
+
 def test_keyframe_texels_and_direct_gather(pkg, api, O, orc, synth, monkeypatch):
     """mbavo_set_level packs the keyframe into fp16 texels when every gradient value survives the fp16 round trip (always
     for Gradient.h's central differences); the kernels then read bit-identical values through fewer, wider loads.  A
