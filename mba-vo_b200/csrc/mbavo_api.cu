@@ -36,6 +36,7 @@ namespace mbavo
                                    int *inexact, cudaStream_t stream);
     cudaError_t launch_pyr_down_kernel(const unsigned char *src, int Ws, unsigned char *dst, int Hd, int Wd, cudaStream_t stream);
     cudaError_t launch_select_kernels(const SelectParams &prm, int total_cells, cudaStream_t stream);
+    cudaError_t launch_pyr_step_kernel(PyrStepParams &p, cudaStream_t stream);
     cudaError_t launch_pack_image_kernel(const unsigned char *I, int H, int W, uint4 *pair, unsigned int *quad, float *grad,
                                          cudaStream_t stream);
 } // namespace mbavo
@@ -88,6 +89,8 @@ namespace
         bool has_key = false, has_live = false, has_pts = false;
         // always owned
         int2 *pattern = nullptr;
+        int pattern_shadow[2 * 128] = {}; // host copy of what `pattern` holds (mbavo_set_frame / set_points: skip unchanged uploads)
+        int pattern_shadow_n = 0;
         unsigned char *flags = nullptr;
         double *patch_cost = nullptr;
         int num_bad = 0;
@@ -1017,6 +1020,7 @@ extern "C"
             texels_pending = true; // the verdict is read after the one synchronisation at the end
         }
         CUDA_TRY(cudaMemcpyAsync(L.pattern, d->pattern_xy, sizeof(int2) * d->patch_size, cudaMemcpyDefault, s));
+        L.pattern_shadow_n = 0;
         if (!d->ext_outlier_flags)
         {
             CUDA_TRY(cudaMemsetAsync(L.flags, 0, ctx->lim.max_num_keypoints, s)); // blur_aware_direct_tracker.cpp:600-601
@@ -1225,7 +1229,8 @@ extern "C"
     // enqueue the uploads of one level's points on the context's stream (no synchronisation)
     // s: stream of the copies; s_flags: stream of the outlier-flag memset.  They differ in mbavo_set_frame: a memset is a KERNEL, and
     // a kernel on the copy stream could not start while a persistent sweep kernel that waits for this very upload holds every SM.
-    static int enqueue_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d, cudaStream_t s, cudaStream_t s_flags = nullptr)
+    static int enqueue_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d, cudaStream_t s, cudaStream_t s_flags = nullptr,
+                                    bool clear_flags = true)
     {
         if (!s_flags)
             s_flags = s;
@@ -1280,8 +1285,20 @@ extern "C"
             L.dev.xy_stride = d->keypoint_xy_stride, L.dev.xy_offset = d->keypoint_xy_offset;
             L.dev.z = d->keypoint_z;
         }
-        CUDA_TRY(cudaMemcpyAsync(L.pattern, d->pattern_xy, sizeof(int2) * d->patch_size, cudaMemcpyDefault, s));
-        CUDA_TRY(cudaMemsetAsync(L.flags, 0, P, s_flags));
+        // the pattern is a few dozen bytes that rarely change: a host-side shadow of what the device holds saves the copy
+        if (d->mem != MBAVO_MEM_HOST || L.pattern_shadow_n != d->patch_size ||
+            std::memcmp(L.pattern_shadow, d->pattern_xy, sizeof(int2) * d->patch_size) != 0)
+        {
+            CUDA_TRY(cudaMemcpyAsync(L.pattern, d->pattern_xy, sizeof(int2) * d->patch_size, cudaMemcpyDefault, s));
+            L.pattern_shadow_n = 0;
+            if (d->mem == MBAVO_MEM_HOST && d->patch_size <= 128)
+            {
+                std::memcpy(L.pattern_shadow, d->pattern_xy, sizeof(int2) * d->patch_size);
+                L.pattern_shadow_n = d->patch_size;
+            }
+        }
+        if (clear_flags)
+            CUDA_TRY(cudaMemsetAsync(L.flags, 0, P, s_flags));
         L.num_bad = 0;
         L.dev.fx = d->fx, L.dev.fy = d->fy, L.dev.cx = d->cx, L.dev.cy = d->cy;
         L.dev.inv_fx = 1.0 / d->fx, L.dev.inv_fy = 1.0 / d->fy;
@@ -1380,7 +1397,7 @@ extern "C"
         *ctx->ready_src = ++ctx->upload_epoch;
         for (int l = n_levels - 1; l >= 0 && rc == MBAVO_OK; --l)
         {
-            rc = enqueue_level_points(ctx, l, points + l, ctx->copy_stream, s); // copies on the copy stream, flag memset on the context's
+            rc = enqueue_level_points(ctx, l, points + l, ctx->copy_stream, s, false); // (the flags are cleared by the pyramid steps below)
             if (rc == MBAVO_OK)
             {
                 cudaError_t e = cudaMemcpyAsync(ctx->ready_dev + l, ctx->ready_src, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->copy_stream);
@@ -1401,10 +1418,42 @@ extern "C"
             if (e != cudaSuccess)
                 rc = fail(MBAVO_ECUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));
         }
-        if (rc == MBAVO_OK && ref_I0)
-            rc = enqueue_keyframe_pyramid(ctx, n_levels, mem, ref_I0, H0, W0, s, 2);
-        if (rc == MBAVO_OK && cur_I0)
-            rc = enqueue_live_pyramid(ctx, n_levels, mem, cur_I0, n_frames, s, 2);
+        // one launch per level: texels of the keyframe's level l, level l + 1 of the keyframe and of the live images, flags of level l
+        for (int l = 0; l < n_levels && rc == MBAVO_OK; ++l)
+        {
+            LevelStore &L = ctx->levels[l];
+            PyrStepParams ps{};
+            int nj = 0;
+            if (ref_I0)
+            {
+                PyrJob &j = ps.job[nj++];
+                j.kind = 0, j.src = L.pyr_ref, j.Hs = L.dev.H, j.Ws = L.dev.W;
+                j.pair = ctx->use_texels ? L.tex_pair : nullptr, j.quad = ctx->use_texels ? L.tex_quad : nullptr;
+                j.grad = ctx->use_texels ? nullptr : reinterpret_cast<float2 *>(L.pyr_grad);
+                if (l + 1 < n_levels)
+                {
+                    PyrJob &d = ps.job[nj++];
+                    LevelStore &C = ctx->levels[l + 1];
+                    d.kind = 1, d.src = L.pyr_ref, d.Hs = L.dev.H, d.Ws = L.dev.W, d.dst = C.pyr_ref, d.Hd = C.dev.H, d.Wd = C.dev.W;
+                }
+            }
+            if (cur_I0 && l + 1 < n_levels)
+                for (int f = 0; f < n_frames; ++f)
+                {
+                    PyrJob &d = ps.job[nj++];
+                    LevelStore &C = ctx->levels[l + 1];
+                    d.kind = 1, d.src = L.pyr_cur[f], d.Hs = L.dev.H, d.Ws = L.dev.W, d.dst = C.pyr_cur[f], d.Hd = C.dev.H, d.Wd = C.dev.W;
+                }
+            {
+                PyrJob &z = ps.job[nj++];
+                z.kind = 2, z.dst = L.flags, z.Wd = ctx->lim.max_num_keypoints; // tracker.cpp:600-601
+            }
+            ps.n_jobs = nj;
+            cudaError_t e = launch_pyr_step_kernel(ps, s);
+            if (e != cudaSuccess)
+                rc = fail(MBAVO_ECUDA, "pyramid step: %s", cudaGetErrorString(e));
+            ctx->launches += 1;
+        }
         if (rc == MBAVO_OK && (flags & MBAVO_UPLOAD_ASYNC))
         {
             ctx->join_pending = true; // joined lazily: by the first entry point that needs the points on the context's stream
@@ -1508,6 +1557,7 @@ extern "C"
         {
             LevelStore &L = ctx->levels[l];
             CUDA_TRY(cudaMemcpyAsync(L.pattern, sel->pattern_xy, sizeof(int2) * sel->patch_size, cudaMemcpyHostToDevice, s));
+            L.pattern_shadow_n = 0;
             CUDA_TRY(cudaMemsetAsync(L.flags, 0, cap, s));
         }
         CUDA_TRY(cudaStreamSynchronize(s));

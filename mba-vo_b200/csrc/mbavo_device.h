@@ -299,6 +299,29 @@ namespace mbavo
         unsigned long long *pass_times;
     };
 
+    // ---- one pyramid step of mbavo_set_frame in ONE launch (track_common.cu) ----------------------------------------------------
+    // Everything that reads the level-l images of a new frame: gradients + texels of the keyframe's level l (pack), the 2x2-box
+    // level l + 1 of the keyframe and of every live image (down), and the reset of the level's outlier flags (zero) — jobs that
+    // are independent of each other, so they share a launch (the host enqueues n_levels kernels instead of ~5 per level).
+    struct PyrJob
+    {
+        int kind;                  // 0: pack, 1: down, 2: zero
+        int block_begin;           // first block of the job in the launch (256 threads per block, one thread per output pixel / byte)
+        const unsigned char *src;  // pack: the level image; down: the finer image
+        int Hs, Ws;                // its size
+        unsigned char *dst;        // down: the coarser image (Hd x Wd); zero: the bytes to clear
+        int Hd, Wd;                // down: size of dst; zero: Wd = number of bytes
+        uint4 *pair;               // pack outputs (each nullable, see launch_pack_image_kernel)
+        unsigned int *quad;
+        float2 *grad;
+    };
+    constexpr int kMaxPyrJobs = 3 + kMaxFrames;
+    struct PyrStepParams
+    {
+        PyrJob job[kMaxPyrJobs];
+        int n_jobs;
+    };
+
     // ---- semi-dense point selection (select_kernel.cu) -------------------------------------------------------------------
     constexpr int kSelectMaxLevels = 8; // MBAVO_MAX_LEVELS of include/mbavo.h
     struct SelectLevel

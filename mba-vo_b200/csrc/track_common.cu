@@ -90,7 +90,69 @@ namespace mbavo
                 pair[i00] = t;
             }
         }
+        // one pyramid step of a new frame (PyrStepParams): the block finds its job, then runs the body of pack_image_kernel /
+        // pyr_down_kernel / a byte clear on its 256 outputs
+        __global__ void __launch_bounds__(256) pyr_step_kernel(const __grid_constant__ PyrStepParams p)
+        {
+            int j = 0;
+            while (j + 1 < p.n_jobs && (int)blockIdx.x >= p.job[j + 1].block_begin)
+                ++j;
+            const PyrJob &job = p.job[j];
+            const int i = ((int)blockIdx.x - job.block_begin) * 256 + (int)threadIdx.x;
+            if (job.kind == 2)
+            {
+                if (i < job.Wd)
+                    job.dst[i] = 0;
+            }
+            else if (job.kind == 1)
+            {
+                if (i < job.Hd * job.Wd)
+                {
+                    const int x = i % job.Wd, y = i / job.Wd;
+                    const unsigned char *q = job.src + (size_t)2 * y * job.Ws + 2 * x;
+                    job.dst[i] = (unsigned char)(((unsigned int)q[0] + q[1] + q[job.Ws] + q[job.Ws + 1]) >> 2);
+                }
+            }
+            else if (i < job.Hs * job.Ws)
+            {
+                const int H = job.Hs, W = job.Ws, x = i % W, y = i / W;
+                const unsigned char *I = job.src;
+                const int x1 = min(x + 1, W - 1), y1 = min(y + 1, H - 1);
+                const unsigned int b00 = I[i], b01 = I[y * W + x1], b10 = I[y1 * W + x], b11 = I[y1 * W + x1];
+                const float2 g0 = central_gradient(I, H, W, x, y), g1 = central_gradient(I, H, W, x1, y);
+                if (job.grad)
+                    job.grad[i] = g0;
+                if (job.pair)
+                {
+                    job.quad[i] = b00 | (b01 << 8) | (b10 << 16) | (b11 << 24);
+                    uint4 t;
+                    t.x = (unsigned int)__half_as_ushort(__float2half_rn(g0.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(g0.y)) << 16);
+                    t.y = (unsigned int)__half_as_ushort(__float2half_rn(g1.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(g1.y)) << 16);
+                    t.z = (unsigned int)__half_as_ushort(__float2half_rn((float)b00)) |
+                          ((unsigned int)__half_as_ushort(__float2half_rn((float)b01)) << 16);
+                    t.w = 0u;
+                    job.pair[i] = t;
+                }
+            }
+        }
     } // namespace
+
+    // jobs[].block_begin is filled here; returns cudaErrorInvalidValue for an empty step
+    cudaError_t launch_pyr_step_kernel(PyrStepParams &p, cudaStream_t stream)
+    {
+        int blocks = 0;
+        for (int j = 0; j < p.n_jobs; ++j)
+        {
+            PyrJob &job = p.job[j];
+            const long long n = job.kind == 0 ? (long long)job.Hs * job.Ws : (job.kind == 1 ? (long long)job.Hd * job.Wd : (long long)job.Wd);
+            job.block_begin = blocks;
+            blocks += (int)((n + 255) / 256);
+        }
+        if (blocks == 0)
+            return cudaErrorInvalidValue;
+        pyr_step_kernel<<<blocks, 256, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
 
     cudaError_t launch_pyr_down_kernel(const unsigned char *src, int Ws, unsigned char *dst, int Hd, int Wd, cudaStream_t stream)
     {
@@ -157,7 +219,7 @@ namespace mbavo
         main_bytes += 8 + (with_j ? (size_t)kWarpsPerBlock * MT * 4 * 32 * 8 : 0); // fp64 tile accumulators
         size_t red_bytes = (size_t)(kWarpsPerBlock > (kThreads / E + 1) ? kWarpsPerBlock : kThreads / E + 1) * E * 8;
         // the device-resident Gauss-Newton step of the last block: packed vector + dense window system + 4 vectors
-        const size_t solve_bytes = with_j ? ((size_t)((E + 1) & ~1) + 72 * NK * NK + 18 * NK + 8) * 8 : 0;
+        const size_t solve_bytes = with_j ? ((size_t)((E + 1) & ~1) + 108 * NK * NK + 18 * NK + 16) * 8 : 0; // + the unit-lower factor of ldlt_solve_rows
         size_t need = main_bytes > red_bytes ? main_bytes : red_bytes;
         need = need > solve_bytes ? need : solve_bytes;
         return need + 16;

@@ -445,6 +445,66 @@ namespace mbavo
             __syncwarp();
         }
 
+        // Compact shared-memory LDL^T solve of the damped window system for 12 < D <= 32, one warp, lane = row: a runtime loop over
+        // the pivots (code that stays in the instruction cache, unlike the fully unrolled register form, whose 40 KB of straight-line
+        // code executed once per level costs more in fetches than it saves in arithmetic).  A (D x D, the damped H) keeps its columns
+        // unscaled — lane i reads A(k, j) of the rows above its own while updating its row — and the unit-lower factor goes to Lm.
+        // On return y holds H^-1 g; same pivot test as the host's fast path.
+        template <int D>
+        __device__ __noinline__ void ldlt_solve_rows(double *__restrict__ A, const double *__restrict__ g, double *__restrict__ Lm,
+                                                     double *__restrict__ y, bool *ok_out)
+        {
+            const int lane = threadIdx.x & 31;
+            const int i = lane < D ? lane : D - 1; // lanes >= D shadow the last row without storing
+            const bool mine = lane < D;
+            bool ok = true;
+            double dmax = 0.0, idiag = 0.0;
+            for (int j = 0; j < D; ++j)
+            {
+                const double d = A[j * D + j];
+                dmax = d > dmax ? d : dmax;
+                if (!(d > 1e-9 * dmax))
+                    ok = false;
+                const double id = rcp_newton(d);
+                if (i == j)
+                    idiag = id;
+                if (i > j)
+                {
+                    const double l = A[i * D + j] * id; // L(i, j)
+                    if (mine)
+                        Lm[i * D + j] = l;
+#pragma unroll 4
+                    for (int k = j + 1; k <= i; ++k) // A(i, k) -= L(i, j) d_j L(k, j) = l * A(k, j)
+                    {
+                        const double v = A[i * D + k] - l * A[k * D + j];
+                        if (mine)
+                            A[i * D + k] = v;
+                    }
+                }
+                __syncwarp();
+            }
+            // forward L z = g, scale by 1 / d, backward L^T x = z: the running value of row i lives in a register, finished
+            // entries travel by shuffle
+            double yi = g[i];
+            for (int k = 0; k < D; ++k)
+            {
+                const double yk = __shfl_sync(0xffffffffu, yi, k);
+                if (i > k)
+                    yi -= Lm[i * D + k] * yk;
+            }
+            yi *= idiag;
+            for (int k = D - 1; k >= 0; --k)
+            {
+                const double xk = __shfl_sync(0xffffffffu, yi, k);
+                if (i < k)
+                    yi -= Lm[k * D + i] * xk;
+            }
+            if (mine)
+                y[lane] = yi;
+            *ok_out = ok;
+            __syncwarp();
+        }
+
         template <int NK>
         __device__ void gn_solve_step(const double *__restrict__ v, const GnParams &gp, double *__restrict__ A, double *__restrict__ w,
                                       unsigned long long *ts = nullptr)
@@ -476,12 +536,21 @@ namespace mbavo
 #ifdef MBAVO_SMEM_SOLVE
             constexpr int kRegSolveMaxD = 0;
 #else
-            constexpr int kRegSolveMaxD = 24; // windows of up to 4 knots: 2 D registers per lane for the row; the shared-memory form
-                                              // below takes 10.5 us for D = 18 (12 steps x 3 warp barriers + runtime-index updates)
+            constexpr int kRegSolveMaxD = 24; // windows of 3 and 4 knots take the lane-per-row shared-memory form (ldlt_solve_rows); the
+                                              // right-looking form below takes 10.5 us for D = 18 (3 warp barriers + runtime-index
+                                              // updates per pivot), the fully unrolled register form 6 us (instruction fetch)
 #endif
-            if constexpr (D <= kRegSolveMaxD)
+#ifndef MBAVO_SOLVE_ROWS
+#define MBAVO_SOLVE_ROWS 0 // 1: windows of 3 and 4 knots take ldlt_solve_rows (measured slower: 9.5 vs 6.0 us for D = 18)
+#endif
+            if constexpr (D <= (MBAVO_SOLVE_ROWS ? 12 : kRegSolveMaxD))
             {
                 ldlt_solve_regs<D>(Hd, g, A, y, &ok);
+            }
+            else if constexpr (D <= kRegSolveMaxD)
+            {
+                // A holds a copy of the damped H (Hd stays intact for the model decrease); the factor goes behind the three vectors
+                ldlt_solve_rows<D>(A, g, w + 3 * D + 2, y, &ok);
             }
             else
             {
@@ -713,6 +782,243 @@ namespace mbavo
         // PERSIST = false: the body of track_kernel (one launch per pass).  PERSIST = true: one pass of sweep_kernel — all
         // blocks stay resident, the pass starts when SweepCtl::done reaches pa.target and its last block releases done =
         // target + 1.  Returns false when the sweep was aborted.
+        // What the LAST block of a pass does once every block has announced its partials: the fixed-order sum, the exchange with the
+        // other ranks, the solve / candidate / pose records (Hessian pass) or record / commit (cost pass), the publication to the
+        // host and — inside a persistent sweep — the release of the pass.  Kept out of line so that this cold, fp64-heavy code does
+        // not compete for registers with the sample loops of track_pass.
+#ifndef MBAVO_FINISH_NOINLINE
+#define MBAVO_FINISH_NOINLINE 0 // measured: out of line, the sweep kernel loses 40 us per C3 sweep (ptxas then schedules the sample loops differently)
+#endif
+#if MBAVO_FINISH_NOINLINE
+#define MBAVO_FINISH_ATTR __noinline__
+#else
+#define MBAVO_FINISH_ATTR __forceinline__
+#endif
+        template <int K, int NK, bool WITH_J, int WARPS, bool PERSIST>
+        __device__ MBAVO_FINISH_ATTR bool pass_finish(const TrackParams &prm, unsigned char *smem_raw, const PersistArgs pa)
+        {
+            using G = RowGeom<NK, WITH_J>;
+            constexpr int kWarpsPerBlock = WARPS, kThreads = kWarpsPerBlock * 32;
+            constexpr int E = G::E;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            (void)lane;
+            double *red_s = reinterpret_cast<double *>(smem_raw);
+            const int num_blocks = gridDim.x * gridDim.y;
+            const double inv_num_residuals = prm.inv_num_residuals;
+            MBAVO_STAMP(8);
+            // last block: sum the partials of all blocks in a fixed order.  GRP adjacent lanes share one element: lane `part`
+            // sums the blocks b = part, part + GRP, ... (32 loads in flight), the GRP partial sums are combined by a fixed
+            // xor-shuffle tree.  Deterministic: the order depends only on the grid size.
+            __threadfence();
+            constexpr int GRP = E >= kThreads ? 1 : (kThreads / E >= 32 ? 32 : (kThreads / E >= 16 ? 16 : (kThreads / E >= 8 ? 8 : (kThreads / E >= 4 ? 4 : (kThreads / E >= 2 ? 2 : 1)))));
+            double *fin_s = red_s; // this rank's vector, scaled by 1 / num_residuals (global when sharded)
+            for (int e0 = 0; e0 < E; e0 += kThreads / GRP)
+            {
+                const int e = e0 + threadIdx.x / GRP, part = threadIdx.x % GRP;
+                double s = 0.0;
+                if (e < E)
+                {
+                    const double *src = prm.block_partials + e;
+                    int b = part;
+                    for (; b + 31 * GRP < num_blocks; b += 32 * GRP)
+                    {
+                        double v[32];
+#pragma unroll
+                        for (int u = 0; u < 32; ++u)
+                            v[u] = __ldcg(src + (size_t)(b + u * GRP) * E);
+#pragma unroll
+                        for (int u = 0; u < 32; ++u)
+                            s += v[u];
+                    }
+                    for (; b + 7 * GRP < num_blocks; b += 8 * GRP)
+                    {
+                        double v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            v[u] = __ldcg(src + (size_t)(b + u * GRP) * E);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            s += v[u];
+                    }
+                    for (; b < num_blocks; b += GRP)
+                        s += __ldcg(src + (size_t)b * E);
+                }
+#pragma unroll
+                for (int o = 1; o < GRP; o <<= 1)
+                    s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (e < E && part == 0)
+                    fin_s[e] = s * inv_num_residuals;
+            }
+            __syncthreads();
+            MBAVO_STAMP(9);
+            const ShardParams &sh = prm.shard;
+            if (sh.world > 1)
+            {
+                // one-shot all-reduce over NVLink: every element goes into the slot [parity][my rank] of EVERY rank's mailbox as one
+                // 16-byte store of two self-validating words; then the same thread polls the W copies of its element in its own
+                // mailbox and sums them in rank order (identical bits on every rank).  No fence, no flag: one NVLink traversal.
+                const int par = (int)(sh.seq & 1ull);
+                const unsigned long long tagv = publish_tag(sh.seq), tag = tagv << 32;
+                for (int e = threadIdx.x; e < E; e += blockDim.x)
+                {
+                    const unsigned long long b = (unsigned long long)__double_as_longlong(fin_s[e]);
+                    const unsigned long long w0 = tag | (b & 0xffffffffull), w1 = tag | (b >> 32);
+                    for (int r = 0; r < sh.world; ++r)
+                        st_sys_v2(&sh.peer[r]->slot[par][sh.rank][e], w0, w1);
+                }
+                const Mailbox *mine = sh.peer[sh.rank];
+                for (int e = threadIdx.x; e < E; e += blockDim.x)
+                {
+                    double s = 0.0;
+                    bool ok = true;
+                    for (int r = 0; r < sh.world && ok; ++r)
+                    {
+                        ulonglong2 w = ld_sys_v2(&mine->slot[par][r][e]);
+                        if ((w.x >> 32) != tagv || (w.y >> 32) != tagv)
+                        {
+                            const unsigned long long t0 = global_timer_ns();
+                            do
+                            {
+                                __nanosleep(20);
+                                w = ld_sys_v2(&mine->slot[par][r][e]);
+                                if (global_timer_ns() - t0 > 4000000000ull) // a peer that never arrives must not hang the GPU
+                                {
+                                    ok = false;
+                                    break;
+                                }
+                            } while ((w.x >> 32) != tagv || (w.y >> 32) != tagv);
+                        }
+                        s += __longlong_as_double((long long)((w.x & 0xffffffffull) | (w.y << 32)));
+                    }
+                    fin_s[e] = ok ? s : __longlong_as_double(0x7ff8000000000000ll); // NaN: a peer timed out
+                }
+                __syncthreads();
+            }
+            const GnParams &gp = prm.gn;
+            if (gp.state)
+            {
+                // device-resident Gauss-Newton sweep: solve / record on the spot, publish the level's scalars
+                GnState *st = gp.state;
+                if constexpr (WITH_J)
+                {
+                    double *A = fin_s + ((E + 1) & ~1), *w = A + 72 * NK * NK;
+                    if (warp == 0)
+                        gn_solve_step<NK>(fin_s, gp, A, w, prm.phase_times ? prm.phase_times + 16 * (prm.trace_row & 63) : nullptr);
+                    if constexpr (PERSIST)
+                    {
+                        // the candidate's sample records (what the stand-alone pose kernel computes between the two passes of a
+                        // level when every pass is its own launch), with Jacobians: the next level may stand on them
+                        __syncthreads();
+                        // into the record buffer the sweep does NOT stand on (a sweep that never commits keeps cur_buf = 0)
+                        const int cb = 1 - *reinterpret_cast<volatile int *>(&st->cur_buf);
+                        // pose part only: all the cost pass needs.  The Jacobian part, which only a finer level standing on the
+                        // committed candidate reads, is computed by the service block WHILE the cost pass runs (below).
+                        pose_records_block<K>(pa.stage, st->cand_t, st->cand_R, gridDim.x > 1 ? 0 : 1,
+                                              const_cast<float *>(prm.samples) + (size_t)cb * prm.samples_stride,
+                                              const_cast<double *>(prm.mid) + (size_t)cb * prm.mid_stride,
+                                              const_cast<int *>(prm.seg_end) + (size_t)cb * prm.seg_end_stride);
+                        MBAVO_STAMP(15);
+                    }
+                }
+                else if (threadIdx.x < 32)
+                {
+                    // record the candidate's cost, commit the candidate when it lowered the cost (the finer level then starts from
+                    // it), publish the level's scalars (and, after the last level, the knots) to the host.  One warp: the knots are
+                    // copied / published a lane per element.  Inside a persistent sweep the pass is released to the other blocks
+                    // BEFORE anything is stored to host memory (a fence behind PCIe stores costs microseconds).
+                    const int lane32 = threadIdx.x;
+                    const double cc = fin_s[0], cost0 = st->cost, model0 = st->model;
+                    const int status0 = st->status;
+                    const bool commit = gp.chain && status0 == 0 && cc < cost0;
+                    const int nk7 = 7 * gp.n_knots; // cur_t (3n) and cur_R (4n) are adjacent in GnState
+                    double *cur = st->cur_t;
+                    const double *cand = st->cand_t;
+                    static_assert(offsetof(GnState, cur_R) == offsetof(GnState, cur_t) + sizeof(double) * 3 * 16 &&
+                                      offsetof(GnState, cand_R) == offsetof(GnState, cand_t) + sizeof(double) * 3 * 16,
+                                  "GnState: rotations follow translations");
+                    double keep[4]; // the knots the sweep stands on after this level, 4 elements per lane (7 * 16 <= 128)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                    {
+                        const int e = lane32 + 32 * u;
+                        const int idx = e < 3 * gp.n_knots ? e : 48 + (e - 3 * gp.n_knots); // element of the padded [t(48) | R(64)] layout
+                        keep[u] = 0.0;
+                        if (e < nk7)
+                        {
+                            keep[u] = commit ? cand[idx] : cur[idx];
+                            if (commit)
+                                cur[idx] = keep[u];
+                        }
+                    }
+                    if (lane32 == 0)
+                    {
+                        st->cand_cost = cc;
+                        if (commit)
+                            st->cur_buf ^= 1; // the candidate's sample records are now those of the knots the sweep stands on
+                    }
+                    if constexpr (PERSIST)
+                    {
+                        __threadfence();
+                        __syncwarp();
+                        if (lane32 == 0)
+                        {
+                            *prm.counter = 0u;
+                            *pa.t_release = global_timer_ns();
+                            st_release_gpu(&pa.ctl->done, pa.target + 1u);
+                        }
+                    }
+                    if (prm.host_out)
+                    {
+                        double2 *o = prm.host_out + 4 * gp.slot;
+                        if (lane32 == 0)
+                        {
+                            publish_host(o + 0, cost0, prm.seq), publish_host(o + 1, cc, prm.seq);
+                            publish_host(o + 2, (double)status0, prm.seq), publish_host(o + 3, model0, prm.seq);
+                        }
+                        if (gp.last)
+                        {
+                            double2 *ok = prm.host_out + 4 * MBAVO_MAX_LEVELS_DEV;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (lane32 + 32 * u < nk7)
+                                    publish_host(ok + lane32 + 32 * u, keep[u], prm.seq);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if constexpr (!PERSIST) // (a sweep publishes scalars and knots, never the packed vector)
+            {
+                for (int e = threadIdx.x; e < E; e += blockDim.x)
+                {
+                    const double s = fin_s[e];
+                    prm.packed_out[e] = s;
+                    if (prm.host_out && !gp.state)
+                        publish_host(prm.host_out + e, s, prm.seq);
+                }
+            }
+            MBAVO_STAMP(10);
+            if constexpr (PERSIST && WITH_J)
+            {
+                // everything this block wrote (records, sweep state, counter) becomes visible to the blocks that acquire `done`
+                // (the cost pass released the sweep above, before its host stores)
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0)
+                {
+                    *prm.counter = 0u;
+                    *pa.t_release = global_timer_ns();
+                    st_release_gpu(&pa.ctl->done, pa.target + 1u);
+                }
+            }
+            else if constexpr (!PERSIST)
+            {
+                if (threadIdx.x == 0)
+                    *prm.counter = 0u; // re-arm for the next launch
+            }
+            return true;
+        }
+
         // DBG: also writes the per-stage intermediates of mbavo_debug_dump (patch centres, raw residuals, raw 1 x 6NK rows)
         template <int K, int NK, bool WITH_J, bool PACKED, int WARPS, bool PERSIST, bool DBG = false>
         __device__ __forceinline__ bool track_pass(const TrackParams &prm, unsigned char *smem_raw, const PersistArgs pa)
@@ -1062,218 +1368,7 @@ namespace mbavo
             __syncthreads();
             if (ticket_s != (unsigned int)(num_blocks - 1))
                 return true;
-            MBAVO_STAMP(8);
-            // last block: sum the partials of all blocks in a fixed order.  GRP adjacent lanes share one element: lane `part`
-            // sums the blocks b = part, part + GRP, ... (32 loads in flight), the GRP partial sums are combined by a fixed
-            // xor-shuffle tree.  Deterministic: the order depends only on the grid size.
-            __threadfence();
-            constexpr int GRP = E >= kThreads ? 1 : (kThreads / E >= 32 ? 32 : (kThreads / E >= 16 ? 16 : (kThreads / E >= 8 ? 8 : (kThreads / E >= 4 ? 4 : (kThreads / E >= 2 ? 2 : 1)))));
-            double *fin_s = red_s; // this rank's vector, scaled by 1 / num_residuals (global when sharded)
-            for (int e0 = 0; e0 < E; e0 += kThreads / GRP)
-            {
-                const int e = e0 + threadIdx.x / GRP, part = threadIdx.x % GRP;
-                double s = 0.0;
-                if (e < E)
-                {
-                    const double *src = prm.block_partials + e;
-                    int b = part;
-                    for (; b + 31 * GRP < num_blocks; b += 32 * GRP)
-                    {
-                        double v[32];
-#pragma unroll
-                        for (int u = 0; u < 32; ++u)
-                            v[u] = __ldcg(src + (size_t)(b + u * GRP) * E);
-#pragma unroll
-                        for (int u = 0; u < 32; ++u)
-                            s += v[u];
-                    }
-                    for (; b + 7 * GRP < num_blocks; b += 8 * GRP)
-                    {
-                        double v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            v[u] = __ldcg(src + (size_t)(b + u * GRP) * E);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            s += v[u];
-                    }
-                    for (; b < num_blocks; b += GRP)
-                        s += __ldcg(src + (size_t)b * E);
-                }
-#pragma unroll
-                for (int o = 1; o < GRP; o <<= 1)
-                    s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (e < E && part == 0)
-                    fin_s[e] = s * inv_num_residuals;
-            }
-            __syncthreads();
-            MBAVO_STAMP(9);
-            const ShardParams &sh = prm.shard;
-            if (sh.world > 1)
-            {
-                // one-shot all-reduce over NVLink: every element goes into the slot [parity][my rank] of EVERY rank's mailbox as one
-                // 16-byte store of two self-validating words; then the same thread polls the W copies of its element in its own
-                // mailbox and sums them in rank order (identical bits on every rank).  No fence, no flag: one NVLink traversal.
-                const int par = (int)(sh.seq & 1ull);
-                const unsigned long long tagv = publish_tag(sh.seq), tag = tagv << 32;
-                for (int e = threadIdx.x; e < E; e += blockDim.x)
-                {
-                    const unsigned long long b = (unsigned long long)__double_as_longlong(fin_s[e]);
-                    const unsigned long long w0 = tag | (b & 0xffffffffull), w1 = tag | (b >> 32);
-                    for (int r = 0; r < sh.world; ++r)
-                        st_sys_v2(&sh.peer[r]->slot[par][sh.rank][e], w0, w1);
-                }
-                const Mailbox *mine = sh.peer[sh.rank];
-                for (int e = threadIdx.x; e < E; e += blockDim.x)
-                {
-                    double s = 0.0;
-                    bool ok = true;
-                    for (int r = 0; r < sh.world && ok; ++r)
-                    {
-                        ulonglong2 w = ld_sys_v2(&mine->slot[par][r][e]);
-                        if ((w.x >> 32) != tagv || (w.y >> 32) != tagv)
-                        {
-                            const unsigned long long t0 = global_timer_ns();
-                            do
-                            {
-                                __nanosleep(20);
-                                w = ld_sys_v2(&mine->slot[par][r][e]);
-                                if (global_timer_ns() - t0 > 4000000000ull) // a peer that never arrives must not hang the GPU
-                                {
-                                    ok = false;
-                                    break;
-                                }
-                            } while ((w.x >> 32) != tagv || (w.y >> 32) != tagv);
-                        }
-                        s += __longlong_as_double((long long)((w.x & 0xffffffffull) | (w.y << 32)));
-                    }
-                    fin_s[e] = ok ? s : __longlong_as_double(0x7ff8000000000000ll); // NaN: a peer timed out
-                }
-                __syncthreads();
-            }
-            const GnParams &gp = prm.gn;
-            if (gp.state)
-            {
-                // device-resident Gauss-Newton sweep: solve / record on the spot, publish the level's scalars
-                GnState *st = gp.state;
-                if constexpr (WITH_J)
-                {
-                    double *A = fin_s + ((E + 1) & ~1), *w = A + 72 * NK * NK;
-                    if (warp == 0)
-                        gn_solve_step<NK>(fin_s, gp, A, w, prm.phase_times ? prm.phase_times + 16 * (prm.trace_row & 63) : nullptr);
-                    if constexpr (PERSIST)
-                    {
-                        // the candidate's sample records (what the stand-alone pose kernel computes between the two passes of a
-                        // level when every pass is its own launch), with Jacobians: the next level may stand on them
-                        __syncthreads();
-                        // into the record buffer the sweep does NOT stand on (a sweep that never commits keeps cur_buf = 0)
-                        const int cb = 1 - *reinterpret_cast<volatile int *>(&st->cur_buf);
-                        // pose part only: all the cost pass needs.  The Jacobian part, which only a finer level standing on the
-                        // committed candidate reads, is computed by the service block WHILE the cost pass runs (below).
-                        pose_records_block<K>(pa.stage, st->cand_t, st->cand_R, gridDim.x > 1 ? 0 : 1,
-                                              const_cast<float *>(prm.samples) + (size_t)cb * prm.samples_stride,
-                                              const_cast<double *>(prm.mid) + (size_t)cb * prm.mid_stride,
-                                              const_cast<int *>(prm.seg_end) + (size_t)cb * prm.seg_end_stride);
-                        MBAVO_STAMP(15);
-                    }
-                }
-                else if (threadIdx.x < 32)
-                {
-                    // record the candidate's cost, commit the candidate when it lowered the cost (the finer level then starts from
-                    // it), publish the level's scalars (and, after the last level, the knots) to the host.  One warp: the knots are
-                    // copied / published a lane per element.  Inside a persistent sweep the pass is released to the other blocks
-                    // BEFORE anything is stored to host memory (a fence behind PCIe stores costs microseconds).
-                    const int lane32 = threadIdx.x;
-                    const double cc = fin_s[0], cost0 = st->cost, model0 = st->model;
-                    const int status0 = st->status;
-                    const bool commit = gp.chain && status0 == 0 && cc < cost0;
-                    const int nk7 = 7 * gp.n_knots; // cur_t (3n) and cur_R (4n) are adjacent in GnState
-                    double *cur = st->cur_t;
-                    const double *cand = st->cand_t;
-                    static_assert(offsetof(GnState, cur_R) == offsetof(GnState, cur_t) + sizeof(double) * 3 * 16 &&
-                                      offsetof(GnState, cand_R) == offsetof(GnState, cand_t) + sizeof(double) * 3 * 16,
-                                  "GnState: rotations follow translations");
-                    double keep[4]; // the knots the sweep stands on after this level, 4 elements per lane (7 * 16 <= 128)
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                    {
-                        const int e = lane32 + 32 * u;
-                        const int idx = e < 3 * gp.n_knots ? e : 48 + (e - 3 * gp.n_knots); // element of the padded [t(48) | R(64)] layout
-                        keep[u] = 0.0;
-                        if (e < nk7)
-                        {
-                            keep[u] = commit ? cand[idx] : cur[idx];
-                            if (commit)
-                                cur[idx] = keep[u];
-                        }
-                    }
-                    if (lane32 == 0)
-                    {
-                        st->cand_cost = cc;
-                        if (commit)
-                            st->cur_buf ^= 1; // the candidate's sample records are now those of the knots the sweep stands on
-                    }
-                    if constexpr (PERSIST)
-                    {
-                        __threadfence();
-                        __syncwarp();
-                        if (lane32 == 0)
-                        {
-                            *prm.counter = 0u;
-                            *pa.t_release = global_timer_ns();
-                            st_release_gpu(&pa.ctl->done, pa.target + 1u);
-                        }
-                    }
-                    if (prm.host_out)
-                    {
-                        double2 *o = prm.host_out + 4 * gp.slot;
-                        if (lane32 == 0)
-                        {
-                            publish_host(o + 0, cost0, prm.seq), publish_host(o + 1, cc, prm.seq);
-                            publish_host(o + 2, (double)status0, prm.seq), publish_host(o + 3, model0, prm.seq);
-                        }
-                        if (gp.last)
-                        {
-                            double2 *ok = prm.host_out + 4 * MBAVO_MAX_LEVELS_DEV;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (lane32 + 32 * u < nk7)
-                                    publish_host(ok + lane32 + 32 * u, keep[u], prm.seq);
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-            if constexpr (!PERSIST) // (a sweep publishes scalars and knots, never the packed vector)
-            {
-                for (int e = threadIdx.x; e < E; e += blockDim.x)
-                {
-                    const double s = fin_s[e];
-                    prm.packed_out[e] = s;
-                    if (prm.host_out && !gp.state)
-                        publish_host(prm.host_out + e, s, prm.seq);
-                }
-            }
-            MBAVO_STAMP(10);
-            if constexpr (PERSIST && WITH_J)
-            {
-                // everything this block wrote (records, sweep state, counter) becomes visible to the blocks that acquire `done`
-                // (the cost pass released the sweep above, before its host stores)
-                __threadfence();
-                __syncthreads();
-                if (threadIdx.x == 0)
-                {
-                    *prm.counter = 0u;
-                    *pa.t_release = global_timer_ns();
-                    st_release_gpu(&pa.ctl->done, pa.target + 1u);
-                }
-            }
-            else if constexpr (!PERSIST)
-            {
-                if (threadIdx.x == 0)
-                    *prm.counter = 0u; // re-arm for the next launch
-            }
-            return true;
+            return pass_finish<K, NK, WITH_J, WARPS, PERSIST>(prm, smem_raw, pa);
         }
 
         template <int K, int NK, bool WITH_J, bool PACKED, bool BIG>
