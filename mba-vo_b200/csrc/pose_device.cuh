@@ -245,6 +245,67 @@ namespace mbavo
             }
         }
 
+        // The pose alone — same expressions for the pose as spline_pose (bit-identical t, q), none of the derivative blocks and none
+        // of their local arrays: what a cost-only evaluation and the candidate of a Gauss-Newton step need.
+        __host__ __device__ inline void so3_log_only(const Q &q, double *phi)
+        {
+            const double n2 = q.x * q.x + q.y * q.y + q.z * q.z;
+            double lam;
+            if (n2 < 1e-20)
+                lam = 2. / q.w - 2. / 3. * n2 / (q.w * q.w * q.w);
+            else
+            {
+                const double n = sqrt(n2);
+                if (fabs(q.w) < 1e-10)
+                    lam = (q.w > 0 ? 1.0 : -1.0) * M_PI / n;
+                else
+                    lam = 2.0 * atan(n / q.w) / n;
+            }
+            phi[0] = lam * q.x, phi[1] = lam * q.y, phi[2] = lam * q.z;
+        }
+        __host__ __device__ inline Q so3_exp_only(const double *phi)
+        {
+            const double t2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+            double fi, fr;
+            if (t2 < 1e-20)
+            {
+                const double t4 = t2 * t2;
+                fi = 0.5 - 1. / 48. * t2 + 1. / 3840. * t4;
+                fr = 1. - 1. / 8. * t2 + 1. / 384. * t4;
+            }
+            else
+            {
+                const double t = sqrt(t2);
+                fi = sin(0.5 * t) / t;
+                fr = cos(0.5 * t);
+            }
+            return Q{fi * phi[0], fi * phi[1], fi * phi[2], fr};
+        }
+        template <int K>
+        __host__ __device__ inline void spline_pose_only(const double *kt, const double *kR, double u, double *t_out, Q &q_out, double *wt)
+        {
+            double wr[K];
+            spline_weights<K>(u, wt, wr);
+            for (int a = 0; a < 3; ++a)
+            {
+                double s = 0;
+                for (int j = 0; j < K; ++j)
+                    s += wt[j] * kt[3 * j + a];
+                t_out[a] = s;
+            }
+            Q q = Q{kR[0], kR[1], kR[2], kR[3]};
+#pragma unroll
+            for (int j = 1; j < K; ++j)
+            {
+                const Q a = Q{kR[4 * j - 4], kR[4 * j - 3], kR[4 * j - 2], kR[4 * j - 1]}, b = Q{kR[4 * j], kR[4 * j + 1], kR[4 * j + 2], kR[4 * j + 3]};
+                double phi[3];
+                so3_log_only(qmul(qconj(a), b), phi);
+                phi[0] *= wr[j], phi[1] *= wr[j], phi[2] *= wr[j];
+                q = qmul(q, so3_exp_only(phi));
+            }
+            q_out = q;
+        }
+
         __host__ __device__ __forceinline__ void rotation_matrix(const Q &q, double *R)
         {
             const double x = q.x, y = q.y, z = q.z, w = q.w;
@@ -303,7 +364,10 @@ namespace mbavo
 
             double tt[3], wt[K], Theta[K * 9];
             Q q;
-            spline_pose<K>(knots_t + 3 * idx, knots_R + 4 * idx, u, tt, q, wt, with_jacobian ? Theta : nullptr);
+            if (with_jacobian)
+                spline_pose<K>(knots_t + 3 * idx, knots_R + 4 * idx, u, tt, q, wt, Theta);
+            else
+                spline_pose_only<K>(knots_t + 3 * idx, knots_R + 4 * idx, u, tt, q, wt);
 
             if (dbg)
             {
