@@ -619,6 +619,7 @@ def run_c2_extra(pkg, torch, dist, api, O, local_rank, stream, args):
                                 "evaluations": int(sum(s_["num_evaluations"] for s_ in summ)),
                                 "final_cost_level0": float(summ[-1]["final_cost"])}
     arm.close()
+    out["shim"] = run_shim_leg(prob)
     depth = np.full((lv0.H, lv0.W), 7.5, dtype=np.float32)
     with pkg.Context(api.limits_for(prob)) as kctx:
         for it in range(13):
@@ -640,6 +641,37 @@ def run_c2_extra(pkg, torch, dist, api, O, local_rank, stream, args):
                 rs.select_points(lv0.ref_I, len(prob.levels), 25.0, 30, 30, depth, max_points=4096)
             out["keyframe_setup"]["cpu_reference_ms"] = (time.perf_counter() - t_kf) / 5 * 1e3
     return out
+
+
+def run_shim_leg(prob):
+    """The drop-in path of INTEGRATION.md §1: the reference's own entry point evaluate_cost_hessian_gradient (same name, same
+    arguments, storages poked with raw cudaMemcpy) implemented by mba-vo_b200/host/spline_update_step.cpp on top of the C-ABI,
+    called from a C++ program (tests/cpp/dropin_main.cpp) on level 0 of this workload: wall clock per evaluation, with the
+    level re-derived on every call (default) and with the opt-in cache.  None when the program cannot be built."""
+    import subprocess
+    import tempfile
+
+    try:
+        binp = os.path.join(ROOT, "tests", "cpp", "dropin_main")
+        libdir = os.path.join(ROOT, "mba-vo_b200", "lib")
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++14", os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"), "-I/usr/local/cuda/include",
+                        "-L" + libdir, "-L/usr/local/cuda/lib64", "-lmbavo_b200", "-lcudart", "-Wl,-rpath," + libdir,
+                        "-Wl,-rpath,/usr/local/cuda/lib64", "-o", binp], check=True, capture_output=True)
+        lv = prob.levels[0]
+        flags = np.zeros(lv.P, dtype=np.uint8)
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "problem.bin")
+            with open(path, "wb") as f:
+                np.array([lv.H, lv.W, lv.P, lv.S, lv.N, prob.n_knots, prob.k, 0], dtype=np.int32).tofile(f)
+                np.array([lv.fx, lv.fy, lv.cx, lv.cy, prob.cap[0], prob.exp[0], prob.t0, prob.dt, prob.huber_a], dtype=np.float64).tofile(f)
+                for a in (lv.ref_I, lv.ref_dIxy, lv.cur_I[0], lv.xy, lv.z, lv.pattern, prob.knots_t, prob.knots_R, flags):
+                    np.ascontiguousarray(a).tofile(f)
+            r = subprocess.run([binp, path], capture_output=True, text=True, timeout=300)
+        got = json.loads(r.stdout)
+        return {"what": "evaluate_cost_hessian_gradient (reference signature) per evaluation on level 0, wall clock, C++ caller",
+                "us_per_evaluation": got["shim_us"]}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
 
 
 def main():

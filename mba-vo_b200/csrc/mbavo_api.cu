@@ -142,6 +142,7 @@ struct mbavo_ctx
     bool use_device_sweep = true;                  // MBAVO_NO_DEVICE_SWEEP=1: every evaluation returns to the host
     long long big_block_batches = 2000; // MBAVO_BIG_BLOCK_BATCHES: Hessian pass uses the big block shape from this many batches
     bool use_pdl = true;     // MBAVO_NO_PDL=1: tracking kernel fully serialised behind the pose kernel
+    bool small_level_split = true; // MBAVO_NO_SMALL_SPLIT=1: lane = pixel on every level, whatever its size
 
     // point sharding (mbavo_shard_*): this rank's mailbox, the mapped mailboxes of all ranks, exchange counters
     Mailbox *mailbox = nullptr;
@@ -439,6 +440,21 @@ namespace
             pl.PH = ctx->force_phases;
             while (pl.PH > pl.N)
                 pl.PH >>= 1;
+        }
+        else if (ctx->small_level_split && pl.S == 8)
+        {
+            // A level with fewer 4-point batches than the GPU has warp slots is pure latency: every warp walks all N samples of its
+            // one batch while most slots idle.  Such levels (coarse pyramid levels; every level of a frame sharded over many GPUs)
+            // give each warp fewer points and split the exposure samples over the lanes instead — 2 points x 8 pixels x 2
+            // phases, or 1 point x 8 pixels x 4 phases — so that the same work spreads over 2x / 4x the warps at half / a quarter
+            // of the per-warp latency.  (For levels that fill the GPU the unsplit form is faster: profiles/r1_history.md.)
+            const long long slots = (long long)ctx->num_sms * 20;
+            const long long pts = (long long)pl.P * pl.F;
+            if (pts <= slots && pl.N >= 8)
+                pl.TP = 1, pl.PH = 4;
+            else if (pts <= 2 * slots && pl.N >= 4)
+                pl.TP = 2, pl.PH = 2;
+            pl.batches_per_frame = (pl.P + pl.TP - 1) / pl.TP;
         }
         // block shape of the Hessian pass: big blocks once the batches occupy most SMs (measured cross-over ~2000 batches)
         pl.big = with_h && (long long)pl.batches_per_frame * pl.F >= ctx->big_block_batches;
@@ -809,6 +825,8 @@ extern "C"
         ctx->use_pdl = !(g && g[0] == '1');
         g = getenv("MBAVO_NO_DEVICE_SWEEP");
         ctx->use_device_sweep = !(g && g[0] == '1');
+        g = getenv("MBAVO_NO_SMALL_SPLIT");
+        ctx->small_level_split = !(g && g[0] == '1');
         g = getenv("MBAVO_NO_PERSISTENT");
         ctx->use_persistent = !(g && g[0] == '1');
         g = getenv("MBAVO_BIG_BLOCK_BATCHES");
@@ -1877,7 +1895,8 @@ extern "C"
         if (rc != MBAVO_OK)
             return rc;
         LevelStore &L = ctx->levels[level];
-        if (ctx->shard.world > 1 || pl.F != 1 || pl.S != 8 || pl.TP != 4 || !L.dev.ref_quad)
+        pl.TP = 4, pl.PH = 1, pl.batches_per_frame = (pl.P + 3) / 4; // the variant's own mapping: lane = pixel, 4 points per warp batch
+        if (ctx->shard.world > 1 || pl.F != 1 || pl.S != 8 || !L.dev.ref_quad)
             return fail(MBAVO_ECAPACITY, "the TMA variant is built for one frame, 8-pixel patterns, texel levels, unsharded contexts");
         if (box_w < 16 || box_w > 256 || box_w % 16 || box_h < 2 || box_h > 256 || (box_w * box_h) % 128 || L.dev.W % 16 ||
             ((uintptr_t)L.dev.ref_I & 15))

@@ -7,6 +7,8 @@
 
 #include <cuda_runtime_api.h>
 
+#include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -94,7 +96,55 @@ int main(int argc, char **argv)
     VO::evaluate_cost_hessian_gradient(N, 1, d_ref, d_g, P, S, K, HW, k, dbl[6], dbl[7], &seg, n, st, dbl[8], &cost_flagged, nullptr,
                                        nullptr);
 
-    std::printf("{\"cost\": %.17g, \"cost_only\": %.17g, \"cost_flagged\": %.17g, \"g\": [", cost, cost_only, cost_flagged);
+    // ---- the same call with the opt-in level cache (CudaSharedStorages::mbavo_texel_cache), and wall-clock per evaluation both ways
+    cudaMemset(st.cuda_keypoints_outlier_flags, 0, P);
+    st.num_bad_keypoints = 0;
+    auto now_us = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const int reps = 50;
+    double cost_again = 0, cost_cached = 0, cost_epoch = 0, us_plain_h, us_plain_c, us_cached_h, us_cached_c;
+    std::vector<double> Hc((size_t)dim * dim), gc(dim);
+    auto eval = [&](bool with_h, double *c, double *Hout, double *gout) {
+        VO::evaluate_cost_hessian_gradient(N, 1, d_ref, d_g, P, S, K, HW, k, dbl[6], dbl[7], &seg, n, st, dbl[8], c, with_h ? Hout : nullptr,
+                                           with_h ? gout : nullptr);
+    };
+    eval(true, &cost_again, Hc.data(), gc.data());
+    double t0 = now_us();
+    for (int i = 0; i < reps; ++i)
+        eval(true, &cost_again, Hc.data(), gc.data());
+    us_plain_h = (now_us() - t0) / reps;
+    t0 = now_us();
+    for (int i = 0; i < reps; ++i)
+        eval(false, &cost_again, nullptr, nullptr);
+    us_plain_c = (now_us() - t0) / reps;
+    st.mbavo_texel_cache = 1;
+    eval(true, &cost_cached, Hc.data(), gc.data()); // fills the cache
+    t0 = now_us();
+    for (int i = 0; i < reps; ++i)
+        eval(true, &cost_cached, Hc.data(), gc.data());
+    us_cached_h = (now_us() - t0) / reps;
+    t0 = now_us();
+    for (int i = 0; i < reps; ++i)
+        eval(false, &cost_epoch, nullptr, nullptr);
+    us_cached_c = (now_us() - t0) / reps;
+    double h_diff = 0;
+    for (int i = 0; i < dim * dim; ++i)
+        h_diff = std::max(h_diff, std::fabs(Hc[i] - Hm[i]));
+    // new keyframe content behind the same pointer: the caller bumps the epoch and the level is re-derived
+    std::vector<unsigned char> ref2(ref_I);
+    for (auto &b : ref2)
+        b = (unsigned char)(255 - b);
+    cudaMemcpy(d_ref, ref2.data(), ref2.size(), cudaMemcpyHostToDevice);
+    double cost_stale = 0;
+    eval(false, &cost_stale, nullptr, nullptr);       // still the cached texels: the old keyframe
+    ++st.mbavo_keyframe_epoch;
+    eval(false, &cost_epoch, nullptr, nullptr);       // re-derived: differs
+    cudaMemcpy(d_ref, ref_I.data(), ref_I.size(), cudaMemcpyHostToDevice);
+    st.mbavo_texel_cache = 0;
+
+    std::printf("{\"shim_us\": {\"hessian\": %.2f, \"cost\": %.2f, \"hessian_cached\": %.2f, \"cost_cached\": %.2f}, "
+                "\"cost_cached\": %.17g, \"H_cached_max_abs_diff\": %.3g, \"cost_stale\": %.17g, \"cost_new_epoch\": %.17g, ",
+                us_plain_h, us_plain_c, us_cached_h, us_cached_c, cost_cached, h_diff, cost_stale, cost_epoch);
+    std::printf("\"cost\": %.17g, \"cost_only\": %.17g, \"cost_flagged\": %.17g, \"g\": [", cost, cost_only, cost_flagged);
     for (int i = 0; i < dim; ++i)
         std::printf("%s%.17g", i ? ", " : "", g[i]);
     std::printf("], \"H\": [");

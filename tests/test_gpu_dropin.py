@@ -18,6 +18,7 @@ BIN = os.path.join(ROOT, "tests", "cpp", "dropin_main")
 
 
 def build_dropin():
+    """(also used by bench.py for its `shim` leg)"""
     libdir = os.path.join(ROOT, "mba-vo_b200", "lib")
     cmd = ["/usr/bin/g++", "-O2", "-std=c++14", os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"), "-I/usr/local/cuda/include",
            "-L" + libdir, "-L/usr/local/cuda/lib64", "-lmbavo_b200", "-lcudart", "-Wl,-rpath," + libdir,
@@ -27,8 +28,7 @@ def build_dropin():
 
 @pytest.mark.parametrize("k,n_knots", [(2, 2), (4, 4)])
 def test_reference_api_drop_in(pkg, O, orc, synth, tmp_path, k, n_knots):
-    if not os.path.exists(BIN):
-        build_dropin()
+    build_dropin()
     prob = synth.make_problem("dropin", W=192, H=144, levels=1, P0=700, N=8, n_knots=n_knots, k=k, seed=31, margin=16)
     lv = prob.levels[0]
     flags = np.zeros(lv.P, dtype=np.uint8)
@@ -60,3 +60,11 @@ def test_reference_api_drop_in(pkg, O, orc, synth, tmp_path, k, n_knots):
     assert np.abs(np.array(got["patch_costs"]) - pc[0]).max() <= 1e-4 * pc.max()
     cf = orc.evaluate(prob, 0, flags=flags, num_bad=int(flags.sum()), with_hessian=False)[0]
     assert abs(got["cost_flagged"] - cf) <= 1e-5 * cf
+    # the opt-in level cache (CudaSharedStorages::mbavo_texel_cache): same result, fewer set-ups; content that changes behind
+    # an unchanged pointer is picked up when the caller bumps mbavo_keyframe_epoch, and only then
+    assert got["cost_cached"] == got["cost"] and got["H_cached_max_abs_diff"] == 0.0
+    assert abs(got["cost_stale"] - got["cost_only"]) <= 1e-12 * got["cost"]     # old texels until the epoch moves
+    assert abs(got["cost_new_epoch"] - got["cost"]) > 1e-3 * got["cost"]        # the inverted keyframe
+    t = got["shim_us"]
+    assert t["hessian_cached"] <= t["hessian"] and t["cost_cached"] <= t["cost"], t
+    print("shim wall clock per evaluation (us):", t)
