@@ -247,12 +247,37 @@ namespace mbavo
 
         // The pose alone — same expressions for the pose as spline_pose (bit-identical t, q), none of the derivative blocks and none
         // of their local arrays: what a cost-only evaluation and the candidate of a Gauss-Newton step need.
+        // For the rotations between neighbouring control knots of a tracker (a few degrees at most) both maps are evaluated by their
+        // power series in the SQUARED norm — no sqrt, no atan, no sin / cos, one division: lam = 2 atan(x) / (x w) with x^2 = n2 / w^2 and
+        // (sin(t/2) / t, cos(t/2)) in t^2.  The truncation error is below 1e-17 relative inside the thresholds (x^2 <= 2^-8: 9 terms of
+        // the alternating series bound it by x^18 / 19 = 1e-23; t^2 <= 2^-6), i.e. at the rounding level of the closed forms that
+        // spline_pose keeps (SplineFunctor.h:155-365 via Quaternion.h:61-233); larger rotations take the closed forms here too.
+        // This chain is the latency of the candidate's pose records between the two passes of a Gauss-Newton level.
+        __host__ __device__ __forceinline__ double atan_over_x_series(double x2)
+        {
+            // atan(x) / x = 1 - x^2/3 + x^4/5 - ... (Horner in x2)
+            double p = 1.0 / 19.0;
+            p = fma(-x2, p, 1.0 / 17.0);
+            p = fma(-x2, p, 1.0 / 15.0);
+            p = fma(-x2, p, 1.0 / 13.0);
+            p = fma(-x2, p, 1.0 / 11.0);
+            p = fma(-x2, p, 1.0 / 9.0);
+            p = fma(-x2, p, 1.0 / 7.0);
+            p = fma(-x2, p, 1.0 / 5.0);
+            p = fma(-x2, p, 1.0 / 3.0);
+            return fma(-x2, p, 1.0);
+        }
         __host__ __device__ inline void so3_log_only(const Q &q, double *phi)
         {
             const double n2 = q.x * q.x + q.y * q.y + q.z * q.z;
             double lam;
             if (n2 < 1e-20)
                 lam = 2. / q.w - 2. / 3. * n2 / (q.w * q.w * q.w);
+            else if (q.w > 0.5 && n2 <= 0.00390625 * q.w * q.w)
+            {
+                const double iw = 1.0 / q.w;
+                lam = 2.0 * iw * atan_over_x_series(n2 * iw * iw);
+            }
             else
             {
                 const double n = sqrt(n2);
@@ -272,6 +297,26 @@ namespace mbavo
                 const double t4 = t2 * t2;
                 fi = 0.5 - 1. / 48. * t2 + 1. / 3840. * t4;
                 fr = 1. - 1. / 8. * t2 + 1. / 384. * t4;
+            }
+            else if (t2 <= 0.015625)
+            {
+                // h = (t/2)^2 <= 2^-8:  sin(t/2) / t = (1/2) (1 - h/6 + h^2/120 - ...),  cos(t/2) = 1 - h/2 + h^2/24 - ...
+                const double h = 0.25 * t2;
+                double s = -1.0 / 6227020800.0;                 // 13!
+                s = fma(h, s, 1.0 / 39916800.0);               // 11!
+                s = fma(h, s, -1.0 / 362880.0);                // 9!
+                s = fma(h, s, 1.0 / 5040.0);
+                s = fma(h, s, -1.0 / 120.0);
+                s = fma(h, s, 1.0 / 6.0);
+                fi = 0.5 * fma(-h, s, 1.0);
+                double c = 1.0 / 87178291200.0;                 // 14!
+                c = fma(h, c, -1.0 / 479001600.0);             // 12!
+                c = fma(h, c, 1.0 / 3628800.0);                // 10!
+                c = fma(h, c, -1.0 / 40320.0);
+                c = fma(h, c, 1.0 / 720.0);
+                c = fma(h, c, -1.0 / 24.0);
+                c = fma(h, c, 0.5);
+                fr = fma(-h, c, 1.0);
             }
             else
             {
