@@ -1824,6 +1824,7 @@ extern "C"
         CUDA_TRY(cudaMalloc(&d_centres, sizeof(double2) * n_pts));
         CUDA_TRY(cudaMalloc(&d_r, sizeof(float) * n_pix));
         CUDA_TRY(cudaMalloc(&d_J, sizeof(float) * n_pix * 6 * pl.NK));
+        CUDA_TRY(cudaMemsetAsync(d_pose, 0, sizeof(double) * n_samp * 47, s));
         CUDA_TRY(cudaMemsetAsync(d_centres, 0, sizeof(double2) * n_pts, s));
         CUDA_TRY(cudaMemsetAsync(d_r, 0, sizeof(float) * n_pix, s));
         CUDA_TRY(cudaMemsetAsync(d_J, 0, sizeof(float) * n_pix * 6 * pl.NK, s));

@@ -33,7 +33,21 @@ def run(prob, pyramid=False):
         poses = np.array([np.concatenate(synth.spline_pose(prob.k, prob.gt_knots_t, prob.gt_knots_R, prob.t0, prob.dt, t))
                           for t in (cap, cap - 0.4 * exp, cap + 0.4 * exp)])
         kf = ctx.keyframe_stats(0, poses)
-        print(prob.name, "ok", c, c2, "sweeps on device", ctx.device_sweeps(), "kf", kf, flush=True)
+        print(prob.name, "ok", c, c2, "sweeps on device", ctx.device_sweeps(), "persistent", ctx.persistent_sweeps(), "kf", kf, flush=True)
+        # round 2: the one-call frame upload (two streams, asynchronous, the persistent sweep waits for the per-level ready flags),
+        # the debug dump of the product kernels, the TMA-staged cost pass
+        if pyramid:
+            for _ in range(2):
+                ctx.set_frame(len(prob.levels), prob.levels[0].ref_I, prob.levels[0].cur_I, prob.levels, async_upload=True)
+                ctx.gn_sweep(top, 0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, 1e4, chain=True)
+            ctx.set_frame(len(prob.levels), None, prob.levels[0].cur_I, prob.levels, async_upload=False)
+            ctx.evaluate(0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, True)
+        lv = prob.levels[0]
+        if prob.k == 2 and prob.n_knots <= 3 and lv.S == 8:
+            d = ctx.debug_dump(0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, prob.F, lv.N, lv.P, lv.S)
+            print(prob.name, "debug dump ok", d["cost"], flush=True)
+            if lv.W % 16 == 0 and ctx.level_uses_texels(0) == 1:
+                print(prob.name, "tma ok", ctx.cost_tma(0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, 32, 16), flush=True)
 
 
 probs = [synth.make_config("tiny"),
@@ -45,6 +59,10 @@ probs = [synth.make_config("tiny"),
 for p in probs:
     run(p)
 run(synth.make_problem("pyr", W=162, H=122, levels=3, P0=300, N=4, n_knots=2, k=2, seed=5, margin=20), pyramid=True)
+run(synth.make_problem("pyr16", W=160, H=128, levels=3, P0=300, N=8, n_knots=3, k=2, seed=6, margin=20), pyramid=True)
+os.environ["MBAVO_NO_PERSISTENT"] = "1"
+run(probs[0])
+del os.environ["MBAVO_NO_PERSISTENT"]
 os.environ["MBAVO_NO_TEXELS"] = "1"
 run(probs[0])
 del os.environ["MBAVO_NO_TEXELS"]
