@@ -505,9 +505,74 @@ namespace mbavo
             __syncwarp();
         }
 
+        // ---- block-wide set-up and factorisation of the damped window system (persistent sweep: the whole last block is there anyway,
+        // and the one-warp forms spend 1.3 us building the system and 6 us factoring it for an 18 x 18 window) ----------------------
+        // A (D x D), Hd (D x D) = the damped H, g = y = the gradient; every thread of the block takes elements
         template <int NK>
+        __device__ __forceinline__ void gn_build_block(const double *__restrict__ v, double radius, double *__restrict__ A, double *__restrict__ w)
+        {
+            constexpr int D = 6 * NK, D1 = D + 1;
+            double *Hd = A + D * D, *g = w, *y = w + D;
+            const double damp = 1.0 / radius;
+            for (int e = threadIdx.x; e < D * D; e += blockDim.x)
+            {
+                const int r = e / D, c = e % D, ra = (r < c ? r : c) + 1, cb = (r < c ? c : r) + 1;
+                double h = v[ra * D1 - ra * (ra - 1) / 2 + (cb - ra)];
+                if (r == c)
+                    h += h * damp;
+                A[e] = h, Hd[e] = h;
+            }
+            for (int e = threadIdx.x; e < D; e += blockDim.x)
+                g[e] = v[1 + e], y[e] = v[1 + e];
+        }
+        // LDL^T with ONE THREAD PER ELEMENT of the lower triangle (D (D + 1) / 2 threads of the block, the others return at once):
+        // per pivot, column j is published to shared memory (double-buffered: one named barrier per pivot), then every element (i, k),
+        // k > j, takes its rank-1 update.  A receives L below the diagonal and d on it.  ~150 cycles per pivot, no unrolled code.
+        template <int D>
+        __device__ __noinline__ void ldlt_factor_block(double *__restrict__ A, double *__restrict__ col, int *__restrict__ ok_out)
+        {
+            constexpr int NEL = D * (D + 1) / 2, NTH = (NEL + 31) / 32 * 32;
+            const int t = threadIdx.x;
+            if (t >= NTH)
+                return;
+            int i = 0;
+            while ((i + 1) * (i + 2) / 2 <= t)
+                ++i;
+            const int k = t - i * (i + 1) / 2;
+            const bool active = t < NEL;
+            double a = active ? A[i * D + k] : 0.0;
+            double dmax = 0.0;
+            bool ok = true;
+            for (int j = 0; j < D; ++j)
+            {
+                double *buf = col + (j & 1) * (D + 2);
+                if (active && k == j)
+                    buf[i] = a; // column j, pivot included
+                asm volatile("bar.sync 1, %0;" ::"r"(NTH) : "memory");
+                const double d = buf[j];
+                dmax = d > dmax ? d : dmax;
+                if (!(d > 1e-9 * dmax))
+                    ok = false;
+                const double id = rcp_newton(d);
+                if (active && k >= j)
+                {
+                    const double l = buf[i] * id; // L(i, j)
+                    if (k > j)
+                        a -= l * buf[k];          // A(i, k) -= L(i, j) d_j L(k, j)
+                    else if (i > j)
+                        A[i * D + j] = l;
+                    else
+                        A[j * D + j] = d;
+                }
+            }
+            if (t == 0)
+                *ok_out = ok ? 1 : 0;
+        }
+
+        // PREFACTORED: gn_build_block + ldlt_factor_block have run (A holds the factor, *prefactored_ok its pivot verdict)
+        template <int NK, bool PREFACTORED = false>
         __device__ void gn_solve_step(const double *__restrict__ v, const GnParams &gp, double *__restrict__ A, double *__restrict__ w,
-                                      unsigned long long *ts = nullptr)
+                                      unsigned long long *ts = nullptr, const int *prefactored_ok = nullptr)
         {
 #ifdef MBAVO_PROFILE_PHASES
 #define MBAVO_TS(k) do { if (ts && (threadIdx.x & 31) == 0) ts[k] = global_timer_ns(); } while (0)
@@ -520,19 +585,48 @@ namespace mbavo
             double *Hd = A + D * D;                 // the damped H (kept for the model decrease); A becomes its LDL^T factor
             double *g = w, *y = w + D, *sv = w + 2 * D;
             const double damp = 1.0 / gp.radius;
-            for (int e = lane; e < D * D; e += 32)
+            if constexpr (!PREFACTORED)
             {
-                const int r = e / D, c = e % D, ra = (r < c ? r : c) + 1, cb = (r < c ? c : r) + 1;
-                double h = v[ra * D1 - ra * (ra - 1) / 2 + (cb - ra)]; // element (ra, cb) of the (D+1) x (D+1) upper triangle
-                if (r == c)
-                    h += h * damp;
-                A[e] = h, Hd[e] = h;
+                for (int e = lane; e < D * D; e += 32)
+                {
+                    const int r = e / D, c = e % D, ra = (r < c ? r : c) + 1, cb = (r < c ? c : r) + 1;
+                    double h = v[ra * D1 - ra * (ra - 1) / 2 + (cb - ra)]; // element (ra, cb) of the (D+1) x (D+1) upper triangle
+                    if (r == c)
+                        h += h * damp;
+                    A[e] = h, Hd[e] = h;
+                }
+                for (int e = lane; e < D; e += 32)
+                    g[e] = v[1 + e], y[e] = v[1 + e];
+                __syncwarp();
             }
-            for (int e = lane; e < D; e += 32)
-                g[e] = v[1 + e], y[e] = v[1 + e];
-            __syncwarp();
+            (void)damp, (void)D1;
             MBAVO_TS(11);
             bool ok = true;
+            if constexpr (PREFACTORED)
+            {
+                // forward L z = g, scale by 1 / d, backward L^T x = z with the factor in A: lane = row, finished entries by shuffle
+                ok = *prefactored_ok != 0;
+                const int i = lane < D ? lane : D - 1;
+                double yi = g[i];
+                for (int k = 0; k < D; ++k)
+                {
+                    const double yk = __shfl_sync(0xffffffffu, yi, k);
+                    if (i > k)
+                        yi -= A[i * D + k] * yk;
+                }
+                yi *= rcp_newton(A[i * D + i]);
+                for (int k = D - 1; k >= 0; --k)
+                {
+                    const double xk = __shfl_sync(0xffffffffu, yi, k);
+                    if (i < k)
+                        yi -= A[k * D + i] * xk;
+                }
+                if (lane < D)
+                    y[lane] = yi;
+                __syncwarp();
+            }
+            else
+            {
 #ifdef MBAVO_SMEM_SOLVE
             constexpr int kRegSolveMaxD = 0;
 #else
@@ -596,6 +690,7 @@ namespace mbavo
                         y[i] -= A[k * D + i] * xk;
                     __syncwarp();
                 }
+            }
             }
             MBAVO_TS(12);
             for (int e = lane; e < D; e += 32)
@@ -902,7 +997,22 @@ namespace mbavo
                 if constexpr (WITH_J)
                 {
                     double *A = fin_s + ((E + 1) & ~1), *w = A + 72 * NK * NK;
-                    if (warp == 0)
+#ifndef MBAVO_BLOCK_SOLVE
+#define MBAVO_BLOCK_SOLVE 1
+#endif
+                    if constexpr (PERSIST && MBAVO_BLOCK_SOLVE && NK >= 3 && NK <= 4)
+                    {
+                        // the whole block builds and factors the damped system; one warp finishes (substitutions, model decrease, candidate)
+                        __shared__ int factor_ok_s;
+                        gn_build_block<NK>(fin_s, gp.radius, A, w);
+                        __syncthreads();
+                        ldlt_factor_block<6 * NK>(A, w + 18 * NK + 2, &factor_ok_s);
+                        __syncthreads();
+                        if (warp == 0)
+                            gn_solve_step<NK, true>(fin_s, gp, A, w, prm.phase_times ? prm.phase_times + 16 * (prm.trace_row & 63) : nullptr,
+                                                    &factor_ok_s);
+                    }
+                    else if (warp == 0)
                         gn_solve_step<NK>(fin_s, gp, A, w, prm.phase_times ? prm.phase_times + 16 * (prm.trace_row & 63) : nullptr);
                     if constexpr (PERSIST)
                     {
@@ -1405,15 +1515,25 @@ namespace mbavo
         {
             extern __shared__ __align__(16) unsigned char smem_raw[];
             constexpr int WARPS = track_warps(true, NK, true);
+            // the frame times / segment table in shared memory: the pose records of a candidate are computed by an out-of-line
+            // function that reads them through a pointer (generic loads from the parameter space are slow and it is latency that counts)
+            __shared__ EvalStage stage_s;
+            {
+                const int *src = reinterpret_cast<const int *>(&stage);
+                int *dst = reinterpret_cast<int *>(&stage_s);
+                for (int e = threadIdx.x; e < (int)(sizeof(EvalStage) / sizeof(int)); e += blockDim.x)
+                    dst[e] = src[e];
+            }
+            __syncthreads();
             cudaGridDependencySynchronize(); // the pose kernel's records (and the sweep state it initialised)
             if (blockIdx.x == 0 && threadIdx.x == 0)
                 sp.pass_times[0] = global_timer_ns();
             for (int li = 0; li < sp.n_levels; ++li)
             {
-                const PersistArgs ph{sp.ctl, sp.base + 2u * (unsigned int)li, &stage, sp.pass_times + 1 + 2 * li};
+                const PersistArgs ph{sp.ctl, sp.base + 2u * (unsigned int)li, &stage_s, sp.pass_times + 1 + 2 * li};
                 if (!track_pass<K, NK, true, PACKED, WARPS, true>(sp.pass[2 * li], smem_raw, ph))
                     return;
-                const PersistArgs pc{sp.ctl, sp.base + 2u * (unsigned int)li + 1u, &stage, sp.pass_times + 2 + 2 * li};
+                const PersistArgs pc{sp.ctl, sp.base + 2u * (unsigned int)li + 1u, &stage_s, sp.pass_times + 2 + 2 * li};
                 if (!track_pass<K, NK, false, PACKED, WARPS, true>(sp.pass[2 * li + 1], smem_raw, pc))
                     return;
             }
