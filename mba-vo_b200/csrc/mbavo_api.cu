@@ -853,6 +853,8 @@ extern "C"
         if (!ctx)
             return MBAVO_OK;
         DeviceGuard guard(ctx->device);
+        if (ctx->copy_stream)
+            cudaStreamSynchronize(ctx->copy_stream); // an asynchronous mbavo_set_frame may still be copying into the buffers freed below
         if (ctx->stream)
             cudaStreamSynchronize(ctx->stream);
         for (auto &L : ctx->levels)
@@ -917,6 +919,11 @@ extern "C"
         if (!ctx)
             return fail(MBAVO_EINVAL, "null context");
         DeviceGuard guard(ctx->device);
+        {
+            const int rcq = quiesce(ctx); // pending uploads belong to the old stream's order
+            if (rcq != MBAVO_OK)
+                return rcq;
+        }
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
         return MBAVO_OK;
