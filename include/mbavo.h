@@ -258,7 +258,10 @@ int mbavo_gn_iteration(mbavo_ctx *ctx, int level, int spline_deg_k, double start
 /* One GN iteration (mbavo_gn_iteration) on every level from level_coarse down to level_fine — the coarse-to-fine loop of
  * optimizeTrajectory (blur_aware_direct_tracker.cpp:571-575) with a single iteration per level.  chain != 0: a level whose
  * candidate lowered the cost hands the candidate knots to the next finer level (knots_t / knots_R are updated in place);
- * chain == 0: every level starts from the given knots.  costs (may be NULL): (cost, candidate cost) per level, coarse first. */
+ * chain == 0: every level starts from the given knots.  costs (may be NULL): (cost, candidate cost) per level, coarse first.
+ * Runs device-resident: the solve, the candidate and the commit happen inside the kernels and the host waits once — as ONE
+ * persistent launch for the whole sweep where mbavo_persistent_sweeps (below) says so, else one launch per pass; normal
+ * equations that need the SVD branch, or a negative model decrease, make the call fall back to mbavo_gn_iteration per level. */
 int mbavo_gn_sweep(mbavo_ctx *ctx, int level_coarse, int level_fine, int chain, int spline_deg_k, double start_time,
                    double sample_dt, int num_ctrl_knots, double *knots_t, double *knots_R, double radius, double huber_a,
                    int solver_type, double *costs);
