@@ -463,9 +463,11 @@ long long mbavo_persistent_sweeps(const mbavo_ctx *ctx);
  * pass by one thread; they are always taken. */
 int mbavo_sweep_pass_times(mbavo_ctx *ctx, double *us_out, int capacity, int *num_passes);
 
-/* 1 if the kernels of `level` read the keyframe through the packed fp16 texels built by mbavo_set_level (every
- * gradient value exactly representable in fp16 — always the case for Gradient.h's central differences of an 8-bit
- * image), 0 if they gather ref_I / ref_dIxy directly, -1 if the level is not set.  Results are identical either way. */
+/* 1 if the kernels of `level` read the keyframe through the packed texels built by mbavo_set_level / mbavo_set_frame (16 bytes
+ * per pixel holding the 4 x 4 byte neighbourhood, from which a sample's four intensities and four gradients come as byte
+ * differences; possible when the gradient image is reproduced exactly by such differences — always the case for Gradient.h's
+ * 0.5 * central differences of an 8-bit image), 0 if they gather ref_I / ref_dIxy directly, -1 if the level is not set.
+ * Results are identical either way. */
 int mbavo_level_uses_texels(const mbavo_ctx *ctx, int level);
 
 /* Device time in milliseconds of the tracking kernel of the last mbavo_evaluate* call on `level` (CUDA events

@@ -32,12 +32,12 @@ namespace mbavo
     size_t sweep_kernel_smem_bytes(int K, int NK, int N, int S, int TP);
     cudaError_t launch_sweep_kernel(int K, int NK, const SweepParams &sp, const EvalStage &stage, int num_sms, size_t smem,
                                     cudaStream_t stream, bool dependent, int *query_occupancy);
-    cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,
+    cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, PairTexel *pair, unsigned int *quad,
                                    int *inexact, cudaStream_t stream);
     cudaError_t launch_pyr_down_kernel(const unsigned char *src, int Ws, unsigned char *dst, int Hd, int Wd, cudaStream_t stream);
     cudaError_t launch_select_kernels(const SelectParams &prm, int total_cells, cudaStream_t stream);
     cudaError_t launch_pyr_step_kernel(PyrStepParams &p, cudaStream_t stream);
-    cudaError_t launch_pack_image_kernel(const unsigned char *I, int H, int W, uint4 *pair, unsigned int *quad, float *grad,
+    cudaError_t launch_pack_image_kernel(const unsigned char *I, int H, int W, PairTexel *pair, unsigned int *quad, float *grad,
                                          cudaStream_t stream);
 } // namespace mbavo
 
@@ -77,7 +77,7 @@ namespace
         size_t cap_pix = 0, cap_pts = 0; // capacities of the owned buffers (pixels per image, points)
         int cap_frames = 0;
         // keyframe texels (LevelDev::ref_pair / ref_quad), rebuilt by every mbavo_set_level
-        uint4 *tex_pair = nullptr;
+        PairTexel *tex_pair = nullptr;
         unsigned int *tex_quad = nullptr;
         size_t cap_tex = 0;
         // device-built pyramid path (mbavo_set_keyframe_pyramid / mbavo_set_live_pyramid / mbavo_set_level_points)
@@ -1023,7 +1023,7 @@ extern "C"
         for (int f = F; f < kMaxFrames; ++f)
             L.dev.cur_I[f] = nullptr;
         // keyframe texels: built from the device copies on every call (the caller may have changed the image content
-        // behind an unchanged pointer); kept only if every gradient value survives the fp16 round trip
+        // behind an unchanged pointer); kept only if the texels reproduce every gradient value exactly (LevelDev)
         L.dev.ref_pair = nullptr, L.dev.ref_quad = nullptr;
         bool texels_pending = false;
         if (ctx->use_texels && npix < (size_t)1 << 27)
@@ -1033,7 +1033,7 @@ extern "C"
                 cudaFree(L.tex_pair);
                 cudaFree(L.tex_quad);
                 L.tex_pair = nullptr, L.tex_quad = nullptr, L.cap_tex = 0;
-                CUDA_TRY(cudaMalloc(&L.tex_pair, npix * sizeof(uint4)));
+                CUDA_TRY(cudaMalloc(&L.tex_pair, npix * sizeof(PairTexel)));
                 CUDA_TRY(cudaMalloc(&L.tex_quad, npix * sizeof(unsigned int)));
                 L.cap_tex = npix;
             }
@@ -1124,7 +1124,7 @@ extern "C"
                 cudaFree(L.tex_pair);
                 cudaFree(L.tex_quad);
                 L.tex_pair = nullptr, L.tex_quad = nullptr, L.cap_tex = 0;
-                CUDA_TRY(cudaMalloc(&L.tex_pair, npix * sizeof(uint4)));
+                CUDA_TRY(cudaMalloc(&L.tex_pair, npix * sizeof(PairTexel)));
                 CUDA_TRY(cudaMalloc(&L.tex_quad, npix * sizeof(unsigned int)));
                 L.cap_tex = npix;
             }

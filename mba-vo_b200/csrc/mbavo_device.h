@@ -49,19 +49,34 @@ namespace mbavo
         unsigned char seg_off[kMaxFrames * 64]; // host-computed segment start knot of every sample minus kmin (authoritative)
     };
 
-    // Keyframe texels, built once per mbavo_set_level by pack_kernel (track_kernel.cu) from ref_I / ref_dIxy when every
-    // gradient value is exactly representable in fp16 (always true for Gradient.h's 0.5 * central differences of an
-    // 8-bit image: multiples of 0.5 up to 127.5).  They carry bit-identical values in a gather-friendly layout:
-    //   pair texel (16 B per pixel): 8 halves  gx(x,y) gy(x,y) | gx(x+1,y) gy(x+1,y) | I(x,y) I(x+1,y) | 0 0
-    //                                — one 128-bit load per image ROW of the bilinear footprint instead of 2 + 2 loads
-    //   quad texel (4 B per pixel):  bytes     I(x,y) I(x+1,y) I(x,y+1) I(x+1,y+1)
-    //                                — the whole footprint of a cost-only sample in one 32-bit load
+    // Keyframe texels, built once per mbavo_set_level / mbavo_set_frame (make_pair_texel, track_common.cu).  They carry the
+    // values of ref_I / ref_dIxy bit for bit in a gather-friendly layout:
+    //   patch texel (16 B per pixel): the 4 x 4 BYTE neighbourhood of (x, y) — rows y-1 .. y+2, one word per row, columns
+    //                                 x-1 .. x+2 from the low byte up.  The middle 2 x 2 bytes are the intensities of the bilinear
+    //                                 footprint (x, y) (x+1, y) (x, y+1) (x+1, y+1); each of the 8 bytes next to them is used by
+    //                                 exactly one tap's gradient: 2 gx(x, y) = byte(x+1, y) - byte(x-1, y) and so on, which is
+    //                                 Gradient.h's 0.5 * central difference when the bytes are the real neighbours — and the
+    //                                 packer CHOOSES those 8 bytes so that the differences reproduce the given gradient image
+    //                                 exactly (real neighbours in the interior, a copy of the opposite byte where Gradient.h
+    //                                 writes the zero gradient of a border pixel).  A gradient image that no bytes reproduce
+    //                                 (not a whole number of half grey levels, or out of a byte's reach) makes the level fall back
+    //                                 to gathering ref_I / ref_dIxy directly.  The 4 corners are unused.
+    //                                 — the whole footprint of a Hessian-pass sample (4 intensities, 4 gradients) in ONE
+    //                                 128-bit load; the kernel converts a byte to 2^23 + b with one PRMT and takes differences
+    //                                 (MBAVO_TEXEL = 0: the round-2 row pairs, 8 halves  gx gy (x,y) | gx gy (x+1,y) | I I | 0,
+    //                                 two 128-bit loads per sample — kept for A/B runs, profiles/r2_history.md)
+    //   quad texel (4 B per pixel):   bytes     I(x,y) I(x+1,y) I(x,y+1) I(x+1,y+1)
+    //                                 — the whole footprint of a cost-only sample in one 32-bit load
     // x+1 / y+1 are clamped to the last column / row (those taps have weight 0 there).
+#ifndef MBAVO_TEXEL
+#define MBAVO_TEXEL 3 // 3: patch texel | 0: row pairs
+#endif
+    typedef uint4 PairTexel;
     struct LevelDev
     {
         const unsigned char *ref_I;
         const float2 *ref_dIxy;
-        const uint4 *ref_pair;        // nullptr: gradients not fp16-exact -> the kernels gather ref_I / ref_dIxy directly
+        const PairTexel *ref_pair;    // nullptr: gradients the texels cannot hold -> the kernels gather ref_I / ref_dIxy directly
         const unsigned int *ref_quad;
         const unsigned char *cur_I[kMaxFrames];
         int H, W;
@@ -311,7 +326,7 @@ namespace mbavo
         int Hs, Ws;                // its size
         unsigned char *dst;        // down: the coarser image (Hd x Wd); zero: the bytes to clear
         int Hd, Wd;                // down: size of dst; zero: Wd = number of bytes
-        uint4 *pair;               // pack outputs (each nullable, see launch_pack_image_kernel)
+        PairTexel *pair;           // pack outputs (each nullable, see launch_pack_image_kernel)
         unsigned int *quad;
         float2 *grad;
     };

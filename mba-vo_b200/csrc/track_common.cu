@@ -16,9 +16,60 @@ namespace mbavo
 
     namespace
     {
-        // Keyframe texels (see LevelDev).  One thread per pixel; *inexact counts gradient values that fp16 cannot hold.
+        // the 16-byte row pair of a pair texel (see LevelDev): (gx gy)(x,y) | (gx gy)(x+1,y) | I(x,y) I(x+1,y) | 0
+        __device__ __forceinline__ uint4 row_pair(float2 g0, float2 g1, unsigned int b0, unsigned int b1)
+        {
+            uint4 t;
+            t.x = (unsigned int)__half_as_ushort(__float2half_rn(g0.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(g0.y)) << 16);
+            t.y = (unsigned int)__half_as_ushort(__float2half_rn(g1.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(g1.y)) << 16);
+            t.z = (unsigned int)__half_as_ushort(__float2half_rn((float)b0)) | ((unsigned int)__half_as_ushort(__float2half_rn((float)b1)) << 16);
+            t.w = 0u;
+            return t;
+        }
+        // free byte of a patch texel: the byte whose doubled central difference against `fixed` is sign * 2 g.  false when no
+        // byte reproduces g exactly (g not a whole number of half grey levels, or out of a byte's reach)
+        __device__ __forceinline__ bool free_byte(unsigned int fixed, float g, float sign, unsigned int &byte)
+        {
+            const float v = fminf(fmaxf(rintf((float)fixed + sign * 2.0f * g), 0.f), 255.f); // NaN -> 0
+            byte = (unsigned int)v;
+            return 0.5f * sign * (v - (float)fixed) == g;
+        }
+        // The keyframe texel of pixel (x, y) from the four taps of its bilinear footprint (bytes b.., gradients g..; x+1 / y+1
+        // already clamped by the caller).  Returns false when the texel cannot hold the gradients exactly.
+        __device__ __forceinline__ bool make_pair_texel(unsigned int b00, unsigned int b01, unsigned int b10, unsigned int b11, float2 g00,
+                                                        float2 g01, float2 g10, float2 g11, PairTexel &out)
+        {
+#if MBAVO_TEXEL == 3
+            // rows y-1 .. y+2 of the 4 x 4 neighbourhood, one word per row, columns x-1 .. x+2 from the low byte up; the middle
+            // 2 x 2 are the intensities, the 8 bytes next to them are chosen so that every tap's gradient is the doubled central
+            // difference the kernel takes (real neighbours for Gradient.h's gradient image; the zero gradient of a border pixel
+            // comes out as a copy of the opposite byte); the corners are unused
+            unsigned int r1c0, r1c3, r2c0, r2c3, r0c1, r0c2, r3c1, r3c2;
+            bool ok = free_byte(b01, g00.x, -1.f, r1c0);
+            ok &= free_byte(b00, g01.x, 1.f, r1c3);
+            ok &= free_byte(b11, g10.x, -1.f, r2c0);
+            ok &= free_byte(b10, g11.x, 1.f, r2c3);
+            ok &= free_byte(b10, g00.y, -1.f, r0c1);
+            ok &= free_byte(b11, g01.y, -1.f, r0c2);
+            ok &= free_byte(b00, g10.y, 1.f, r3c1);
+            ok &= free_byte(b01, g11.y, 1.f, r3c2);
+            out.x = (r0c1 << 8) | (r0c2 << 16);
+            out.y = r1c0 | (b00 << 8) | (b01 << 16) | (r1c3 << 24);
+            out.z = r2c0 | (b10 << 8) | (b11 << 16) | (r2c3 << 24);
+            out.w = (r3c1 << 8) | (r3c2 << 16);
+            return ok;
+#else
+            const __half hx = __float2half_rn(g00.x), hy = __float2half_rn(g00.y);
+            // bitwise round trip (also rejects NaN and values that overflow to inf); every pixel vouches for its own gradient
+            const bool ok = __float_as_uint(__half2float(hx)) == __float_as_uint(g00.x) && __float_as_uint(__half2float(hy)) == __float_as_uint(g00.y);
+            out = row_pair(g00, g01, b00, b01);
+            return ok;
+#endif
+        }
+
+        // Keyframe texels (see LevelDev).  One thread per pixel; *inexact counts the pixels whose texel cannot hold the gradients.
         __global__ void pack_kernel(const unsigned char *__restrict__ I, const float2 *__restrict__ g, int H, int W,
-                                    uint4 *__restrict__ pair, unsigned int *__restrict__ quad, int *__restrict__ inexact)
+                                    PairTexel *__restrict__ pair, unsigned int *__restrict__ quad, int *__restrict__ inexact)
         {
             const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
             if (x >= W)
@@ -27,20 +78,8 @@ namespace mbavo
             const int i00 = y * W + x, i01 = y * W + x1, i10 = y1 * W + x, i11 = y1 * W + x1;
             const unsigned int b00 = I[i00], b01 = I[i01], b10 = I[i10], b11 = I[i11];
             quad[i00] = b00 | (b01 << 8) | (b10 << 16) | (b11 << 24);
-            const float2 g0 = g[i00], g1 = g[i01];
-            const __half hx0 = __float2half_rn(g0.x), hy0 = __float2half_rn(g0.y);
-            const __half hx1 = __float2half_rn(g1.x), hy1 = __float2half_rn(g1.y);
-            // bitwise round trip (also rejects NaN and values that overflow to inf)
-            if (__float_as_uint(__half2float(hx0)) != __float_as_uint(g0.x) ||
-                __float_as_uint(__half2float(hy0)) != __float_as_uint(g0.y))
+            if (!make_pair_texel(b00, b01, b10, b11, g[i00], g[i01], g[i10], g[i11], pair[i00]))
                 atomicAdd(inexact, 1);
-            const unsigned int hI0 = __half_as_ushort(__float2half_rn((float)b00)), hI1 = __half_as_ushort(__float2half_rn((float)b01));
-            uint4 t; // (gx gy)(x,y) | (gx gy)(x+1,y) | I(x,y) I(x+1,y) | 0
-            t.x = (unsigned int)__half_as_ushort(hx0) | ((unsigned int)__half_as_ushort(hy0) << 16);
-            t.y = (unsigned int)__half_as_ushort(hx1) | ((unsigned int)__half_as_ushort(hy1) << 16);
-            t.z = hI0 | (hI1 << 16);
-            t.w = 0u;
-            pair[i00] = t;
         }
 
         // ImagePyramid<T>::computePyramid, one level (src/core/measurements/ImagePyramid.h:76-95): T(0.25 * (float sum of the
@@ -66,7 +105,7 @@ namespace mbavo
             const unsigned char *c = I + (size_t)y * W + x;
             return make_float2(0.5f * ((float)c[1] - (float)c[-1]), 0.5f * ((float)c[W] - (float)c[-W]));
         }
-        __global__ void pack_image_kernel(const unsigned char *__restrict__ I, int H, int W, uint4 *__restrict__ pair,
+        __global__ void pack_image_kernel(const unsigned char *__restrict__ I, int H, int W, PairTexel *__restrict__ pair,
                                           unsigned int *__restrict__ quad, float2 *__restrict__ grad)
         {
             const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -81,13 +120,7 @@ namespace mbavo
             if (pair)
             {
                 quad[i00] = b00 | (b01 << 8) | (b10 << 16) | (b11 << 24);
-                uint4 t;
-                t.x = (unsigned int)__half_as_ushort(__float2half_rn(g0.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(g0.y)) << 16);
-                t.y = (unsigned int)__half_as_ushort(__float2half_rn(g1.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(g1.y)) << 16);
-                t.z = (unsigned int)__half_as_ushort(__float2half_rn((float)b00)) |
-                      ((unsigned int)__half_as_ushort(__float2half_rn((float)b01)) << 16);
-                t.w = 0u;
-                pair[i00] = t;
+                make_pair_texel(b00, b01, b10, b11, g0, g1, central_gradient(I, H, W, x, y1), central_gradient(I, H, W, x1, y1), pair[i00]);
             }
         }
         // one pyramid step of a new frame (PyrStepParams): the block finds its job, then runs the body of pack_image_kernel /
@@ -125,13 +158,7 @@ namespace mbavo
                 if (job.pair)
                 {
                     job.quad[i] = b00 | (b01 << 8) | (b10 << 16) | (b11 << 24);
-                    uint4 t;
-                    t.x = (unsigned int)__half_as_ushort(__float2half_rn(g0.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(g0.y)) << 16);
-                    t.y = (unsigned int)__half_as_ushort(__float2half_rn(g1.x)) | ((unsigned int)__half_as_ushort(__float2half_rn(g1.y)) << 16);
-                    t.z = (unsigned int)__half_as_ushort(__float2half_rn((float)b00)) |
-                          ((unsigned int)__half_as_ushort(__float2half_rn((float)b01)) << 16);
-                    t.w = 0u;
-                    job.pair[i] = t;
+                    make_pair_texel(b00, b01, b10, b11, g0, g1, central_gradient(I, H, W, x, y1), central_gradient(I, H, W, x1, y1), job.pair[i]);
                 }
             }
         }
@@ -161,7 +188,7 @@ namespace mbavo
         return cudaGetLastError();
     }
 
-    cudaError_t launch_pack_image_kernel(const unsigned char *I, int H, int W, uint4 *pair, unsigned int *quad, float *grad,
+    cudaError_t launch_pack_image_kernel(const unsigned char *I, int H, int W, PairTexel *pair, unsigned int *quad, float *grad,
                                          cudaStream_t stream)
     {
         const dim3 block(128, 1, 1), grid((W + 127) / 128, H, 1);
@@ -225,7 +252,7 @@ namespace mbavo
         return need + 16;
     }
 
-    cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, uint4 *pair, unsigned int *quad,
+    cudaError_t launch_pack_kernel(const unsigned char *I, const float *dIxy, int H, int W, PairTexel *pair, unsigned int *quad,
                                    int *inexact, cudaStream_t stream)
     {
         const dim3 block(128, 1, 1), grid((W + 127) / 128, H, 1);

@@ -195,7 +195,7 @@ namespace mbavo
                             I00 = byte_to_float<0>(tq), I01 = byte_to_float<1>(tq), I10 = byte_to_float<2>(tq), I11 = byte_to_float<3>(tq);
                             n_fallback += ok ? 1 : 0;
                         }
-                        sumI += w11 * I11 + w10 * I10 + w01 * I01 + w00 * I00;
+                        sumI += blend4(w00, w01, w10, w11, I00, I01, I10, I11);
                     }
                 }
                 const float icur = __int_as_float(r1.x);

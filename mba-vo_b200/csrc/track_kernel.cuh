@@ -20,9 +20,9 @@
 //      accumulated in 2x2 register tiles, one or more tiles per lane (fp32 over the 32 rows, fp64 across chunks).
 // Epilogue: deterministic block reduction -> per-block partials -> last block sums all partials in block order.
 //
-// Keyframe texels.  With LevelDev::ref_pair / ref_quad (built by pack_kernel below when the gradient image is exactly
-// representable in fp16) a Hessian-pass sample needs 2 x 128-bit loads and a cost-only sample 1 x 32-bit load instead
-// of 4 + 4 / 4 scattered loads; the values are bit-identical to ref_I / ref_dIxy.  Without them the same kernels
+// Keyframe texels.  With LevelDev::ref_pair / ref_quad (built by pack_kernel, track_common.cu, when the gradient image is
+// reproducible from byte differences, LevelDev) a Hessian-pass sample needs 1 x 128-bit load and a cost-only sample 1 x 32-bit
+// load instead of 4 + 4 / 4 scattered loads; the values are bit-identical to ref_I / ref_dIxy.  Without them the same kernels
 // gather ref_I / ref_dIxy directly (PACKED = false).
 //
 // Precision: per-sample arithmetic fp32 (the reference's bilinear taps/weights are fp32 too, compute_pixel_intensity.h:43-68),
@@ -92,6 +92,12 @@ namespace mbavo
         {
             return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540 | BYTE)) - 8388608.0f;
         }
+        // 2^23 + byte k of a packed word (exact): the bias cancels in a difference of two of them
+        template <int BYTE>
+        __device__ __forceinline__ float biased_byte(unsigned int v)
+        {
+            return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540 | BYTE));
+        }
         // packed fp32 pairs (FFMA2 / FMUL2 / FADD2); bc() broadcasts a scalar, which the instruction takes as a .F32 operand
         __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
         __device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
@@ -99,6 +105,12 @@ namespace mbavo
         __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
         __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 
+        // the bilinear blend (compute_pixel_intensity.h:40-68) with the contraction spelled out, so that every texel format and
+        // the direct gather round identically
+        __device__ __forceinline__ float blend4(float w00, float w01, float w10, float w11, float i00, float i01, float i10, float i11)
+        {
+            return fmaf(w00, i00, fmaf(w01, i01, fmaf(w10, i10, w11 * i11)));
+        }
         __device__ __forceinline__ float2 halves(unsigned int v)
         {
             return __half22float2(*reinterpret_cast<const __half2 *>(&v));
@@ -196,7 +208,7 @@ namespace mbavo
             float D, iD;              // plane depth, 1 / (D + 1e-8)
             float lox, hix, loy, hiy; // the reference coordinate (X + du, Y + dv) is inside [0, W-1] x [0, H-1] iff
                                       // lox <= du <= hix and loy <= dv <= hiy (all four are exact small integers)
-            float2 fxyiD;             // (fx, fy) / (D + 1e-8)
+            float2 fxyiD;             // (fx, fy) / (D + 1e-8); halved when the texels deliver doubled gradients
             int X, Y;
         };
 
@@ -267,18 +279,31 @@ namespace mbavo
             float2 gxy;
             if constexpr (PACKED && WITH_J)
             {
+#if MBAVO_TEXEL == 3
+                // patch texel: the 4 x 4 byte neighbourhood of the tap in one 128-bit load.  biased(b) = 2^23 + b exactly; the
+                // difference of two biased bytes is the DOUBLED central difference, exactly (PixelRegs::fxyiD carries the 1/2)
+                const uint4 t = __ldg(lv.ref_pair + idx);
+                (void)rowoff;
+                const float r0c1 = biased_byte<1>(t.x), r0c2 = biased_byte<2>(t.x);
+                const float r1c0 = biased_byte<0>(t.y), r1c1 = biased_byte<1>(t.y), r1c2 = biased_byte<2>(t.y), r1c3 = biased_byte<3>(t.y);
+                const float r2c0 = biased_byte<0>(t.z), r2c1 = biased_byte<1>(t.z), r2c2 = biased_byte<2>(t.z), r2c3 = biased_byte<3>(t.z);
+                const float r3c1 = biased_byte<1>(t.w), r3c2 = biased_byte<2>(t.w);
+                const float2 g00 = f2(r1c2 - r1c0, r2c1 - r0c1), g01 = f2(r1c3 - r1c1, r2c2 - r0c2);
+                const float2 g10 = f2(r2c2 - r2c0, r3c1 - r1c1), g11 = f2(r2c3 - r2c1, r3c2 - r1c2);
+                const float2 i0 = f2(r1c1 - 8388608.0f, r1c2 - 8388608.0f), i1 = f2(r2c1 - 8388608.0f, r2c2 - 8388608.0f);
+#else
                 const uint4 ta = __ldg(lv.ref_pair + idx);
                 const uint4 tb = __ldg(lv.ref_pair + idx + rowoff);
                 const float2 g00 = halves(ta.x), g01 = halves(ta.y), i0 = halves(ta.z); // (gx gy)(x,y) | (gx gy)(x+1,y) | I(x,y) I(x+1,y)
                 const float2 g10 = halves(tb.x), g11 = halves(tb.y), i1 = halves(tb.z);
-                sumI += w11 * i1.y + w10 * i1.x + w01 * i0.y + w00 * i0.x;
+#endif
+                sumI += blend4(w00, w01, w10, w11, i0.x, i0.y, i1.x, i1.y);
                 gxy = fma2(bc(w00), g00, fma2(bc(w01), g01, fma2(bc(w10), g10, mul2(bc(w11), g11))));
             }
             else if constexpr (PACKED)
             {
                 const unsigned int t = __ldg(lv.ref_quad + idx);
-                sumI += w11 * byte_to_float<3>(t) + w10 * byte_to_float<2>(t) + w01 * byte_to_float<1>(t) +
-                        w00 * byte_to_float<0>(t);
+                sumI += blend4(w00, w01, w10, w11, byte_to_float<0>(t), byte_to_float<1>(t), byte_to_float<2>(t), byte_to_float<3>(t));
             }
             else
             {
@@ -286,7 +311,7 @@ namespace mbavo
                 const int i00 = idx, i01 = idx + coloff, i10 = idx + rowoff, i11 = i10 + coloff;
                 const float I00 = u8_to_float(__ldg(lv.ref_I + i00)), I01 = u8_to_float(__ldg(lv.ref_I + i01));
                 const float I10 = u8_to_float(__ldg(lv.ref_I + i10)), I11 = u8_to_float(__ldg(lv.ref_I + i11));
-                sumI += w11 * I11 + w10 * I10 + w01 * I01 + w00 * I00;
+                sumI += blend4(w00, w01, w10, w11, I00, I01, I10, I11);
                 if constexpr (WITH_J)
                 {
                     const float2 g00 = __ldg(lv.ref_dIxy + i00), g01 = __ldg(lv.ref_dIxy + i01);
@@ -1276,7 +1301,7 @@ namespace mbavo
                         ps.X = r1.y, ps.Y = r1.z;
                         ps.lox = -(float)ps.X, ps.hix = (float)(lv.W - 1 - ps.X);
                         ps.loy = -(float)ps.Y, ps.hiy = (float)(lv.H - 1 - ps.Y);
-                        ps.fxyiD = mul2(fxy, bc(ps.iD));
+                        ps.fxyiD = mul2(fxy, bc((PACKED && MBAVO_TEXEL == 3) ? 0.5f * ps.iD : ps.iD)); // (patch texels: doubled gradients)
 
                         float sumI = 0.f;
                         float2 J[NJ][3];

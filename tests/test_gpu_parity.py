@@ -183,9 +183,10 @@ def test_tma_staged_cost_pass_variant(pkg, api, O, orc, synth):
 
 
 def test_keyframe_texels_and_direct_gather(pkg, api, O, orc, synth, monkeypatch):
-    """mbavo_set_level packs the keyframe into fp16 texels when every gradient value survives the fp16 round trip (always
-    for Gradient.h's central differences); the kernels then read bit-identical values through fewer, wider loads.  A
-    gradient image that fp16 cannot hold exactly makes the same kernels gather ref_I / ref_dIxy directly."""
+    """mbavo_set_level packs the keyframe into patch texels (the 4 x 4 byte neighbourhood of every pixel) when byte differences
+    reproduce every gradient value exactly (always for Gradient.h's central differences); the kernels then read bit-identical
+    values through one 128-bit load per sample.  A gradient image the texels cannot hold makes the same kernels gather
+    ref_I / ref_dIxy directly."""
     prob = synth.make_config("C1")
     with pkg.Context(api.limits_for(prob)) as ctx:
         api.upload_problem(ctx, prob)
@@ -201,7 +202,7 @@ def test_keyframe_texels_and_direct_gather(pkg, api, O, orc, synth, monkeypatch)
     monkeypatch.delenv("MBAVO_NO_TEXELS")
     assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     assert abs(a_cost - b_cost) <= 1e-7 * b_cost  # same tap values; only the FMA contraction of the blend may differ
-    # a gradient image fp16 cannot hold: scaled by 1/3
+    # a gradient image the texels cannot hold: scaled by 1/3
     prob.levels[0].ref_dIxy = (prob.levels[0].ref_dIxy / np.float32(3.0)).astype(np.float32)
     with pkg.Context(api.limits_for(prob)) as ctx:
         api.upload_problem(ctx, prob)
@@ -528,7 +529,7 @@ def test_sharded_evaluator_single_rank(pkg, api, synth):
         c, H, g = ev.evaluate(0, prob.knots_t, prob.knots_R, True)
         c2, _, _ = ev.evaluate(0, prob.knots_t, prob.knots_R, False)
     assert c == want[0] and np.array_equal(H, want[1]) and np.array_equal(g, want[2])
-    assert abs(c2 - c) <= 1e-6 * c  # the cost-only pass blends byte taps, the Hessian pass fp16 texels: same values, other FMA order
+    assert abs(c2 - c) <= 1e-6 * c  # the cost-only pass and the Hessian pass read the same tap values from different texels
 
 
 @pytest.mark.parametrize("world", [2, 3])
