@@ -448,7 +448,7 @@ namespace
             // give each warp fewer points and split the exposure samples over the lanes instead — 2 points x 8 pixels x 2
             // phases, or 1 point x 8 pixels x 4 phases — so that the same work spreads over 2x / 4x the warps at half / a quarter
             // of the per-warp latency.  (For levels that fill the GPU the unsplit form is faster: profiles/r1_history.md.)
-            const long long slots = (long long)ctx->num_sms * 20;
+            const long long slots = (long long)ctx->num_sms * track_warps(true, 3, true); // warp slots of the big block shape
             const long long pts = (long long)pl.P * pl.F;
             if (pts <= slots && pl.N >= 8)
                 pl.TP = 1, pl.PH = 4;

@@ -15,7 +15,10 @@ namespace mbavo
     // need more shared memory) — more resident warps and half as many per-block partials for the last-block reduction,
     // best once there are enough batches to occupy the SMs — and "small" = two blocks of 8 warps per SM, which spreads
     // the few batches of a coarse pyramid level over more SMs (profiles/r1_history.md).
-    __host__ __device__ constexpr int track_warps(bool with_j, int NK, bool big) { return (with_j && big) ? (NK <= 3 ? 20 : 16) : 8; }
+#ifndef MBAVO_BIG_WARPS
+#define MBAVO_BIG_WARPS 20 // warps of a "big" block for knot windows <= 3 (16: 128 registers per thread instead of 96)
+#endif
+    __host__ __device__ constexpr int track_warps(bool with_j, int NK, bool big) { return (with_j && big) ? (NK <= 3 ? MBAVO_BIG_WARPS : 16) : 8; }
 
     // One exposure sample (virtual pose) as the tracking kernel consumes it: fp32, 16-byte aligned records laid out so
     // that every operand PAIR of the kernel's packed FFMA2 arithmetic is an aligned pair of one 128-bit shared load.

@@ -58,6 +58,16 @@
 #ifndef MBAVO_MAGIC_FLOOR
 #define MBAVO_MAGIC_FLOOR 1
 #endif
+// Hessian pass with patch texels: sample loop software-pipelined by hand (sample_front / sample_back below)
+#ifndef MBAVO_PIPELINE
+#define MBAVO_PIPELINE 0
+#endif
+#ifndef MBAVO_PIPE_UNROLL
+#define MBAVO_PIPE_UNROLL 2
+#endif
+#ifndef MBAVO_PIPE_LEAN
+#define MBAVO_PIPE_LEAN 1 // 8 registers cross the split instead of 10 (m01 is recomputed from the re-read rotation groups)
+#endif
 
 namespace mbavo
 {
@@ -65,6 +75,7 @@ namespace mbavo
     {
         constexpr int kSampleUnroll = MBAVO_UNROLL;
         constexpr int kCostUnroll = MBAVO_UNROLL_C;
+        constexpr int kPipeUnroll = MBAVO_PIPE_UNROLL;
         constexpr int MBAVO_MAX_LEVELS_DEV = 8; // host_out layout of a sweep: 4 scalars per level, then the final knots
 
 #ifdef MBAVO_PROFILE_PHASES
@@ -355,6 +366,108 @@ namespace mbavo
             }
         }
 
+        // ---- Hessian-pass sample in two halves (MBAVO_PIPELINE, patch texels) ------------------------------------------------
+        // ptxas keeps the texel load of sample_step right in front of its first use (17 instructions), so a warp has ONE gather in
+        // flight and every L1 miss (31 % of the sectors) is paid in full: long-scoreboard is the largest stall of the sweep kernel
+        // (profiles/r2w_sweep_kernel_c3_patch_texel_ncu_raw.csv).  Split at the load, the sample loop is software-pipelined by
+        // hand: front(i + 1) — geometry, tap address, LDG — is issued BEFORE back(i) — texel decode, chain rule, accumulation —
+        // so the gather of the next sample flies under ~90 instructions of the current one.  Same arithmetic in the same order as
+        // sample_step (bit-identical sums); what crosses the split is 14 registers, and the two rotation groups of the record
+        // are read from shared memory a second time.
+        struct TapState
+        {
+            uint4 t;     // patch texel of the tap
+            float dx, dy; // fractional tap offsets (the bilinear weights are rebuilt from them)
+            float il, s; // 1 / lambda (0: invalid sample), (D - t_z) / lambda
+#if !MBAVO_PIPE_LEAN
+            float2 m01;  // ray + (R - I) ray, x and y (lean form: recomputed from the rotation groups the second half re-reads anyway)
+#endif
+        };
+        template <class Rec>
+        __device__ __forceinline__ TapState sample_front(const Rec rec, const PixelRegs &ps, const LevelDev &lv, float2 fxy)
+        {
+            const float4 g0 = rec.q(0), g1 = rec.q(1), g2 = rec.q(2);
+            const float2 A01 = f2(fmaf(g0.x, ps.rxy.x, fmaf(g0.y, ps.rxy.y, g1.z)), fmaf(g0.z, ps.rxy.x, fmaf(g0.w, ps.rxy.y, g1.w)));
+            const float A2 = fmaf(g1.x, ps.rxy.x, fmaf(g1.y, ps.rxy.y, g2.x));
+            const float2 m01 = add2(ps.rxy, A01);
+            const float m2 = 1.0f + A2;
+            const float il_raw = rcp_approx(m2);
+            const float tau = g2.y * ps.iD;
+            const float2 num = fma2(bc(-tau), m01, fma2(bc(-A2), ps.rxy, A01));
+            const float2 duv = mul2(fxy, fma2(num, bc(il_raw), mul2(f2(g2.z, g2.w), bc(ps.iD))));
+#if MBAVO_PIPE_LEAN >= 2
+            // fewer registers live across the loop: the upper bounds are rebuilt from the lower ones (exact small integers)
+            const bool ok = duv.x >= ps.lox && duv.x <= (float)(lv.W - 1) + ps.lox && duv.y >= ps.loy && duv.y <= (float)(lv.H - 1) + ps.loy;
+#else
+            const bool ok = duv.x >= ps.lox && duv.x <= ps.hix && duv.y >= ps.loy && duv.y <= ps.hiy;
+#endif
+            TapState st;
+            st.il = ok ? il_raw : 0.f;
+            int xo, yo;
+            const float xf = floor_to_int(duv.x, xo), yf = floor_to_int(duv.y, yo);
+            st.dx = duv.x - xf, st.dy = duv.y - yf; // exact
+            const int idx = ok ? (ps.Y + yo) * lv.W + ps.X + xo : 0;
+            st.t = __ldg(lv.ref_pair + idx);
+            st.s = (ps.D - g2.y) * st.il;
+#if !MBAVO_PIPE_LEAN
+            st.m01 = m01;
+#endif
+            return st;
+        }
+        template <int K, int NK, int OFF, class Rec>
+        __device__ __forceinline__ void sample_back(const Rec rec, const PixelRegs &ps, float2 fxy, const TapState &st, float &sumI, float2 (&J)[NK][3])
+        {
+            // an invalid sample (il == 0; a valid one has 1 / lambda > 0) runs with zero weights
+            const bool ok = st.il != 0.f;
+            const float dxdy = st.dx * st.dy;
+            const float w00 = ok ? 1.0f - st.dx - st.dy + dxdy : 0.f, w01 = ok ? st.dx - dxdy : 0.f, w10 = ok ? st.dy - dxdy : 0.f, w11 = ok ? dxdy : 0.f;
+            const uint4 t = st.t;
+            const float r0c1 = biased_byte<1>(t.x), r0c2 = biased_byte<2>(t.x);
+            const float r1c0 = biased_byte<0>(t.y), r1c1 = biased_byte<1>(t.y), r1c2 = biased_byte<2>(t.y), r1c3 = biased_byte<3>(t.y);
+            const float r2c0 = biased_byte<0>(t.z), r2c1 = biased_byte<1>(t.z), r2c2 = biased_byte<2>(t.z), r2c3 = biased_byte<3>(t.z);
+            const float r3c1 = biased_byte<1>(t.w), r3c2 = biased_byte<2>(t.w);
+            const float2 g00 = f2(r1c2 - r1c0, r2c1 - r0c1), g01 = f2(r1c3 - r1c1, r2c2 - r0c2);
+            const float2 g10 = f2(r2c2 - r2c0, r3c1 - r1c1), g11 = f2(r2c3 - r2c1, r3c2 - r1c2);
+            const float2 i0 = f2(r1c1 - 8388608.0f, r1c2 - 8388608.0f), i1 = f2(r2c1 - 8388608.0f, r2c2 - 8388608.0f);
+            sumI += blend4(w00, w01, w10, w11, i0.x, i0.y, i1.x, i1.y);
+            const float2 gxy = fma2(bc(w00), g00, fma2(bc(w01), g01, fma2(bc(w10), g10, mul2(bc(w11), g11))));
+            const float4 g0 = rec.q(0), g1 = rec.q(1);
+            const float rm22 = rec.p[8];
+#if MBAVO_PIPE_LEAN
+            const float2 m01 = add2(ps.rxy, f2(fmaf(g0.x, ps.rxy.x, fmaf(g0.y, ps.rxy.y, g1.z)), fmaf(g0.z, ps.rxy.x, fmaf(g0.w, ps.rxy.y, g1.w))));
+#else
+            const float2 m01 = st.m01;
+#endif
+#if MBAVO_PIPE_LEAN >= 2
+            const float2 gt = mul2(gxy, mul2(fxy, bc(0.5f * ps.iD))); // = PixelRegs::fxyiD, rebuilt
+#else
+            const float2 gt = mul2(gxy, ps.fxyiD);
+#endif
+            const float gtz = -(gt.x * m01.x + gt.y * m01.y) * st.il;
+            const float2 b01 = mul2(bc(st.s), fma2(bc(gt.x), f2(g0.x, g0.y), fma2(bc(gt.y), f2(g0.z, g0.w), fma2(bc(gtz), f2(g1.x, g1.y), gt))));
+            const float b2 = st.s * fmaf(g1.z, gt.x, fmaf(g1.w, gt.y, fmaf(rm22, gtz, gtz)));
+            const float v0 = fmaf(ps.rxy.y, b2, -b01.y);
+            const float v1 = fmaf(-ps.rxy.x, b2, b01.x);
+            const float v2 = fmaf(ps.rxy.x, b01.y, -ps.rxy.y * b01.x);
+            constexpr int NC = (10 * K + 3) / 4 * 4;
+            float c[NC];
+#pragma unroll
+            for (int q = 0; q < NC / 4; ++q)
+            {
+                const float4 v = rec.q(kRecGeom / 4 + q);
+                c[4 * q] = v.x, c[4 * q + 1] = v.y, c[4 * q + 2] = v.z, c[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+            {
+                const float *k = c + 10 * j;
+                J[OFF + j][0] = fma2(bc(k[0]), gt, J[OFF + j][0]);
+                J[OFF + j][1].x = fmaf(k[0], gtz, J[OFF + j][1].x);
+                J[OFF + j][1].y = fmaf(v0, k[1], fmaf(v1, k[2], fmaf(v2, k[3], J[OFF + j][1].y)));
+                J[OFF + j][2] = fma2(bc(v0), f2(k[4], k[5]), fma2(bc(v1), f2(k[6], k[7]), fma2(bc(v2), f2(k[8], k[9]), J[OFF + j][2])));
+            }
+        }
+
         // Samples of the segments OFF, OFF + 1, ... in time order, PH exposure phases (lane-dependent start, step PH)
         template <int K, int NK, bool PACKED, int OFF>
         struct SegmentLoop
@@ -365,9 +478,29 @@ namespace mbavo
             {
                 constexpr int REC = sample_rec_floats(K);
                 const int end = seg_end_s[OFF];
+                if constexpr (MBAVO_PIPELINE && PACKED && MBAVO_TEXEL == 3 && MBAVO_BRANCHLESS)
+                {
+                    if (i < end)
+                    {
+                        TapState cur = sample_front(SmemRec{samples_s + i * REC}, ps, lv, fxy);
+                        int n = i + PH;
+#pragma unroll kPipeUnroll
+                        for (; n < end; n += PH)
+                        {
+                            const TapState nxt = sample_front(SmemRec{samples_s + n * REC}, ps, lv, fxy);
+                            sample_back<K, NK, OFF>(SmemRec{samples_s + (n - PH) * REC}, ps, fxy, cur, sumI, J);
+                            cur = nxt;
+                        }
+                        sample_back<K, NK, OFF>(SmemRec{samples_s + (n - PH) * REC}, ps, fxy, cur, sumI, J);
+                        i = n;
+                    }
+                }
+                else
+                {
 #pragma unroll kSampleUnroll
                 for (; i < end; i += PH)
                     sample_step<K, NK, true, PACKED, OFF>(SmemRec{samples_s + i * REC}, ps, lv, fxy, sumI, J);
+                }
                 if constexpr (OFF + 1 <= NK - K)
                     SegmentLoop<K, NK, PACKED, (OFF + 1 <= NK - K ? OFF + 1 : OFF)>::run(samples_s, seg_end_s, i, PH, ps, lv, fxy,
                                                                                       sumI, J);
