@@ -596,7 +596,7 @@ namespace
         int rc = join_uploads(ctx);
         if (rc != MBAVO_OK)
             return rc;
-        rc = ensure_block_partials(ctx, (size_t)pl.grid.x * pl.grid.y * pl.E);
+        rc = ensure_block_partials(ctx, (size_t)pl.grid.x * pl.grid.y * (pl.E + 1)); // (rows padded to an even pitch)
         if (rc != MBAVO_OK)
             return rc;
         L.last_eval_frames = pl.F;
@@ -677,7 +677,7 @@ namespace
                     return 1;
                 const size_t need = sweep_kernel_smem_bytes(pl.K, plans[0].NK, pl.N, pl.S, pl.TP);
                 smem = need > smem ? need : smem;
-                partials = (size_t)ctx->num_sms * pl.E > partials ? (size_t)ctx->num_sms * pl.E : partials;
+                partials = (size_t)ctx->num_sms * (pl.E + 1) > partials ? (size_t)ctx->num_sms * (pl.E + 1) : partials; // (rows padded to an even pitch)
             }
         if (smem > 200 * 1024)
             return 1;
@@ -1841,7 +1841,7 @@ extern "C"
         const int wpb = track_warps(true, pl.NK, false);
         int want = (pl.batches_per_frame + wpb - 1) / wpb;
         pl.grid = dim3(want < 4 * ctx->num_sms ? want : 4 * ctx->num_sms, pl.F, 1);
-        rc = ensure_block_partials(ctx, (size_t)pl.grid.x * pl.grid.y * pl.E);
+        rc = ensure_block_partials(ctx, (size_t)pl.grid.x * pl.grid.y * (pl.E + 1)); // (rows padded to an even pitch)
         if (rc != MBAVO_OK)
             return rc;
         CUDA_TRY(launch_pose_kernel(pl.K, ctx->stage, pl.N * pl.F, 1, ctx->samples, ctx->mid, ctx->seg_end, s, nullptr, 0, false, kBufA,

@@ -395,17 +395,27 @@ namespace mbavo
         // dbg (nullable): fp64 values BEFORE the rounding to the fp32 record, per sample [t(3) q(4) wt(K) Theta(9K)] with stride
         // kPoseDebugStride doubles (mbavo_debug_dump)
         constexpr int kPoseDebugStride = 7 + 4 + 36;
-        template <int K>
-        __host__ __device__ inline void pose_one(const EvalStage *st, const double *knots_t, const double *knots_R, int g,
-                                                 int with_jacobian, float *samples, double *mid, int *seg_end, double *dbg = nullptr)
+        // normalised position of sample g inside its spline segment (compute_virtual_camera_poses.cu:33, SplineFunctor.h:13-19);
+        // depends on the frame times and the sample count only, not on the knots
+        __host__ __device__ inline double sample_u(const EvalStage *st, int g)
         {
             const int N = st->N;
             const int f = g / N, i = g % N;
-            // compute_virtual_camera_poses.cu:33
             const double t_mu = st->exp_time[f];
             const double ts = add_rn(add_rn(st->cap[f], -mul_rn(t_mu, 0.5)), div_rn(mul_rn((double)i, t_mu), (double)(N - 1) + 1e-8));
             const int idx = st->kmin + st->seg_off[g]; // host-computed with the same expression (SplineFunctor.h:13-19)
-            const double u = div_rn(add_rn(ts, -st->t0), st->dt) - (double)idx;
+            return div_rn(add_rn(ts, -st->t0), st->dt) - (double)idx;
+        }
+        // u_pre (nullable): sample_u of every sample, computed ahead of time (persistent sweep: off the path between two passes)
+        template <int K>
+        __host__ __device__ inline void pose_one(const EvalStage *st, const double *knots_t, const double *knots_R, int g,
+                                                 int with_jacobian, float *samples, double *mid, int *seg_end, double *dbg = nullptr,
+                                                 const double *u_pre = nullptr)
+        {
+            const int N = st->N;
+            const int f = g / N, i = g % N;
+            const int idx = st->kmin + st->seg_off[g];
+            const double u = u_pre ? u_pre[g] : sample_u(st, g);
 
             double tt[3], wt[K], Theta[K * 9];
             Q q;

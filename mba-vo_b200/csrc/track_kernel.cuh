@@ -65,6 +65,16 @@
 #ifndef MBAVO_PIPE_UNROLL
 #define MBAVO_PIPE_UNROLL 2
 #endif
+// last block: sum of the per-block partials with 128-bit loads, all of a thread's rows in flight at once (pass_finish)
+#ifndef MBAVO_WIDE_SUM
+#define MBAVO_WIDE_SUM 1
+#endif
+// persistent sweep, serial section of a Hessian pass: the knots the step starts from are fetched into shared memory under the
+// sum of the partials, the candidate reaches the pose records through shared memory (no L2 round trips), the sample positions
+// u are computed once at kernel entry, the candidate's quaternions take the power series of so3_exp_only
+#ifndef MBAVO_FAST_FINISH
+#define MBAVO_FAST_FINISH 1
+#endif
 #ifndef MBAVO_PIPE_LEAN
 #define MBAVO_PIPE_LEAN 1 // 8 registers cross the split instead of 10 (m01 is recomputed from the re-read rotation groups)
 #endif
@@ -729,8 +739,10 @@ namespace mbavo
 
         // PREFACTORED: gn_build_block + ldlt_factor_block have run (A holds the factor, *prefactored_ok its pivot verdict)
         template <int NK, bool PREFACTORED = false>
+        // knots_s (nullable, shared memory, 2 x 112 doubles): the knots the step starts from are read from its first half instead
+        // of GnState, and the candidate is ALSO left in its second half (persistent sweep: the pose records follow at once)
         __device__ void gn_solve_step(const double *__restrict__ v, const GnParams &gp, double *__restrict__ A, double *__restrict__ w,
-                                      unsigned long long *ts = nullptr, const int *prefactored_ok = nullptr)
+                                      unsigned long long *ts = nullptr, const int *prefactored_ok = nullptr, double *knots_s = nullptr)
         {
 #ifdef MBAVO_PROFILE_PHASES
 #define MBAVO_TS(k) do { if (ts && (threadIdx.x & 31) == 0) ts[k] = global_timer_ns(); } while (0)
@@ -878,16 +890,29 @@ namespace mbavo
                 st->step[3 * gp.kmin + e] = sv[e];
                 st->step[3 * n + 3 * gp.kmin + e] = sv[3 * NK + e];
             }
+            const double *cur_t = knots_s ? knots_s : st->cur_t, *cur_R = knots_s ? knots_s + 48 : st->cur_R;
             for (int e = lane; e < 3 * n; e += 32)
             {
                 const int a = e / 3 - gp.kmin;
-                st->cand_t[e] = st->cur_t[e] + ((a >= 0 && a < NK) ? sv[3 * a + e % 3] : 0.0);
+                const double ct = cur_t[e] + ((a >= 0 && a < NK) ? sv[3 * a + e % 3] : 0.0);
+                st->cand_t[e] = ct;
+                if (knots_s)
+                    knots_s[112 + e] = ct;
             }
             for (int j = lane; j < n; j += 32)
             {
                 const int a = j - gp.kmin;
-                const double *q = st->cur_R + 4 * j;
+                const double *q = cur_R + 4 * j;
                 double dq[4] = {0, 0, 0, 1};
+#if MBAVO_FAST_FINISH
+                if (a >= 0 && a < NK)
+                {
+                    // Sophus::SO3d::exp(w).unit_quaternion() (Spline.h:326): power series for the small steps of a tracker, closed
+                    // form otherwise (so3_exp_only, pose_device.cuh; equal to lm_driver.cpp so3_exp at the rounding level)
+                    const Q e = so3_exp_only(sv + 3 * NK + 3 * a);
+                    dq[0] = e.x, dq[1] = e.y, dq[2] = e.z, dq[3] = e.w;
+                }
+#else
                 if (a >= 0 && a < NK)
                 {
                     // Sophus::SO3d::exp(w).unit_quaternion() (Spline.h:326), as lm_driver.cpp so3_exp
@@ -910,11 +935,19 @@ namespace mbavo
                     }
                     dq[0] = fi * om[0], dq[1] = fi * om[1], dq[2] = fi * om[2], dq[3] = fr;
                 }
-                double *o = st->cand_R + 4 * j;
+#endif
+                double o[4];
                 o[0] = q[3] * dq[0] + q[0] * dq[3] + q[1] * dq[2] - q[2] * dq[1];
                 o[1] = q[3] * dq[1] + q[1] * dq[3] + q[2] * dq[0] - q[0] * dq[2];
                 o[2] = q[3] * dq[2] + q[2] * dq[3] + q[0] * dq[1] - q[1] * dq[0];
                 o[3] = q[3] * dq[3] - q[0] * dq[0] - q[1] * dq[1] - q[2] * dq[2];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    st->cand_R[4 * j + c] = o[c];
+                    if (knots_s)
+                        knots_s[112 + 48 + 4 * j + c] = o[c];
+                }
             }
             MBAVO_TS(14);
             if (lane == 0)
@@ -960,6 +993,8 @@ namespace mbavo
             unsigned int target;     // ctl->done value that makes the records of this pass valid
             const EvalStage *stage;  // frame times / segment table for the candidate's sample records
             unsigned long long *t_release; // where the pass's last block stamps the globaltimer when it releases the pass
+            const double *sample_u;  // shared memory: sample_u of every exposure sample (nullptr: computed on the spot)
+            double *knots_s;         // shared memory, 2 x 112 doubles: [t(48) | R(64)] of the knots a step starts from / of its candidate
         };
 
         // spin (thread 0) until ctl->done reaches target; false: aborted or timed out (the caller leaves the kernel)
@@ -1023,11 +1058,11 @@ namespace mbavo
         // same arithmetic as pose_kernel, one thread per (frame, sample)
         template <int K>
         __device__ __noinline__ void pose_records_block(const EvalStage *st, const double *kt, const double *kR, int with_jacobian,
-                                                        float *samples, double *mid, int *seg_end)
+                                                        float *samples, double *mid, int *seg_end, const double *u_pre = nullptr)
         {
             const int total = st->N * st->F;
             for (int g = threadIdx.x; g < total; g += blockDim.x)
-                pose_one<K>(st, kt, kR, g, with_jacobian, samples, mid, seg_end);
+                pose_one<K>(st, kt, kR, g, with_jacobian, samples, mid, seg_end, nullptr, u_pre);
         }
 
         // One pass over one pyramid level.  K: knots per segment, NK: knots in the window (NK - K + 1 segments touched),
@@ -1063,8 +1098,75 @@ namespace mbavo
             // sums the blocks b = part, part + GRP, ... (32 loads in flight), the GRP partial sums are combined by a fixed
             // xor-shuffle tree.  Deterministic: the order depends only on the grid size.
             __threadfence();
-            constexpr int GRP = E >= kThreads ? 1 : (kThreads / E >= 32 ? 32 : (kThreads / E >= 16 ? 16 : (kThreads / E >= 8 ? 8 : (kThreads / E >= 4 ? 4 : (kThreads / E >= 2 ? 2 : 1)))));
+            // (persistent Hessian pass) the knots the step will start from: the load travels under the sum of the partials
+            constexpr bool kKnotsInSmem = PERSIST && WITH_J && MBAVO_FAST_FINISH;
+            double knot_pre = 0.0;
+            if constexpr (kKnotsInSmem)
+            {
+                if (prm.gn.state && threadIdx.x < 112)
+                    knot_pre = __ldcg(prm.gn.state->cur_t + threadIdx.x); // cur_t (48) and cur_R (64) are adjacent in GnState
+            }
             double *fin_s = red_s; // this rank's vector, scaled by 1 / num_residuals (global when sharded)
+            constexpr int EP = (E + 1) & ~1; // row pitch of the per-block partials (even: rows are 16-byte aligned)
+            if constexpr (MBAVO_WIDE_SUM && E > 1)
+            {
+                // Hessian pass: a thread owns a PAIR of elements (one 128-bit load per block row) and one of PARTS interleaved subsets
+                // of the rows, with up to 24 loads in flight — the 148 x 190 partials of a C3 pass are ONE round trip to L2 per thread
+                // instead of four dependent ones; the PARTS partial sums are then combined in part order through shared memory.
+                // Deterministic: the order depends only on the grid size and the block shape.
+                constexpr int COLS = EP / 2;
+                constexpr int PARTS = kThreads / COLS >= 8 ? 8 : (kThreads / COLS >= 1 ? kThreads / COLS : 1);
+                constexpr int U = 24;
+                double *part_s = fin_s + EP; // [PARTS][EP]; aliases the solve scratch, which is touched only after this sum
+                for (int c0 = 0; c0 < COLS; c0 += kThreads / PARTS)
+                {
+                    const int col = c0 + threadIdx.x % (kThreads / PARTS), part = threadIdx.x / (kThreads / PARTS);
+                    if (col < COLS && part < PARTS)
+                    {
+                        const double2 *src = reinterpret_cast<const double2 *>(prm.block_partials) + col;
+                        double2 acc = make_double2(0.0, 0.0);
+                        int b = part;
+                        for (; b + (U - 1) * PARTS < num_blocks; b += U * PARTS)
+                        {
+                            double2 v[U];
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+                                v[u] = __ldcg(src + (size_t)(b + u * PARTS) * COLS);
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+                                acc.x += v[u].x, acc.y += v[u].y;
+                        }
+                        for (; b + 3 * PARTS < num_blocks; b += 4 * PARTS)
+                        {
+                            double2 v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                v[u] = __ldcg(src + (size_t)(b + u * PARTS) * COLS);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                acc.x += v[u].x, acc.y += v[u].y;
+                        }
+                        for (; b < num_blocks; b += PARTS)
+                        {
+                            const double2 v = __ldcg(src + (size_t)b * COLS);
+                            acc.x += v.x, acc.y += v.y;
+                        }
+                        part_s[part * EP + 2 * col] = acc.x, part_s[part * EP + 2 * col + 1] = acc.y;
+                    }
+                }
+                __syncthreads();
+                for (int e = threadIdx.x; e < E; e += kThreads)
+                {
+                    double s = part_s[e];
+#pragma unroll
+                    for (int q = 1; q < PARTS; ++q)
+                        s += part_s[q * EP + e];
+                    fin_s[e] = s * inv_num_residuals;
+                }
+            }
+            else
+            {
+            constexpr int GRP = E >= kThreads ? 1 : (kThreads / E >= 32 ? 32 : (kThreads / E >= 16 ? 16 : (kThreads / E >= 8 ? 8 : (kThreads / E >= 4 ? 4 : (kThreads / E >= 2 ? 2 : 1)))));
             for (int e0 = 0; e0 < E; e0 += kThreads / GRP)
             {
                 const int e = e0 + threadIdx.x / GRP, part = threadIdx.x % GRP;
@@ -1078,7 +1180,7 @@ namespace mbavo
                         double v[32];
 #pragma unroll
                         for (int u = 0; u < 32; ++u)
-                            v[u] = __ldcg(src + (size_t)(b + u * GRP) * E);
+                            v[u] = __ldcg(src + (size_t)(b + u * GRP) * EP);
 #pragma unroll
                         for (int u = 0; u < 32; ++u)
                             s += v[u];
@@ -1088,19 +1190,25 @@ namespace mbavo
                         double v[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u)
-                            v[u] = __ldcg(src + (size_t)(b + u * GRP) * E);
+                            v[u] = __ldcg(src + (size_t)(b + u * GRP) * EP);
 #pragma unroll
                         for (int u = 0; u < 8; ++u)
                             s += v[u];
                     }
                     for (; b < num_blocks; b += GRP)
-                        s += __ldcg(src + (size_t)b * E);
+                        s += __ldcg(src + (size_t)b * EP);
                 }
 #pragma unroll
                 for (int o = 1; o < GRP; o <<= 1)
                     s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (e < E && part == 0)
                     fin_s[e] = s * inv_num_residuals;
+            }
+            }
+            if constexpr (kKnotsInSmem)
+            {
+                if (threadIdx.x < 112)
+                    pa.knots_s[threadIdx.x] = knot_pre;
             }
             __syncthreads();
             MBAVO_STAMP(9);
@@ -1168,10 +1276,11 @@ namespace mbavo
                         __syncthreads();
                         if (warp == 0)
                             gn_solve_step<NK, true>(fin_s, gp, A, w, prm.phase_times ? prm.phase_times + 16 * (prm.trace_row & 63) : nullptr,
-                                                    &factor_ok_s);
+                                                    &factor_ok_s, kKnotsInSmem ? pa.knots_s : nullptr);
                     }
                     else if (warp == 0)
-                        gn_solve_step<NK>(fin_s, gp, A, w, prm.phase_times ? prm.phase_times + 16 * (prm.trace_row & 63) : nullptr);
+                        gn_solve_step<NK>(fin_s, gp, A, w, prm.phase_times ? prm.phase_times + 16 * (prm.trace_row & 63) : nullptr, nullptr,
+                                          kKnotsInSmem ? pa.knots_s : nullptr);
                     if constexpr (PERSIST)
                     {
                         // the candidate's sample records (what the stand-alone pose kernel computes between the two passes of a
@@ -1181,10 +1290,12 @@ namespace mbavo
                         const int cb = 1 - *reinterpret_cast<volatile int *>(&st->cur_buf);
                         // pose part only: all the cost pass needs.  The Jacobian part, which only a finer level standing on the
                         // committed candidate reads, is computed by the service block WHILE the cost pass runs (below).
-                        pose_records_block<K>(pa.stage, st->cand_t, st->cand_R, gridDim.x > 1 ? 0 : 1,
+                        pose_records_block<K>(pa.stage, kKnotsInSmem ? pa.knots_s + 112 : st->cand_t, kKnotsInSmem ? pa.knots_s + 160 : st->cand_R,
+                                              gridDim.x > 1 ? 0 : 1,
                                               const_cast<float *>(prm.samples) + (size_t)cb * prm.samples_stride,
                                               const_cast<double *>(prm.mid) + (size_t)cb * prm.mid_stride,
-                                              const_cast<int *>(prm.seg_end) + (size_t)cb * prm.seg_end_stride);
+                                              const_cast<int *>(prm.seg_end) + (size_t)cb * prm.seg_end_stride,
+                                              kKnotsInSmem ? pa.sample_u : nullptr);
                         MBAVO_STAMP(15);
                     }
                 }
@@ -1292,10 +1403,11 @@ namespace mbavo
         __device__ __forceinline__ bool track_pass(const TrackParams &prm, unsigned char *smem_raw, const PersistArgs pa)
         {
             using G = RowGeom<NK, WITH_J>;
-            constexpr int kWarpsPerBlock = WARPS, kThreads = kWarpsPerBlock * 32;
+            constexpr int kWarpsPerBlock = WARPS;
             constexpr int REC = sample_rec_floats(K);
             constexpr int NJ = WITH_J ? NK : 1;
             constexpr int D1 = G::D1, PITCH = G::PITCH, NT = G::NT, MT = G::MT, E = G::E;
+            constexpr int EPITCH = (E + 1) & ~1; // row pitch of the per-block partials (pass_finish reads them in 16-byte pairs)
 
             MBAVO_STAMP(0);
             if constexpr (!PERSIST)
@@ -1625,8 +1737,10 @@ namespace mbavo
 #pragma unroll
                 for (int w = 0; w < kWarpsPerBlock; ++w)
                     s += red_s[w * E + e];
-                prm.block_partials[(size_t)block_linear * E + e] = s;
+                prm.block_partials[(size_t)block_linear * EPITCH + e] = s;
             }
+            if (EPITCH != E && threadIdx.x == 0)
+                prm.block_partials[(size_t)block_linear * EPITCH + E] = 0.0; // padding element of the row (read as half of a pair)
             MBAVO_STAMP(7);
             __threadfence();
             __shared__ unsigned int ticket_s;
@@ -1683,15 +1797,23 @@ namespace mbavo
                     dst[e] = src[e];
             }
             __syncthreads();
+            // MBAVO_FAST_FINISH: position of every exposure sample inside its spline segment — fixed for the whole sweep, so the two
+            // divisions per sample leave the serial section between a Hessian pass and its cost pass — and room for the knots
+            __shared__ double sample_u_s[64];
+            __shared__ double knots_s[2 * 112];
+            const bool have_u = MBAVO_FAST_FINISH && stage_s.N * stage_s.F <= 64;
+            if (have_u && (int)threadIdx.x < stage_s.N * stage_s.F)
+                sample_u_s[threadIdx.x] = sample_u(&stage_s, threadIdx.x);
+            __syncthreads();
             cudaGridDependencySynchronize(); // the pose kernel's records (and the sweep state it initialised)
             if (blockIdx.x == 0 && threadIdx.x == 0)
                 sp.pass_times[0] = global_timer_ns();
             for (int li = 0; li < sp.n_levels; ++li)
             {
-                const PersistArgs ph{sp.ctl, sp.base + 2u * (unsigned int)li, &stage_s, sp.pass_times + 1 + 2 * li};
+                const PersistArgs ph{sp.ctl, sp.base + 2u * (unsigned int)li, &stage_s, sp.pass_times + 1 + 2 * li, have_u ? sample_u_s : nullptr, knots_s};
                 if (!track_pass<K, NK, true, PACKED, WARPS, true>(sp.pass[2 * li], smem_raw, ph))
                     return;
-                const PersistArgs pc{sp.ctl, sp.base + 2u * (unsigned int)li + 1u, &stage_s, sp.pass_times + 2 + 2 * li};
+                const PersistArgs pc{sp.ctl, sp.base + 2u * (unsigned int)li + 1u, &stage_s, sp.pass_times + 2 + 2 * li, have_u ? sample_u_s : nullptr, knots_s};
                 if (!track_pass<K, NK, false, PACKED, WARPS, true>(sp.pass[2 * li + 1], smem_raw, pc))
                     return;
             }
