@@ -233,10 +233,12 @@ class Context:
         self._check(self.lib.mbavo_set_points_pyramid(self._h, C.c_int(len(levels)), arr))
 
     def set_frame(self, n_levels: int, ref_I0: Optional[np.ndarray], cur_I0: Optional[Sequence[np.ndarray]], levels: Sequence,
-                  async_upload: bool = False):
+                  async_upload: bool = False, defer_points: bool = False):
         """mbavo_set_frame: level-0 keyframe + live images (either may be None) and the points of every level (synth.Level list,
         level 0 first) in one call.  async_upload: no synchronisation — the arrays must stay alive and unchanged until the next
-        blocking call on this context returns (they are kept referenced here)."""
+        blocking call on this context returns (they are kept referenced here).  defer_points (with async_upload,
+        MBAVO_UPLOAD_DEFER_POINTS): the point copies of all but the coarsest level are issued by the next call on the context —
+        a persistent gn_sweep issues them right behind the launch of its kernel."""
         arr = (_LevelPoints * len(levels))()
         for l, lv in enumerate(levels):
             arr[l] = _LevelPoints(MEM_HOST, lv.fx, lv.fy, lv.cx, lv.cy, lv.xy.ctypes.data, 16, 0, lv.z.ctypes.data, lv.xy.shape[0],
@@ -247,7 +249,49 @@ class Context:
         self._keep["frame"] = (ref_I0, cur_I0, levels, arr, cur)
         self._check(self.lib.mbavo_set_frame(self._h, C.c_int(n_levels), C.c_int(MEM_HOST),
                                              C.c_void_p(ref_I0.ctypes.data if ref_I0 is not None else 0), C.c_int(H0), C.c_int(W0), cur,
-                                             C.c_int(F), arr, C.c_int(1 if async_upload else 0)))
+                                             C.c_int(F), arr, C.c_int((1 if async_upload else 0) | (2 if async_upload and defer_points else 0))))
+
+    def prepare_frame(self, n_levels: int, ref_I0: Optional[np.ndarray], cur_I0: Optional[Sequence[np.ndarray]], levels: Sequence,
+                      async_upload: bool = False, defer_points: bool = False):
+        """set_frame with its argument marshalling done ONCE: returns a callable that only makes the C call (a caller that re-uses
+        its frame buffers — pinned staging memory — pays the ctypes set-up of ~20 structure fields per level once, not per frame;
+        a C / C++ caller of mbavo_set_frame never pays it).  The arrays are kept referenced by the returned callable."""
+        arr = (_LevelPoints * len(levels))()
+        for l, lv in enumerate(levels):
+            arr[l] = _LevelPoints(MEM_HOST, lv.fx, lv.fy, lv.cx, lv.cy, lv.xy.ctypes.data, 16, 0, lv.z.ctypes.data, lv.xy.shape[0],
+                                  lv.pattern.ctypes.data, lv.S, lv.N)
+        H0, W0 = ref_I0.shape if ref_I0 is not None else (0, 0)
+        F = len(cur_I0) if cur_I0 is not None else 0
+        cur = (C.c_void_p * F)(*[c.ctypes.data for c in cur_I0]) if F else None
+        keep = (ref_I0, cur_I0, levels, arr, cur)
+        args = (self._h, C.c_int(n_levels), C.c_int(MEM_HOST), C.c_void_p(ref_I0.ctypes.data if ref_I0 is not None else 0), C.c_int(H0),
+                C.c_int(W0), cur, C.c_int(F), arr, C.c_int((1 if async_upload else 0) | (2 if async_upload and defer_points else 0)))
+        fn, check = self.lib.mbavo_set_frame, self._check
+
+        def call(_keep=keep):
+            check(fn(*args))
+
+        return call
+
+    def prepare_gn_sweep(self, level_coarse: int, level_fine: int, k: int, t0: float, dt: float, knots_t, knots_R, huber_a: float,
+                         radius: float = 1e4, chain: bool = False, solver_type: int = SOLVER_SVD_JACOBI):
+        """gn_sweep with its argument marshalling done once: returns a callable that restores the starting knots into its own
+        buffers, makes the C call and returns (costs, knots_t, knots_R) — views of buffers that the next call overwrites."""
+        kt0 = np.array(knots_t, dtype=np.float64, order="C")
+        kR0 = np.array(knots_R, dtype=np.float64, order="C")
+        kt, kR = kt0.copy(), kR0.copy()
+        costs = np.zeros((level_coarse - level_fine + 1, 2))
+        args = (self._h, C.c_int(level_coarse), C.c_int(level_fine), C.c_int(1 if chain else 0), C.c_int(k), C.c_double(t0), C.c_double(dt),
+                C.c_int(kt.shape[0]), _dp(kt), _dp(kR), C.c_double(radius), C.c_double(huber_a), C.c_int(solver_type), _dp(costs))
+        fn, check, copyto = self.lib.mbavo_gn_sweep, self._check, np.copyto
+
+        def call():
+            copyto(kt, kt0)
+            copyto(kR, kR0)
+            check(fn(*args))
+            return costs, kt, kR
+
+        return call
 
     def set_live_images(self, level: int, cur_I: Sequence[np.ndarray]):
         """mbavo_set_live_images with host images: a new blurred frame for a level whose keyframe stays resident."""
