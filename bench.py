@@ -322,12 +322,9 @@ class Arm:
     def upload_all(self):
         """The frame from pinned host memory through the C-ABI: mbavo_set_frame (level-0 keyframe + live image on the context's
         stream, pyramid / gradients / texels built on the GPU, points of every level on a second stream), no synchronisation —
-        the pinned buffers live as long as this object and the sweep that follows is the blocking call.  The point copies of the
-        finer levels are issued behind the launch of that sweep (MBAVO_UPLOAD_DEFER_POINTS; MBAVO_BENCH_DEFER=0 issues them all
-        inside mbavo_set_frame, the form measured before)."""
+        the pinned buffers live as long as this object and the sweep that follows is the blocking call."""
         if self._upload is None:  # (argument marshalling once: the pinned buffers never move)
-            self._upload = self.ctx.prepare_frame(self.n_levels, self.pinned[0].ref_I, self.pinned[0].cur_I, self.pinned, async_upload=True,
-                                                  defer_points=os.environ.get("MBAVO_BENCH_DEFER", "1") == "1")
+            self._upload = self.ctx.prepare_frame(self.n_levels, self.pinned[0].ref_I, self.pinned[0].cur_I, self.pinned, async_upload=True)
         self._upload()
 
     def evaluate(self, level, kt, kR, with_h):

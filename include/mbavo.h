@@ -147,11 +147,6 @@ int mbavo_set_points_pyramid(mbavo_ctx *ctx, int n_levels, const mbavo_level_poi
  * buffers must then stay valid and unchanged until the next blocking call on this context (any evaluation, sweep,
  * LM or statistics entry point) has returned. */
 #define MBAVO_UPLOAD_ASYNC 1
-/* with MBAVO_UPLOAD_ASYNC: only the coarsest level's points are enqueued by the call itself; the copies of the other levels are
- * issued by the next call on this context — mbavo_gn_sweep issues them right behind the launch of its kernel, which waits level by
- * level for them, so the sweep starts about three driver calls per level earlier (the host's enqueue time, not the PCIe link, is what
- * a frame waits for).  Same contract for the host buffers as MBAVO_UPLOAD_ASYNC. */
-#define MBAVO_UPLOAD_DEFER_POINTS 2
 int mbavo_set_frame(mbavo_ctx *ctx, int n_levels, int mem, const unsigned char *ref_I0, int H0, int W0,
                     const unsigned char *const *cur_I0, int n_frames, const mbavo_level_points *points, int flags);
 

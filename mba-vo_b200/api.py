@@ -233,12 +233,10 @@ class Context:
         self._check(self.lib.mbavo_set_points_pyramid(self._h, C.c_int(len(levels)), arr))
 
     def set_frame(self, n_levels: int, ref_I0: Optional[np.ndarray], cur_I0: Optional[Sequence[np.ndarray]], levels: Sequence,
-                  async_upload: bool = False, defer_points: bool = False):
+                  async_upload: bool = False):
         """mbavo_set_frame: level-0 keyframe + live images (either may be None) and the points of every level (synth.Level list,
         level 0 first) in one call.  async_upload: no synchronisation — the arrays must stay alive and unchanged until the next
-        blocking call on this context returns (they are kept referenced here).  defer_points (with async_upload,
-        MBAVO_UPLOAD_DEFER_POINTS): the point copies of all but the coarsest level are issued by the next call on the context —
-        a persistent gn_sweep issues them right behind the launch of its kernel."""
+        blocking call on this context returns (they are kept referenced here)."""
         arr = (_LevelPoints * len(levels))()
         for l, lv in enumerate(levels):
             arr[l] = _LevelPoints(MEM_HOST, lv.fx, lv.fy, lv.cx, lv.cy, lv.xy.ctypes.data, 16, 0, lv.z.ctypes.data, lv.xy.shape[0],
@@ -249,10 +247,10 @@ class Context:
         self._keep["frame"] = (ref_I0, cur_I0, levels, arr, cur)
         self._check(self.lib.mbavo_set_frame(self._h, C.c_int(n_levels), C.c_int(MEM_HOST),
                                              C.c_void_p(ref_I0.ctypes.data if ref_I0 is not None else 0), C.c_int(H0), C.c_int(W0), cur,
-                                             C.c_int(F), arr, C.c_int((1 if async_upload else 0) | (2 if async_upload and defer_points else 0))))
+                                             C.c_int(F), arr, C.c_int(1 if async_upload else 0)))
 
     def prepare_frame(self, n_levels: int, ref_I0: Optional[np.ndarray], cur_I0: Optional[Sequence[np.ndarray]], levels: Sequence,
-                      async_upload: bool = False, defer_points: bool = False):
+                      async_upload: bool = False):
         """set_frame with its argument marshalling done ONCE: returns a callable that only makes the C call (a caller that re-uses
         its frame buffers — pinned staging memory — pays the ctypes set-up of ~20 structure fields per level once, not per frame;
         a C / C++ caller of mbavo_set_frame never pays it).  The arrays are kept referenced by the returned callable."""
@@ -265,7 +263,7 @@ class Context:
         cur = (C.c_void_p * F)(*[c.ctypes.data for c in cur_I0]) if F else None
         keep = (ref_I0, cur_I0, levels, arr, cur)
         args = (self._h, C.c_int(n_levels), C.c_int(MEM_HOST), C.c_void_p(ref_I0.ctypes.data if ref_I0 is not None else 0), C.c_int(H0),
-                C.c_int(W0), cur, C.c_int(F), arr, C.c_int((1 if async_upload else 0) | (2 if async_upload and defer_points else 0)))
+                C.c_int(W0), cur, C.c_int(F), arr, C.c_int(1 if async_upload else 0))
         fn, check = self.lib.mbavo_set_frame, self._check
 
         def call(_keep=keep):

@@ -112,10 +112,6 @@ struct mbavo_ctx
     bool join_pending = false;
     int upload_levels = 0;
     unsigned int upload_epoch = 0;
-    // MBAVO_UPLOAD_DEFER_POINTS: point copies of an asynchronous mbavo_set_frame that have not been enqueued yet (bit l = level l);
-    // flush_deferred_points issues them — right behind the launch of a persistent sweep, or from any entry point that joins the upload
-    unsigned int deferred_mask = 0;
-    mbavo_level_points deferred_pts[MBAVO_MAX_LEVELS] = {};
     unsigned int *ready_dev = nullptr;    // [MBAVO_MAX_LEVELS] epoch of the points resident in each level
     unsigned int *ready_src = nullptr;    // pinned: the value the flag copies carry
     int num_sms = 148;
@@ -515,17 +511,9 @@ namespace
         int buf_select = kBufA; // record buffer the pose kernel writes and the tracking kernel reads
     };
 
-    int flush_deferred_points(mbavo_ctx *ctx);
-
     // make the context's stream wait for the point copies of an asynchronous mbavo_set_frame (see mbavo_ctx::join_pending)
     int join_uploads(mbavo_ctx *ctx)
     {
-        if (ctx->deferred_mask)
-        {
-            const int rc = flush_deferred_points(ctx);
-            if (rc != MBAVO_OK)
-                return rc;
-        }
         if (ctx->join_pending)
         {
             CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
@@ -537,12 +525,6 @@ namespace
     // before buffers of the context are replaced: nothing may be in flight on either stream
     int quiesce(mbavo_ctx *ctx)
     {
-        if (ctx->deferred_mask)
-        {
-            const int rc = flush_deferred_points(ctx);
-            if (rc != MBAVO_OK)
-                return rc;
-        }
         if (ctx->join_pending)
         {
             CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
@@ -699,8 +681,19 @@ namespace
             }
         if (smem > 200 * 1024)
             return 1;
+        // is there an instantiation for this window, and does one block per SM fit?  (asked once per shape: with_h = 2 marks the entries
+        // of the sweep kernel in the occupancy cache)
         int occ = 0;
-        cudaError_t e = launch_sweep_kernel(plans[0].K, plans[0].NK, SweepParams{}, ctx->stage, ctx->num_sms, smem, s, false, &occ);
+        cudaError_t e = cudaSuccess;
+        for (const auto &c : ctx->occ_cache)
+            if (c.K == plans[0].K && c.NK == plans[0].NK && c.with_h == 2 && c.smem == smem)
+                occ = c.occ;
+        if (occ == 0)
+        {
+            e = launch_sweep_kernel(plans[0].K, plans[0].NK, SweepParams{}, ctx->stage, ctx->num_sms, smem, s, false, &occ);
+            if (e == cudaSuccess && occ >= 1)
+                ctx->occ_cache.push_back({plans[0].K, plans[0].NK, 2, 0, smem, occ});
+        }
         if (e == cudaErrorNotSupported || (e == cudaSuccess && occ < 1))
         {
             cudaGetLastError();
@@ -719,6 +712,11 @@ namespace
         int rc = ensure_block_partials(ctx, partials);
         if (rc != MBAVO_OK)
             return rc;
+        // records of the starting knots (with Jacobians) into buffer A; initialises the sweep state (cur knots, status, cur_buf = 0).
+        // Launched before the passes' parameters are put together: the kernel runs while the host does that.
+        ctx->launches += 2;
+        CUDA_TRY(launch_pose_kernel(plans[0].K, ctx->stage, plans[0].N, 1, ctx->samples, ctx->mid, ctx->seg_end, s, ctx->gn_state, 0, false, kBufA,
+                                    ctx->samples_stride, kMidDoubles * kMaxFrames, kMaxSegments * kMaxFrames));
         static thread_local SweepParams prm; // ~10 KB: kept off the stack of the caller's thread
         prm.n_levels = nlev, prm.ctl = ctx->sweep_ctl, prm.base = ctx->sweep_base, prm.pass_times = ctx->sweep_pass_times;
         ctx->sweep_last_levels = nlev;
@@ -755,10 +753,6 @@ namespace
                     seq_of_level[li] = ctx->seq;
             }
         }
-        // records of the starting knots (with Jacobians) into buffer A; initialises the sweep state (cur knots, status, cur_buf = 0)
-        ctx->launches += 2;
-        CUDA_TRY(launch_pose_kernel(plans[0].K, ctx->stage, plans[0].N, 1, ctx->samples, ctx->mid, ctx->seg_end, s, ctx->gn_state, 0, false, kBufA,
-                                    ctx->samples_stride, kMidDoubles * kMaxFrames, kMaxSegments * kMaxFrames));
         if (ctx->timing)
             CUDA_TRY(cudaEventRecord(ctx->ev0, s));
         e = launch_sweep_kernel(plans[0].K, plans[0].NK, prm, ctx->stage, ctx->num_sms, smem, s, ctx->use_pdl && !ctx->timing, nullptr);
@@ -767,13 +761,6 @@ namespace
         if (ctx->timing)
             CUDA_TRY(cudaEventRecord(ctx->ev1, s));
         ctx->sweep_base += 2u * (unsigned int)nlev;
-        // deferred point copies of the frame: the kernel is on its way and waits per level for the flag behind each of them
-        if (ctx->deferred_mask)
-        {
-            const int rcf = flush_deferred_points(ctx);
-            if (rcf != MBAVO_OK)
-                return rcf;
-        }
         // levels of the upload this sweep does not visit are not covered by its flag waits
         if (ctx->join_pending && !(level_coarse - nlev + 1 == 0 && level_coarse + 1 >= ctx->upload_levels))
             return join_uploads(ctx);
@@ -1279,10 +1266,8 @@ extern "C"
     // enqueue the uploads of one level's points on the context's stream (no synchronisation)
     // s: stream of the copies; s_flags: stream of the outlier-flag memset.  They differ in mbavo_set_frame: a memset is a KERNEL, and
     // a kernel on the copy stream could not start while a persistent sweep kernel that waits for this very upload holds every SM.
-    // part: 0 = everything; 1 = validation, buffers and the level's metadata only (the copies are deferred); 2 = only the copies of a
-    // level whose metadata part 1 has set (MBAVO_UPLOAD_DEFER_POINTS)
     static int enqueue_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d, cudaStream_t s, cudaStream_t s_flags = nullptr,
-                                    bool clear_flags = true, int part = 0)
+                                    bool clear_flags = true)
     {
         if (!s_flags)
             s_flags = s;
@@ -1322,22 +1307,15 @@ extern "C"
                 CUDA_TRY(cudaMalloc(&L.pts_z, sizeof(double) * P));
                 L.pts_cap = P;
             }
-            if (part != 1)
-            {
-                if (d->keypoint_xy_stride == 16 && d->keypoint_xy_offset == 0)
-                    CUDA_TRY(cudaMemcpyAsync(L.pts_xy, d->keypoint_xy, sizeof(double) * 2 * P, cudaMemcpyHostToDevice, s));
-                else // compact the records to packed double2 on the way in
-                    CUDA_TRY(cudaMemcpy2DAsync(L.pts_xy, 16, (const char *)d->keypoint_xy + d->keypoint_xy_offset, d->keypoint_xy_stride, 16, P,
-                                               cudaMemcpyHostToDevice, s));
-                CUDA_TRY(cudaMemcpyAsync(L.pts_z, d->keypoint_z, sizeof(double) * P, cudaMemcpyHostToDevice, s));
-            }
-            if (part == 2)
-                return MBAVO_OK;
+            if (d->keypoint_xy_stride == 16 && d->keypoint_xy_offset == 0)
+                CUDA_TRY(cudaMemcpyAsync(L.pts_xy, d->keypoint_xy, sizeof(double) * 2 * P, cudaMemcpyHostToDevice, s));
+            else // compact the records to packed double2 on the way in
+                CUDA_TRY(cudaMemcpy2DAsync(L.pts_xy, 16, (const char *)d->keypoint_xy + d->keypoint_xy_offset, d->keypoint_xy_stride, 16, P,
+                                           cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(L.pts_z, d->keypoint_z, sizeof(double) * P, cudaMemcpyHostToDevice, s));
             L.dev.xy = reinterpret_cast<const char *>(L.pts_xy), L.dev.xy_stride = 16, L.dev.xy_offset = 0;
             L.dev.z = L.pts_z;
         }
-        else if (part == 2)
-            return MBAVO_OK; // device-resident points: nothing to copy
         else
         {
             L.dev.xy = reinterpret_cast<const char *>(d->keypoint_xy);
@@ -1370,31 +1348,6 @@ extern "C"
         return MBAVO_OK;
     }
 
-
-    extern "C++"
-    {
-    namespace
-    {
-        // the point copies mbavo_set_frame deferred (MBAVO_UPLOAD_DEFER_POINTS), coarse level first, each followed by its ready flag
-        int flush_deferred_points(mbavo_ctx *ctx)
-        {
-            const unsigned int mask = ctx->deferred_mask;
-            ctx->deferred_mask = 0;
-            for (int l = MBAVO_MAX_LEVELS - 1; l >= 0; --l)
-            {
-                if (!(mask >> l & 1u))
-                    continue;
-                const int rc = enqueue_level_points(ctx, l, &ctx->deferred_pts[l], ctx->copy_stream, nullptr, false, 2);
-                if (rc != MBAVO_OK)
-                    return rc;
-                CUDA_TRY(cudaMemcpyAsync(ctx->ready_dev + l, ctx->ready_src, sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->copy_stream));
-            }
-            if (mask)
-                CUDA_TRY(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
-            return MBAVO_OK;
-        }
-    } // namespace
-    } // extern "C++"
 
     int mbavo_set_level_points(mbavo_ctx *ctx, int level, const mbavo_level_points *d)
     {
@@ -1479,23 +1432,8 @@ extern "C"
         // 2. the points, coarse level first (the order a sweep needs them), behind the images on the same stream; behind each level's
         //    points goes its ready flag
         *ctx->ready_src = ++ctx->upload_epoch;
-        // MBAVO_UPLOAD_DEFER_POINTS (with MBAVO_UPLOAD_ASYNC, host points): only the coarsest level's points are enqueued now; the
-        // other levels' copies follow from the next call on this context — a persistent sweep issues them right BEHIND its launch, so
-        // that its kernel starts ~3 API calls per level earlier and waits, level by level, for the flags behind the copies
-        const bool defer = (flags & MBAVO_UPLOAD_ASYNC) && (flags & MBAVO_UPLOAD_DEFER_POINTS);
-        ctx->deferred_mask = 0; // (copies a previous frame deferred and nobody asked for are dropped with it)
         for (int l = n_levels - 1; l >= 0 && rc == MBAVO_OK; --l)
         {
-            if (defer && l != n_levels - 1 && points[l].mem == MBAVO_MEM_HOST)
-            {
-                rc = enqueue_level_points(ctx, l, points + l, ctx->copy_stream, s, false, 1);
-                if (rc == MBAVO_OK)
-                {
-                    ctx->deferred_pts[l] = points[l];
-                    ctx->deferred_mask |= 1u << l;
-                }
-                continue;
-            }
             rc = enqueue_level_points(ctx, l, points + l, ctx->copy_stream, s, false); // (the flags are cleared by the pyramid steps below)
             if (rc == MBAVO_OK)
             {
@@ -1559,7 +1497,6 @@ extern "C"
             ctx->upload_levels = n_levels;
             return MBAVO_OK;
         }
-        ctx->deferred_mask = 0;
         cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(s);
         if (rc == MBAVO_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
             return fail(MBAVO_ECUDA, "upload failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));

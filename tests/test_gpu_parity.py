@@ -266,43 +266,41 @@ def test_device_built_pyramid(pkg, api, O, orc, synth, monkeypatch, no_texels):
         check_parity(O, gpu_eval(pkg, api, prob, 2, ctx=b), orc.evaluate(prob, 2))
 
 
-@pytest.mark.parametrize("async_upload", [False, True, "defer"])
+@pytest.mark.parametrize("async_upload", [False, True])
 def test_set_frame_single_call_upload(pkg, api, O, orc, synth, async_upload):
     """mbavo_set_frame (keyframe + live frame + points of every level in one call, point copies on a second stream under the
-    pyramid build, optionally without synchronisation, optionally with the fine levels' point copies deferred to the next call)
-    leaves exactly the state the three separate calls leave: bit-identical evaluations on every level; a later call with only a
-    new live frame keeps keyframe and points; a sweep launched straight behind a deferred upload (its kernel waits for the copies
-    the host issues behind the launch) equals the sweep on the synchronously uploaded frame."""
-    defer = async_upload == "defer"
-    async_upload = bool(async_upload)
+    pyramid build, optionally without synchronisation) leaves exactly the state the three separate calls leave: bit-identical
+    evaluations on every level; a later call with only a new live frame keeps keyframe and points; a sweep launched straight
+    behind an asynchronous upload (its kernel waits, level by level, for the point copies) equals the sweep on the synchronously
+    uploaded frame."""
     prob = synth.make_problem("frame", W=322, H=246, levels=4, P0=1500, N=8, n_knots=2, k=2, seed=6, margin=24)
     n = len(prob.levels)
     with pkg.Context(api.limits_for(prob)) as a, pkg.Context(api.limits_for(prob)) as b:
         api.upload_problem_pyramid(a, prob)
         b.set_frame_times(prob.cap, prob.exp)
         for _ in range(2):  # the second round re-uses every buffer
-            b.set_frame(n, prob.levels[0].ref_I, prob.levels[0].cur_I, prob.levels, async_upload=async_upload, defer_points=defer)
+            b.set_frame(n, prob.levels[0].ref_I, prob.levels[0].cur_I, prob.levels, async_upload=async_upload)
             for level in range(n):
                 ra, rb = gpu_eval(pkg, api, prob, level, ctx=a), gpu_eval(pkg, api, prob, level, ctx=b)
                 assert ra[0] == rb[0] and np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2]) and np.array_equal(ra[3], rb[3])
         other = [np.ascontiguousarray(np.roll(c, 2, axis=0)) for c in prob.levels[0].cur_I]
         a.set_live_pyramid(n, other)
-        b.set_frame(n, None, other, prob.levels, async_upload=async_upload, defer_points=defer)
+        b.set_frame(n, None, other, prob.levels, async_upload=async_upload)
         for level in (0, n - 1):
             ra, rb = gpu_eval(pkg, api, prob, level, ctx=a), gpu_eval(pkg, api, prob, level, ctx=b)
             assert ra[0] == rb[0] and np.array_equal(ra[1], rb[1])
         costs_a, kta, kRa = a.gn_sweep(n - 1, 0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, 1e4, chain=True)
         costs_b, ktb, kRb = b.gn_sweep(n - 1, 0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, 1e4, chain=True)
         assert np.array_equal(costs_a, costs_b) and np.array_equal(kta, ktb) and np.array_equal(kRa, kRb)
-        # the sweep as the FIRST call behind the upload: with deferred points its kernel is launched before the fine levels' copies
+        # the sweep as the FIRST call behind the upload
         for _ in range(3):
             before = b.persistent_sweeps()
-            b.set_frame(n, prob.levels[0].ref_I, other, prob.levels, async_upload=async_upload, defer_points=defer)
+            b.set_frame(n, prob.levels[0].ref_I, other, prob.levels, async_upload=async_upload)
             costs_b, ktb, kRb = b.gn_sweep(n - 1, 0, prob.k, prob.t0, prob.dt, prob.knots_t, prob.knots_R, prob.huber_a, 1e4, chain=True)
             assert b.persistent_sweeps() == before + 1
             assert np.array_equal(costs_a, costs_b) and np.array_equal(kta, ktb) and np.array_equal(kRa, kRb)
-        # ... and a deferred upload followed by something that is not a sweep (the entry point issues the copies itself)
-        b.set_frame(n, prob.levels[0].ref_I, other, prob.levels, async_upload=async_upload, defer_points=defer)
+        # ... and an upload followed by something that is not a sweep
+        b.set_frame(n, prob.levels[0].ref_I, other, prob.levels, async_upload=async_upload)
         ra, rb = gpu_eval(pkg, api, prob, 0, ctx=a), gpu_eval(pkg, api, prob, 0, ctx=b)
         assert ra[0] == rb[0] and np.array_equal(ra[1], rb[1])
 
