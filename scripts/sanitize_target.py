@@ -1,6 +1,6 @@
 """Target for compute-sanitizer (memcheck / racecheck / initcheck / synccheck): every kernel of the library on small inputs —
 pack, pyramid, pose, tracking (Hessian + cost, texel and direct-gather variants, ragged shapes, borders, k = 4, multi-segment),
-outlier and keyframe statistics, point selection, the per-frame driver, and a two-rank sharded evaluation on one device.   usage: python scripts/sanitize_target.py"""
+outlier and keyframe statistics, point selection, the per-frame driver, and a two-rank sharded evaluation on one device.   usage: python scripts/sanitize_target.py [--quick]"""
 import os
 import sys
 import threading
@@ -56,6 +56,12 @@ probs = [synth.make_config("tiny"),
          synth.make_problem("border", W=160, H=120, levels=1, P0=600, N=8, n_knots=2, k=2, seed=77, margin=0, motion_scale=2.0),
          synth.make_problem("cubic", W=160, H=120, levels=1, P0=200, N=8, n_knots=7, k=4, seed=9, margin=16, motion_scale=2.0),
          synth.make_problem("multi", W=160, H=120, levels=2, P0=300, N=16, n_knots=5, k=2, seed=11, margin=16)]
+if "--quick" in sys.argv:
+    # the persistent sweep (2- and 3-knot windows: odd and even lengths of the packed vector), the asynchronous frame upload, the
+    # last block's sum / solve / pose records — a few seconds per sanitizer tool
+    run(probs[0])
+    run(synth.make_problem("pyr16", W=160, H=128, levels=3, P0=300, N=8, n_knots=3, k=2, seed=6, margin=20), pyramid=True)
+    sys.exit(0)
 for p in probs:
     run(p)
 run(synth.make_problem("pyr", W=162, H=122, levels=3, P0=300, N=4, n_knots=2, k=2, seed=5, margin=20), pyramid=True)
