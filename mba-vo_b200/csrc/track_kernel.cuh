@@ -75,6 +75,14 @@
 #ifndef MBAVO_FAST_FINISH
 #define MBAVO_FAST_FINISH 1
 #endif
+// serial sections, third cut: pivot reciprocals seeded by rcp.approx.f64 (one MUFU instead of a float division between two
+// conversions), the record-buffer selector and the inputs of the cost pass's commit fetched under the sum of the partials
+#ifndef MBAVO_FINISH3
+#define MBAVO_FINISH3 1
+#endif
+#ifndef MBAVO_RCP64
+#define MBAVO_RCP64 MBAVO_FINISH3
+#endif
 #ifndef MBAVO_PIPE_LEAN
 #define MBAVO_PIPE_LEAN 1 // 8 registers cross the split instead of 10 (m01 is recomputed from the re-read rotation groups)
 #endif
@@ -542,7 +550,15 @@ namespace mbavo
         // level); an IEEE division costs about twice the latency and the factorisation is a chain of D of them
         __device__ __forceinline__ double rcp_newton(double d)
         {
+#if MBAVO_RCP64
+            // rcp.approx.ftz.f64 (MUFU.RCP64H): ~20 good bits from the upper word of d in ONE instruction; two Newton steps square
+            // the error twice (2^-20 -> 2^-40 -> 2^-80).  The float route costs two conversions, a range check and a float
+            // division on the chain of every pivot.  (d <= 0 / NaN: garbage in, flagged by the pivot test of the callers)
+            double r;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+#else
             double r = (double)(1.0f / (float)d);
+#endif
             r = fma(r, fma(-d, r, 1.0), r);
             r = fma(r, fma(-d, r, 1.0), r);
             return r;
@@ -1106,6 +1122,32 @@ namespace mbavo
                 if (prm.gn.state && threadIdx.x < 112)
                     knot_pre = __ldcg(prm.gn.state->cur_t + threadIdx.x); // cur_t (48) and cur_R (64) are adjacent in GnState
             }
+            // (third cut) the record-buffer selector for the candidate's records (Hessian pass); what the commit of a cost pass reads —
+            // the level's cost, model decrease and status, the knots and the candidate, four elements per lane of warp 0
+            constexpr bool kPre3 = PERSIST && MBAVO_FINISH3;
+            int cur_buf_pre = 0, status_pre = 0;
+            double cost_pre = 0.0, model_pre = 0.0, cand_pre[4] = {0.0, 0.0, 0.0, 0.0}, cur_pre[4] = {0.0, 0.0, 0.0, 0.0};
+            if constexpr (kPre3)
+            {
+                if (prm.gn.state)
+                {
+                    const GnState *st = prm.gn.state;
+                    if constexpr (WITH_J)
+                        cur_buf_pre = __ldcg(&st->cur_buf);
+                    else if (threadIdx.x < 32)
+                    {
+                        cost_pre = __ldcg(&st->cost), model_pre = __ldcg(&st->model), status_pre = __ldcg(&st->status);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                        {
+                            const int e = (int)threadIdx.x + 32 * u;
+                            const int idx = e < 3 * prm.gn.n_knots ? e : 48 + (e - 3 * prm.gn.n_knots);
+                            if (e < 7 * prm.gn.n_knots)
+                                cand_pre[u] = __ldcg(st->cand_t + idx), cur_pre[u] = __ldcg(st->cur_t + idx);
+                        }
+                    }
+                }
+            }
             double *fin_s = red_s; // this rank's vector, scaled by 1 / num_residuals (global when sharded)
             constexpr int EP = (E + 1) & ~1; // row pitch of the per-block partials (even: rows are 16-byte aligned)
             if constexpr (MBAVO_WIDE_SUM && E > 1)
@@ -1287,7 +1329,7 @@ namespace mbavo
                         // level when every pass is its own launch), with Jacobians: the next level may stand on them
                         __syncthreads();
                         // into the record buffer the sweep does NOT stand on (a sweep that never commits keeps cur_buf = 0)
-                        const int cb = 1 - *reinterpret_cast<volatile int *>(&st->cur_buf);
+                        const int cb = 1 - (kPre3 ? cur_buf_pre : *reinterpret_cast<volatile int *>(&st->cur_buf));
                         // pose part only: all the cost pass needs.  The Jacobian part, which only a finer level standing on the
                         // committed candidate reads, is computed by the service block WHILE the cost pass runs (below).
                         pose_records_block<K>(pa.stage, kKnotsInSmem ? pa.knots_s + 112 : st->cand_t, kKnotsInSmem ? pa.knots_s + 160 : st->cand_R,
@@ -1306,8 +1348,8 @@ namespace mbavo
                     // copied / published a lane per element.  Inside a persistent sweep the pass is released to the other blocks
                     // BEFORE anything is stored to host memory (a fence behind PCIe stores costs microseconds).
                     const int lane32 = threadIdx.x;
-                    const double cc = fin_s[0], cost0 = st->cost, model0 = st->model;
-                    const int status0 = st->status;
+                    const double cc = fin_s[0], cost0 = kPre3 ? cost_pre : st->cost, model0 = kPre3 ? model_pre : st->model;
+                    const int status0 = kPre3 ? status_pre : st->status;
                     const bool commit = gp.chain && status0 == 0 && cc < cost0;
                     const int nk7 = 7 * gp.n_knots; // cur_t (3n) and cur_R (4n) are adjacent in GnState
                     double *cur = st->cur_t;
@@ -1324,7 +1366,7 @@ namespace mbavo
                         keep[u] = 0.0;
                         if (e < nk7)
                         {
-                            keep[u] = commit ? cand[idx] : cur[idx];
+                            keep[u] = kPre3 ? (commit ? cand_pre[u] : cur_pre[u]) : (commit ? cand[idx] : cur[idx]);
                             if (commit)
                                 cur[idx] = keep[u];
                         }
