@@ -571,7 +571,9 @@ def run_own(args, pkg):
             "config": config_dict(args.workload, prob, world),
             "gn_iters_per_s": len(prob.levels) * args.steps / (ms_value * 1e-3),
             "e2e": {"value": e2e_value, "unit": "point-samples/s", "h2d_bytes_per_step": int(arm.h2d_step),
-                    "d2h_bytes_per_step": int(arm.d2h_step), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(arm.d2h_step), "ms_per_step": ms_e2e / args.steps,
+                    "calls": "per step: mbavo_set_frame(MBAVO_UPLOAD_ASYNC) from pinned host buffers + mbavo_gn_sweep (blocking: costs and "
+                             "knots back in host memory), C-ABI through ctypes with the argument structures marshalled once"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "parity": parity,
