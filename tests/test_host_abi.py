@@ -284,3 +284,29 @@ def test_header_is_plain_c_and_example_links(pkg, cuda_lib, tmp_path):
                         "-I" + os.path.join(root, "include"), "-L" + libdir, "-lmbavo_b200", "-lm", "-Wl,-rpath," + libdir,
                         "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_pose_only_series_host(tmp_path):
+    """The pose-only path of the persistent sweep (csrc/pose_device.cuh: so3_log_only / so3_exp_only / spline_pose_only — power
+    series in the squared norm instead of sqrt / atan / sincos — and sample_u) compiled as HOST code: against long-double closed
+    forms of Exp / Log over every branch (tiny, series, closed form), against the closed-form path spline_pose keeps (the
+    restatement of SplineFunctor.h:155-365) for linear and cubic segments, and against the plain expression of the sample
+    position (compute_virtual_camera_poses.cu:33).  All at the fp64 rounding level."""
+    import os
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(str(tmp_path), "pose_series")
+    r = subprocess.run([nvcc, "-O2", "-std=c++17", "-x", "cu", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-o", exe, os.path.join(root, "tests", "cpp", "pose_series_main.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    err = {k: float(v) for k, v in (line.split() for line in out.stdout.strip().splitlines())}
+    assert err["exp_only_vs_long_double"] <= 5e-16 and err["log_only_vs_long_double"] <= 1e-15 and err["log_exp_round_trip"] <= 1e-15, err
+    assert err["pose_only_vs_closed_form_t"] == 0.0 and err["pose_only_vs_closed_form_q"] <= 5e-16, err
+    assert err["sample_u_vs_plain"] <= 1e-12, err
